@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of quantum-mg on B200: Wilson stencil apply (Stencil2D::apply_M through
+apply_stencil_2D_M, /root/reference/stencil/stencil_2d.h:912,2571) on a synthetic U(1) lattice.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--L 8192] [--impl reference]
+
+A "step" is one out-of-place apply lhs = M rhs over the whole (per-rank) lattice.  `value` is the
+whole-job algorithmic GB/s (384 B/site for the stored-block Wilson operator) with all
+operands resident in HBM; `e2e` is the same apply through the C ABI with HOST source/result vectors
+(pinned host -> device copy of rhs and device -> host copy of lhs inside the timed region).
+N > 1: y-slab weak scaling, every rank owns an L x L slab of an L x (N L) lattice and exchanges
+one boundary row with its two ring neighbours per apply.
+
+--impl reference: the reference's own CPU implementation (oracle/_ref: the unmodified reference
+headers, single thread -- the reference has no threading) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "quantum-mg_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+BYTES_PER_SITE = 384.0       # 16 * (nc^2 * 5 + 2 nc), nc = 2
+METRIC = "wilson_stencil_GBps"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = max([float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()] or [0.0])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_apply(L, reps, warm=1):
+    """Time the reference's CPU apply (oracle/_ref) on an L x L Wilson lattice; returns (GB/s, seconds per apply)."""
+    import capi
+    import latutil
+    if not capi.have_ref():
+        raise RuntimeError("oracle/_ref/libqmg_ref.so missing: run __graft_entry__.build() in the build container")
+    be = capi.Backend("ref")
+    lat = be.lattice(L, L, 2)
+    op = lat.wilson(-0.075, latutil.synthetic_gauge(L, L))
+    rhs = latutil.gaussian_cv(lat.size_cv, 1)
+    sec = op.time_apply(rhs, 0, warm, reps) / reps
+    op.free()
+    return BYTES_PER_SITE * L * L / sec / 1e9, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L = args.cpu_L
+    times = []
+    for i in range(args.warmup + args.steps):
+        gbs, sec = cpu_reference_apply(L, args.cpu_reps, warm=1 if i == 0 else 0)
+        if i >= args.warmup:
+            times.append(sec)
+    sec = sum(times) / len(times)
+    val = BYTES_PER_SITE * L * L / sec / 1e9
+    sample = "Wilson apply on %dx%d (of the %dx%d workload), %d applies per step, g++ -O2 single thread" % (L, L, args.L, args.L, args.cpu_reps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3 * args.cpu_reps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "wilson_stencil_apply_%dx%d_u1" % (args.L, args.L), "sample_L": L},
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": 1, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_gpu(args):
+    import ctypes as C
+    import torch
+    import qmg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    qmg.init(local)
+    lib = qmg.lib()
+    L = args.L
+    X, Y = L, L
+    V = X * Y
+    n = 2 * V
+    beta = 6.0
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1337 + rank)
+    phases = torch.randn(2 * V, generator=gen, device="cuda", dtype=torch.float64) / beta ** 0.5
+    gauge = torch.polar(torch.ones_like(phases), phases)
+    del phases
+    clover, hopping = qmg.fill_wilson(X, Y, gauge)
+    del gauge
+    rhs = qmg.cvec(n)
+    qmg.check(lib.qmg_gaussian(qmg.ptr(rhs), C.c_long(n), C.c_uint64(7), C.c_uint64(rank), C.c_double(1.0)))
+    lhs = qmg.cvec(n)
+    halo_ym = halo_yp = None
+    row = X * 2  # complex elements in one boundary row (both parities)
+    if world > 1:
+        halo_ym, halo_yp = qmg.cvec(row), qmg.cvec(row)
+        send_lo, send_hi = qmg.cvec(row), qmg.cvec(row)
+    desc = qmg.stencil_desc(X, Y, 2, clover, hopping, shift=-0.075, halo_ym=halo_ym, halo_yp=halo_yp)
+    xh = X // 2
+    half = xh * Y * 2
+
+    def exchange():
+        # boundary rows y=0 and y=Y-1 of rhs (parity-major) to the ring neighbours
+        import torch.distributed as dist
+        send_lo[:xh * 2] = rhs[0:xh * 2]
+        send_lo[xh * 2:] = rhs[half:half + xh * 2]
+        send_hi[:xh * 2] = rhs[(Y - 1) * xh * 2:Y * xh * 2]
+        send_hi[xh * 2:] = rhs[half + (Y - 1) * xh * 2:half + Y * xh * 2]
+        up, down = (rank + 1) % world, (rank - 1) % world
+        ops = [dist.P2POp(dist.isend, send_hi, up), dist.P2POp(dist.irecv, halo_ym, down),
+               dist.P2POp(dist.isend, send_lo, down), dist.P2POp(dist.irecv, halo_yp, up)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+    def step():
+        if world > 1:
+            exchange()
+        qmg.stencil_apply(desc, lhs, rhs)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = qmg.kernel_launches()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    launches = qmg.kernel_launches() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    # the stencil kernel alone (events bracket exchange + kernel when N > 1; at N = 1 a step IS the kernel)
+    kern_ms = total_ms / args.steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = BYTES_PER_SITE * V * world / (ms_per_step * 1e-3) / 1e9
+
+    # end to end: host rhs -> device, apply, device lhs -> host, through the C ABI
+    e2e_steps = max(1, min(args.steps, 3))
+    hin, hout = C.c_void_p(), C.c_void_p()
+    qmg.check(lib.qmg_malloc_host(C.byref(hin), C.c_size_t(16 * n)))
+    qmg.check(lib.qmg_malloc_host(C.byref(hout), C.c_size_t(16 * n)))
+    qmg.check(lib.qmg_memcpy_d2h(hin, qmg.ptr(rhs), C.c_size_t(16 * n)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        qmg.check(lib.qmg_memcpy_h2d(qmg.ptr(rhs), hin, C.c_size_t(16 * n)))
+        step()
+        qmg.check(lib.qmg_memcpy_d2h(hout, qmg.ptr(lhs), C.c_size_t(16 * n)))
+    barrier()
+    e2e_sec = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([e2e_sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    e2e_val = BYTES_PER_SITE * V * world / e2e_sec / 1e9
+    lib.qmg_free_host(hin)
+    lib.qmg_free_host(hout)
+    clocks = sampler.summary() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = BYTES_PER_SITE * V / (kern_ms * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            try:
+                gbs, sec = cpu_reference_apply(args.cpu_L, args.cpu_reps)
+                cpu = {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "reference",
+                       "sample": "Wilson apply on %dx%d, %d applies, oracle/_ref (unmodified reference headers, g++ -O2, 1 thread; the reference is single-threaded)" % (args.cpu_L, args.cpu_L, args.cpu_reps),
+                       "ms_per_apply": sec * 1e3, "host_cores_available": os.cpu_count()}
+            except Exception as e:  # the baseline is a report, never the product path
+                cpu = {"value": None, "unit": "GB/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "wilson_stencil_apply_%dx%d_u1" % (X, Y * world), "per_gpu_lattice": [X, Y], "beta": beta, "mass": -0.075,
+                       "bytes_per_site": BYTES_PER_SITE, "l2": "operands (%.1f GB per apply) far larger than the 126 MB L2; no flush needed" % (BYTES_PER_SITE * V / 1e9),
+                       "parallelism": "y-slabs x%d, 1-row halo ring" % world},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0, "kernel": "qmg::stencil_kernel<2>"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--L", type=int, default=8192, help="per-GPU lattice is L x L")
+    ap.add_argument("--cpu-L", type=int, default=2048, dest="cpu_L")
+    ap.add_argument("--cpu-reps", type=int, default=5, dest="cpu_reps")
+    ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,180 @@
+/* qmg_b200.h -- C ABI of libqmg_b200.so: the sm_100a kernels behind quantum-mg's
+ * data-parallel hot path (2D stencil apply, transfer, BLAS-1 reductions).
+ *
+ * Every vector/matrix argument is a DEVICE pointer to interleaved
+ * complex<double> (re,im pairs, 16-byte aligned) in the reference's even-odd
+ * layouts (/root/reference/lattice/lattice.h:75-182):
+ *   site      i = (y + parity*Y)*X/2 + x/2,  parity = (x+y)%2  (all even, then all odd)
+ *   cv        i*nc + c
+ *   cm        (i*nc + c1)*nc + c2            (row major)
+ *   hopping   mu*size_cm + cm,  mu in {+x,+y,-x,-y}
+ *   gauge     mu*V + i,         mu in {x,y}  (nc = 1 lattice)
+ * All functions return 0 on success, non-zero on failure; qmg_last_error()
+ * gives the message.  One host thread drives one device; work is issued on
+ * the stream set by qmg_set_stream (default: the legacy default stream).
+ * There is no CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * Each entry names the reference interface it replaces (paths relative to
+ * /root/reference; "qlinalg" = the un-vendored quantum-linalg dependency,
+ * whose contract is fixed by the cited call site).
+ */
+#ifndef QMG_B200_H
+#define QMG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef double qmg_cplx; /* pointer arithmetic is in doubles: element k is at p[2k], p[2k+1] */
+
+/* ------------------------------------------------------------ runtime ---- */
+int qmg_init(int device);                 /* cudaSetDevice + scratch; idempotent */
+int qmg_finalize(void);
+int qmg_set_stream(void* cuda_stream);    /* cudaStream_t (e.g. torch's current stream) */
+void* qmg_get_stream(void);
+int qmg_sync(void);                       /* cudaStreamSynchronize on the active stream */
+const char* qmg_last_error(void);
+int qmg_device_count(void);
+int qmg_sm_count(void);
+long qmg_kernel_launches(void);           /* kernels launched by this library so far */
+
+/* allocate_vector / deallocate_vector (qlinalg; stencil/stencil_2d.h:220,299) */
+int qmg_malloc(void** dptr, size_t bytes);
+int qmg_free(void* dptr);
+int qmg_memcpy_h2d(void* dst, const void* src, size_t bytes);
+int qmg_memcpy_d2h(void* dst, const void* src, size_t bytes);
+int qmg_memcpy_d2d(void* dst, const void* src, size_t bytes);
+int qmg_malloc_host(void** hptr, size_t bytes);   /* pinned host staging */
+int qmg_free_host(void* hptr);
+
+/* ------------------------------------------------------------ stencil ---- */
+/* One stored stencil = one pointer set of Stencil2D (stencil/stencil_2d.h:148-210). */
+typedef struct qmg_stencil_desc
+{
+  int X, Y, nc;                /* Lattice2D dims and dof per site (lattice.h:29) */
+  const qmg_cplx* clover;      /* V*nc*nc or NULL (stencil_2d.h:155) */
+  const qmg_cplx* hopping;     /* 4*V*nc*nc or NULL (stencil_2d.h:158) */
+  double shift[2];             /* stencil_2d.h:170 */
+  double eo_shift[2];          /* stencil_2d.h:173: + on even, - on odd sites */
+  double dof_shift[2];         /* stencil_2d.h:177: + on top half of dof, - on bottom half */
+  /* y-slab sharding: rows y=-1 and y=Y of the INPUT vector, as received from
+   * the neighbouring ranks, each X*nc elements laid out (parity, x/2, c) with
+   * parity that of the halo row's sites; NULL = periodic wrap inside this
+   * lattice (cshift/cshift_2d.h:101,114 "Becomes MPI"). */
+  const qmg_cplx* halo_ym;     /* row below y=0   */
+  const qmg_cplx* halo_yp;     /* row above y=Y-1 */
+} qmg_stencil_desc;
+
+/* pieces bitmask (mirrors apply_M_clover/_eo/_oe/_shift, stencil_2d.h:694-909) */
+enum { QMG_APPLY_CLOVER = 1, QMG_APPLY_HOP_TO_EVEN = 2 /* apply_M_eo */, QMG_APPLY_HOP_TO_ODD = 4 /* apply_M_oe */,
+       QMG_APPLY_SHIFT = 8, QMG_APPLY_ALL = 15,
+       QMG_APPLY_IDENTITY_CLOVER = 16 /* rbjacobi: clover is 1 and is not read, stencil_2d.h:1685 */,
+       QMG_APPLY_ACCUMULATE = 32 /* lhs += ...  (Stencil2D::apply_M accumulates, stencil_2d.h:912) */,
+       QMG_APPLY_EVEN_ROWS_ONLY = 64 /* write only the even half of lhs */,
+       QMG_APPLY_ODD_ROWS_ONLY = 128 /* write only the odd half of lhs */ };
+/* dir_mask: bit mu selects hopping direction mu (stencil_dir_index, stencil_2d.h:25-31); 15 = all */
+
+/* lhs (=|+=) [clover + shifts] rhs + sum_mu hopping_mu(x) rhs(x+mu).
+ * Replaces Stencil2D::apply_M and its pieces (stencil_2d.h:666-936) and the
+ * zero_vector + apply of the apply_stencil_2D_* wrappers (:2571-2716). */
+int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs);
+
+/* Fused apply + reductions for the Krylov updates: out3 = { <lhs|rhs_dot>, |lhs|^2 } after lhs = A rhs.
+ * (MR step: alpha = <Ar|r>/<Ar|Ar>, stateful_multigrid.h:860 via qlinalg minres.)
+ * dot_with may be NULL (then only the norm is produced).  result: 3 doubles (re, im, norm2). */
+int qmg_stencil_apply_dot(const qmg_stencil_desc* st, int pieces, qmg_cplx* lhs, const qmg_cplx* rhs,
+                          const qmg_cplx* dot_with, double* result3);
+
+/* Operator fills from U(1) links (gauge: 2*V complex on the nc=1 lattice). */
+int qmg_fill_wilson(int X, int Y, double wilson_coeff, const qmg_cplx* gauge, qmg_cplx* clover, qmg_cplx* hopping);      /* operators/wilson.h:153-209 */
+int qmg_fill_staggered(int X, int Y, const qmg_cplx* gauge, qmg_cplx* hopping);                                         /* operators/staggered.h:50-72 */
+int qmg_fill_laplace(int X, int Y, const qmg_cplx* gauge, qmg_cplx* clover, qmg_cplx* hopping);                         /* operators/gaugedlaplace.h:45-68 */
+int qmg_fill_dwf(int X, int Y, int Ls, double wilson_coeff, double mass_re, double mass_im, const qmg_cplx* gauge, qmg_cplx* clover, qmg_cplx* hopping); /* operators/dwf.h:154-255 */
+
+/* Stencil-variant builders. */
+int qmg_build_dagger(int X, int Y, int nc, const qmg_cplx* clover, const qmg_cplx* hopping,
+                     qmg_cplx* dagger_clover, qmg_cplx* dagger_hopping);                       /* stencil_2d.h:1080-1139 */
+int qmg_build_rbjacobi(const qmg_stencil_desc* st, qmg_cplx* cinv, qmg_cplx* rbj_clover, qmg_cplx* rbj_hopping); /* stencil_2d.h:1452-1601 */
+
+/* cshift (cshift/cshift_2d.h:225): lhs(x) = rhs(x + dir) for the source parities in eo (1 even, 2 odd, 3 both). */
+int qmg_cshift(qmg_cplx* lhs, const qmg_cplx* rhs, int cdir, int eo, int dof_per_site, int X, int Y);
+
+/* ------------------------------------------------- batched site matrices -- */
+int qmg_cmat_xy(const qmg_cplx* M, const qmg_cplx* x, qmg_cplx* y, long nsites, int nc, int accumulate);  /* qlinalg cMATxy / cMATxpy (stencil_2d.h:675,1055) */
+int qmg_cmat_single_xy(const qmg_cplx* M, const qmg_cplx* x, qmg_cplx* y, long nsites, int nc);           /* qlinalg cMAT_single_xy (dwf.h:106) */
+int qmg_cmat_conjtrans(const qmg_cplx* in, qmg_cplx* out, long nsites, int nc);                           /* qlinalg cMATcopy_conjtrans_square (stencil_2d.h:1097); in == out allowed */
+int qmg_cmat_mul(const qmg_cplx* Xm, const qmg_cplx* Ym, qmg_cplx* Zm, long nsites, int nc);                /* qlinalg cMATxtMATyMATz_square (stencil_2d.h:1564) */
+int qmg_cmat_inverse(const qmg_cplx* M, qmg_cplx* Minv, long nsites, int nc);                             /* qlinalg cMATx_do_qr_square + cMATqr_do_xinv_square (stencil_2d.h:1536-1537) */
+int qmg_cmat_add_pattern(const double* pattern_host, int len, qmg_cplx* v, long nrepeat);                  /* qlinalg capx_pattern (stencil_2d.h:1526); pattern: len complex on HOST */
+
+/* ------------------------------------------------------------- BLAS-1 ---- */
+/* qlinalg blas/generic_vector.h; n counts complex elements; scalars are (re,im). */
+int qmg_zero(qmg_cplx* x, long n);                                                     /* zero_vector */
+int qmg_copy(qmg_cplx* dst, const qmg_cplx* src, long n);                              /* copy_vector */
+int qmg_constant(qmg_cplx* x, double re, double im, long n);                           /* constant_vector */
+int qmg_cax(double ar, double ai, qmg_cplx* x, long n);                                /* cax   x *= a */
+int qmg_caxy(double ar, double ai, const qmg_cplx* x, qmg_cplx* y, long n);            /* caxy  y = a x */
+int qmg_caxpy(double ar, double ai, const qmg_cplx* x, qmg_cplx* y, long n);           /* caxpy y += a x */
+int qmg_caxpby(double ar, double ai, const qmg_cplx* x, double br, double bi, qmg_cplx* y, long n);                         /* y = a x + b y */
+int qmg_caxpbyz(double ar, double ai, const qmg_cplx* x, double br, double bi, const qmg_cplx* y, qmg_cplx* z, long n);     /* z = a x + b y */
+int qmg_caxpbypz(double ar, double ai, const qmg_cplx* x, double br, double bi, const qmg_cplx* y, qmg_cplx* z, long n);    /* z += a x + b y */
+int qmg_cxty(const qmg_cplx* x, qmg_cplx* y, long n);                                  /* y *= x elementwise */
+int qmg_conj(qmg_cplx* x, long n);                                                     /* conj_vector */
+int qmg_cinvx(qmg_cplx* x, long n);                                                    /* cinvx */
+int qmg_polar(qmg_cplx* x, long n);                                                    /* polar: x = exp(i Re x) */
+/* strided flavours (the *_blas family, operators/wilson.h:79-125): element k at x[k*stride] */
+int qmg_zero_strided(qmg_cplx* x, long stride, long n);
+int qmg_constant_strided(qmg_cplx* x, long stride, double re, double im, long n);
+int qmg_caxy_strided(double ar, double ai, const qmg_cplx* x, long xs, qmg_cplx* y, long ys, long n, int accumulate); /* caxy_blas / caxpy_blas / copy_vector_blas */
+int qmg_cax_strided(double ar, double ai, qmg_cplx* x, long stride, long n);
+/* per-site dof pattern: out[s*nc+i] = scale[i]*in[s*nc+shuffle[i]] (caxy_shuffle_pattern, wilson.h:132); scale/shuffle on HOST */
+int qmg_shuffle_pattern(const double* scale_host, const int* shuffle_host, int nc, const qmg_cplx* in, qmg_cplx* out, long nsites);
+
+/* reductions: result written to HOST (synchronises the stream) */
+int qmg_dot(const qmg_cplx* x, const qmg_cplx* y, long n, double* result2);            /* dot: sum conj(x) y */
+int qmg_norm2sq(const qmg_cplx* x, long n, double* result);                            /* norm2sq */
+int qmg_diffnorm2sq(const qmg_cplx* x, const qmg_cplx* y, long n, double* result);     /* diffnorm2sq */
+int qmg_norminf(const qmg_cplx* x, long n, double* result);                            /* norminf */
+/* k dot products against one vector in one pass: result[2j..] = <xs[j]|y> (GCR orthogonalisation). xs: HOST array of k device pointers. */
+int qmg_multi_dot(const qmg_cplx* const* xs_host, int k, const qmg_cplx* y, long n, double* result2k);
+/* fused Krylov updates */
+/* x += a p ; r -= a q ; result = |r|^2   (MR / GCR step) */
+int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p, const qmg_cplx* q, qmg_cplx* x, qmg_cplx* r, long n, double* result);
+/* y += sum_j a_j xs[j]   (GCR: p_k += sum beta_i p_i) ; a: HOST 2k doubles; xs: HOST array of k device pointers */
+int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y, long n);
+/* gaussian fill, counter-based (Philox) so results do not depend on the launch shape */
+int qmg_gaussian(qmg_cplx* x, long n, uint64_t seed, uint64_t stream_id, double dev);
+
+/* ------------------------------------------------------------ transfer ---- */
+/* Regular non-overlapping blocking of a fine (Xf,Yf,ncf) lattice onto a coarse
+ * (Xc,Yc) lattice with ncc dof per coarse site (transfer/transfer.h:118-140).
+ * null vectors: HOST array of nvec DEVICE pointers, each a fine cv vector.
+ * nvec may be smaller than ncc (the 1-vector calls of block_orthonormalize,
+ * transfer.h:540-602, always address coarse dof 0.. of an ncc-strided vector). */
+typedef struct qmg_transfer_desc
+{
+  int Xf, Yf, ncf;
+  int Xc, Yc, ncc;
+} qmg_transfer_desc;
+int qmg_prolong(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec,
+                const qmg_cplx* coarse, qmg_cplx* fine);     /* fine += P coarse  (transfer.h:455-480) */
+int qmg_restrict(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec,
+                 const qmg_cplx* fine, qmg_cplx* coarse);    /* coarse += P^dag fine (transfer.h:487-511) */
+/* one pass of per-aggregate Gram-Schmidt, in place (transfer.h:514-607);
+ * cholesky: optional V_c*ncc*ncc output of the triangular factor (:555-594) or NULL */
+int qmg_block_orthonormalize(const qmg_transfer_desc* t, qmg_cplx* const* nullvecs_host, int nvec, qmg_cplx* cholesky);
+
+/* ------------------------------------------------------- coarse operator -- */
+/* Galerkin coarse stencil  R A P  of a nearest-neighbour fine stencil
+ * (operators/coarse.h:90-471): clover_c (V_c*ncc^2) and hopping_c (4*V_c*ncc^2), overwritten. */
+int qmg_coarse_build(const qmg_transfer_desc* t, const qmg_stencil_desc* fine,
+                     const qmg_cplx* const* prolong_vecs_host, const qmg_cplx* const* restrict_vecs_host,
+                     qmg_cplx* clover_c, qmg_cplx* hopping_c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QMG_B200_H */

@@ -1,0 +1,433 @@
+// BLAS-1 on device vectors of complex<double>: the quantum-linalg calls the
+// reference makes on the solve path, plus the fused
+// Krylov updates.  All kernels are HBM-bound streaming kernels: 16-byte
+// (double2) coalesced accesses, grid-stride loops sized to fill every SM,
+// warp-shuffle tree reductions finished deterministically by the last block.
+#include "qmg_common.cuh"
+
+namespace qmg {
+
+constexpr int kEwBlock = 256;
+
+template <class F>
+__global__ void __launch_bounds__(kEwBlock) ew_kernel(long n, F f)
+{
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
+template <int W, class F>
+__global__ void __launch_bounds__(kEwBlock) reduce_kernel(long n, F f, double* partials, unsigned int* counter, double* result)
+{
+  __shared__ double smem[(kEwBlock / 32) * W];
+  double acc[W];
+#pragma unroll
+  for (int w = 0; w < W; w++) acc[w] = 0.0;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, acc);
+  grid_reduce_finish<W>(acc, smem, partials, counter, result);
+}
+
+static inline int ew_grid(long n)
+{
+  long want = (n + kEwBlock - 1) / kEwBlock;
+  long cap = (long)rt().sm_count * 8;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+template <class F> static int launch_ew(long n, F f)
+{
+  if (n <= 0) return 0;
+  ew_kernel<<<ew_grid(n), kEwBlock, 0, rt().stream>>>(n, f);
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int W, class F> static int launch_reduce(long n, F f, double* host_out)
+{
+  Runtime& r = rt();
+  int grid = ew_grid(n > 0 ? n : 1);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  reduce_kernel<W><<<grid, kEwBlock, 0, r.stream>>>(n, f, r.d_partials, r.d_counter, r.d_result);
+  QMG_LAUNCH_CHECK();
+  return host_out ? fetch_result(host_out, W) : 0;
+}
+
+} // namespace qmg
+
+using namespace qmg;
+
+#define CD(p) reinterpret_cast<cd*>(p)
+#define CCD(p) reinterpret_cast<const cd*>(p)
+
+extern "C" {
+
+int qmg_zero(qmg_cplx* x, long n)
+{
+  QMG_REQUIRE_INIT();
+  if (n <= 0) return 0;
+  QMG_CUDA(cudaMemsetAsync(x, 0, sizeof(cd) * (size_t)n, rt().stream));
+  rt().launches++;
+  return 0;
+}
+
+int qmg_copy(qmg_cplx* dst, const qmg_cplx* src, long n)
+{
+  QMG_REQUIRE_INIT();
+  if (n <= 0 || dst == src) return 0;
+  QMG_CUDA(cudaMemcpyAsync(dst, src, sizeof(cd) * (size_t)n, cudaMemcpyDeviceToDevice, rt().stream));
+  rt().launches++;
+  return 0;
+}
+
+int qmg_constant(qmg_cplx* x_, double re, double im, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_); const cd v = cmake(re, im);
+  return launch_ew(n, [=] __device__(long i) { x[i] = v; });
+}
+
+int qmg_cax(double ar, double ai, qmg_cplx* x_, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_); const cd a = cmake(ar, ai);
+  return launch_ew(n, [=] __device__(long i) { x[i] = cmul(a, x[i]); });
+}
+
+int qmg_caxy(double ar, double ai, const qmg_cplx* x_, qmg_cplx* y_, long n)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); cd* y = CD(y_); const cd a = cmake(ar, ai);
+  return launch_ew(n, [=] __device__(long i) { y[i] = cmul(a, x[i]); });
+}
+
+int qmg_caxpy(double ar, double ai, const qmg_cplx* x_, qmg_cplx* y_, long n)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); cd* y = CD(y_); const cd a = cmake(ar, ai);
+  return launch_ew(n, [=] __device__(long i) { cd t = y[i]; cfma(t, a, x[i]); y[i] = t; });
+}
+
+int qmg_caxpby(double ar, double ai, const qmg_cplx* x_, double br, double bi, qmg_cplx* y_, long n)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); cd* y = CD(y_); const cd a = cmake(ar, ai), b = cmake(br, bi);
+  return launch_ew(n, [=] __device__(long i) { cd t = cmul(b, y[i]); cfma(t, a, x[i]); y[i] = t; });
+}
+
+int qmg_caxpbyz(double ar, double ai, const qmg_cplx* x_, double br, double bi, const qmg_cplx* y_, qmg_cplx* z_, long n)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); const cd* y = CCD(y_); cd* z = CD(z_); const cd a = cmake(ar, ai), b = cmake(br, bi);
+  return launch_ew(n, [=] __device__(long i) { cd t = cmul(b, y[i]); cfma(t, a, x[i]); z[i] = t; });
+}
+
+int qmg_caxpbypz(double ar, double ai, const qmg_cplx* x_, double br, double bi, const qmg_cplx* y_, qmg_cplx* z_, long n)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); const cd* y = CCD(y_); cd* z = CD(z_); const cd a = cmake(ar, ai), b = cmake(br, bi);
+  return launch_ew(n, [=] __device__(long i) { cd t = z[i]; cfma(t, b, y[i]); cfma(t, a, x[i]); z[i] = t; });
+}
+
+int qmg_cxty(const qmg_cplx* x_, qmg_cplx* y_, long n)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); cd* y = CD(y_);
+  return launch_ew(n, [=] __device__(long i) { y[i] = cmul(x[i], y[i]); });
+}
+
+int qmg_conj(qmg_cplx* x_, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_);
+  return launch_ew(n, [=] __device__(long i) { x[i] = cconj(x[i]); });
+}
+
+int qmg_cinvx(qmg_cplx* x_, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_);
+  return launch_ew(n, [=] __device__(long i) { x[i] = cdiv(cmake(1.0, 0.0), x[i]); });
+}
+
+int qmg_polar(qmg_cplx* x_, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_);
+  return launch_ew(n, [=] __device__(long i) { double s, c; sincos(x[i].x, &s, &c); x[i] = cmake(c, s); });
+}
+
+int qmg_zero_strided(qmg_cplx* x_, long stride, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_);
+  return launch_ew(n, [=] __device__(long i) { x[i * stride] = cmake(0.0, 0.0); });
+}
+
+int qmg_constant_strided(qmg_cplx* x_, long stride, double re, double im, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_); const cd v = cmake(re, im);
+  return launch_ew(n, [=] __device__(long i) { x[i * stride] = v; });
+}
+
+int qmg_caxy_strided(double ar, double ai, const qmg_cplx* x_, long xs, qmg_cplx* y_, long ys, long n, int accumulate)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); cd* y = CD(y_); const cd a = cmake(ar, ai);
+  if (accumulate)
+    return launch_ew(n, [=] __device__(long i) { cd t = y[i * ys]; cfma(t, a, x[i * xs]); y[i * ys] = t; });
+  return launch_ew(n, [=] __device__(long i) { y[i * ys] = cmul(a, x[i * xs]); });
+}
+
+int qmg_cax_strided(double ar, double ai, qmg_cplx* x_, long stride, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_); const cd a = cmake(ar, ai);
+  return launch_ew(n, [=] __device__(long i) { x[i * stride] = cmul(a, x[i * stride]); });
+}
+
+struct ShufflePattern { double scale[64]; int shuffle[64]; };
+
+int qmg_shuffle_pattern(const double* scale_host, const int* shuffle_host, int nc, const qmg_cplx* in_, qmg_cplx* out_, long nsites)
+{
+  QMG_REQUIRE_INIT();
+  if (nc > 64) return fail_msg("qmg_shuffle_pattern: nc > 64 unsupported");
+  ShufflePattern pat;
+  for (int i = 0; i < nc; i++) { pat.scale[i] = scale_host[i]; pat.shuffle[i] = shuffle_host[i]; }
+  const cd* in = CCD(in_); cd* out = CD(out_);
+  return launch_ew(nsites * nc, [=] __device__(long e) {
+    long s = e / nc; int i = (int)(e - s * nc);
+    cd v = in[s * nc + pat.shuffle[i]];
+    out[e] = cmake(pat.scale[i] * v.x, pat.scale[i] * v.y);
+  });
+}
+
+// ---------------------------------------------------------------- reductions --
+
+int qmg_dot(const qmg_cplx* x_, const qmg_cplx* y_, long n, double* result2)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); const cd* y = CCD(y_);
+  return launch_reduce<2>(n, [=] __device__(long i, double (&acc)[2]) {
+    cd a = x[i], b = y[i];
+    acc[0] += a.x * b.x + a.y * b.y;
+    acc[1] += a.x * b.y - a.y * b.x;
+  }, result2);
+}
+
+int qmg_norm2sq(const qmg_cplx* x_, long n, double* result)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_);
+  return launch_reduce<1>(n, [=] __device__(long i, double (&acc)[1]) {
+    cd a = x[i];
+    acc[0] += a.x * a.x + a.y * a.y;
+  }, result);
+}
+
+int qmg_diffnorm2sq(const qmg_cplx* x_, const qmg_cplx* y_, long n, double* result)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); const cd* y = CCD(y_);
+  return launch_reduce<1>(n, [=] __device__(long i, double (&acc)[1]) {
+    cd d = csub(x[i], y[i]);
+    acc[0] += d.x * d.x + d.y * d.y;
+  }, result);
+}
+
+} // extern "C"
+
+namespace qmg {
+// max-reduction for norminf: reuse the sum machinery on a monotone transform is
+// not exact, so do a dedicated two-stage max.
+__global__ void __launch_bounds__(kEwBlock) norminf_kernel(const cd* x, long n, double* partials, unsigned int* counter, double* result)
+{
+  __shared__ double smem[kEwBlock / 32];
+  __shared__ bool is_last;
+  double m = 0.0;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    cd a = x[i];
+    m = fmax(m, hypot(a.x, a.y));
+  }
+  auto block_max = [&](double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, shfl_down_d(v, o));
+    if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+      v = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) v = fmax(v, shfl_down_d(v, o));
+    }
+    __syncthreads();
+    return v;
+  };
+  m = block_max(m);
+  if (threadIdx.x == 0)
+  {
+    partials[blockIdx.x] = m;
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last)
+  {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) v = fmax(v, __ldcg(&partials[b]));
+    v = block_max(v);
+    if (threadIdx.x == 0) { result[0] = v; *counter = 0u; }
+  }
+}
+} // namespace qmg
+
+extern "C" {
+
+int qmg_norminf(const qmg_cplx* x_, long n, double* result)
+{
+  QMG_REQUIRE_INIT();
+  Runtime& r = rt();
+  int grid = ew_grid(n > 0 ? n : 1);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  norminf_kernel<<<grid, kEwBlock, 0, r.stream>>>(CCD(x_), n, r.d_partials, r.d_counter, r.d_result);
+  QMG_LAUNCH_CHECK();
+  return fetch_result(result, 1);
+}
+
+} // extern "C"
+
+namespace qmg {
+
+template <int K> struct PtrPack { const cd* p[K]; };
+template <int K> struct CoefPack { cd a[K]; };
+
+template <int K>
+static int multi_dot_pass(const qmg_cplx* const* xs, int k, const cd* y, long n, double* out2k)
+{
+  PtrPack<K> pk;
+  for (int j = 0; j < K; j++) pk.p[j] = CCD(xs[j < k ? j : 0]);
+  double tmp[2 * K];
+  int rc = launch_reduce<2 * K>(n, [=] __device__(long i, double (&acc)[2 * K]) {
+    cd b = y[i];
+#pragma unroll
+    for (int j = 0; j < K; j++)
+    {
+      cd a = pk.p[j][i];
+      acc[2 * j] += a.x * b.x + a.y * b.y;
+      acc[2 * j + 1] += a.x * b.y - a.y * b.x;
+    }
+  }, tmp);
+  if (rc) return rc;
+  for (int j = 0; j < k; j++) { out2k[2 * j] = tmp[2 * j]; out2k[2 * j + 1] = tmp[2 * j + 1]; }
+  return 0;
+}
+
+template <int K>
+static int multi_axpy_pass(const double* a_host, const qmg_cplx* const* xs, int k, cd* y, long n)
+{
+  PtrPack<K> pk; CoefPack<K> ck;
+  for (int j = 0; j < K; j++)
+  {
+    pk.p[j] = CCD(xs[j < k ? j : 0]);
+    ck.a[j] = j < k ? cmake(a_host[2 * j], a_host[2 * j + 1]) : cmake(0.0, 0.0);
+  }
+  return launch_ew(n, [=] __device__(long i) {
+    cd t = y[i];
+#pragma unroll
+    for (int j = 0; j < K; j++) cfma(t, ck.a[j], pk.p[j][i]);
+    y[i] = t;
+  });
+}
+
+} // namespace qmg
+
+extern "C" {
+
+int qmg_multi_dot(const qmg_cplx* const* xs_host, int k, const qmg_cplx* y_, long n, double* result2k)
+{
+  QMG_REQUIRE_INIT();
+  const cd* y = CCD(y_);
+  int done = 0;
+  while (done < k)
+  {
+    int left = k - done, rc;
+    if (left >= 8) { rc = multi_dot_pass<8>(xs_host + done, 8, y, n, result2k + 2 * done); done += 8; }
+    else if (left > 4) { rc = multi_dot_pass<8>(xs_host + done, left, y, n, result2k + 2 * done); done += left; }
+    else if (left > 2) { rc = multi_dot_pass<4>(xs_host + done, left, y, n, result2k + 2 * done); done += left; }
+    else if (left == 2) { rc = multi_dot_pass<2>(xs_host + done, 2, y, n, result2k + 2 * done); done += 2; }
+    else { rc = multi_dot_pass<1>(xs_host + done, 1, y, n, result2k + 2 * done); done += 1; }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y_, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* y = CD(y_);
+  int done = 0;
+  while (done < k)
+  {
+    int left = k - done, rc, take;
+    if (left >= 8) { take = 8; rc = multi_axpy_pass<8>(a_host + 2 * done, xs_host + done, take, y, n); }
+    else if (left > 4) { take = left; rc = multi_axpy_pass<8>(a_host + 2 * done, xs_host + done, take, y, n); }
+    else if (left > 2) { take = left; rc = multi_axpy_pass<4>(a_host + 2 * done, xs_host + done, take, y, n); }
+    else if (left == 2) { take = 2; rc = multi_axpy_pass<2>(a_host + 2 * done, xs_host + done, take, y, n); }
+    else { take = 1; rc = multi_axpy_pass<1>(a_host + 2 * done, xs_host + done, take, y, n); }
+    if (rc) return rc;
+    done += take;
+  }
+  return 0;
+}
+
+int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p_, const qmg_cplx* q_, qmg_cplx* x_, qmg_cplx* r_, long n, double* result)
+{
+  QMG_REQUIRE_INIT();
+  const cd* p = CCD(p_); const cd* q = CCD(q_); cd* x = CD(x_); cd* r = CD(r_);
+  const cd a = cmake(ar, ai), ma = cmake(-ar, -ai);
+  return launch_reduce<1>(n, [=] __device__(long i, double (&acc)[1]) {
+    cd xi = x[i]; cfma(xi, a, p[i]); x[i] = xi;
+    cd ri = r[i]; cfma(ri, ma, q[i]); r[i] = ri;
+    acc[0] += ri.x * ri.x + ri.y * ri.y;
+  }, result);
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------ gaussian --
+namespace qmg {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+  for (int round = 0; round < 10; round++)
+  {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+} // namespace qmg
+
+extern "C" int qmg_gaussian(qmg_cplx* x_, long n, uint64_t seed, uint64_t stream_id, double dev)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_);
+  return launch_ew(n, [=] __device__(long i) {
+    uint32_t c[4] = { (uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32) };
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    // two 53-bit-ish uniforms in (0,1): 32 random bits each, centred
+    const double u1 = ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
+    const double u2 = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
+    const double rad = dev * sqrt(-2.0 * log(u1));
+    double s, co;
+    sincospi(2.0 * u2, &s, &co);
+    x[i] = cmake(rad * co, rad * s);
+  });
+}

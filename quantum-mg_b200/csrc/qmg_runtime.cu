@@ -1,0 +1,143 @@
+// Runtime plumbing of libqmg_b200: device selection, stream, memory, error text.
+#include "qmg_common.cuh"
+#include <string.h>
+
+namespace qmg {
+
+Runtime& rt() { static Runtime r; return r; }
+
+int fail(const char* what, cudaError_t e, const char* file, int line)
+{
+  char buf[512];
+  snprintf(buf, sizeof(buf), "[QMG-ERROR]: CUDA failure %s (%s) at %s:%d", cudaGetErrorString(e), what, file, line);
+  rt().error = buf;
+  fprintf(stderr, "%s\n", buf);
+  return 1;
+}
+
+int fail_msg(const char* msg)
+{
+  rt().error = std::string("[QMG-ERROR]: ") + msg;
+  fprintf(stderr, "%s\n", rt().error.c_str());
+  return 2;
+}
+
+int fetch_result(double* host_out, int count)
+{
+  Runtime& r = rt();
+  QMG_CUDA(cudaMemcpyAsync(r.h_result, r.d_result, sizeof(double) * count, cudaMemcpyDeviceToHost, r.stream));
+  QMG_CUDA(cudaStreamSynchronize(r.stream));
+  for (int i = 0; i < count; i++) host_out[i] = r.h_result[i];
+  return 0;
+}
+
+double* ensure_partials(size_t ndoubles)
+{
+  Runtime& r = rt();
+  if (ndoubles <= r.partials_cap) return r.d_partials;
+  cudaStreamSynchronize(r.stream);
+  if (r.d_partials) cudaFree(r.d_partials);
+  r.d_partials = nullptr; r.partials_cap = 0;
+  if (cudaMalloc(&r.d_partials, sizeof(double) * ndoubles) != cudaSuccess) { fail_msg("out of device memory for reduction scratch"); return nullptr; }
+  r.partials_cap = ndoubles;
+  return r.d_partials;
+}
+
+int reduction_grid(long n_items, int items_per_block)
+{
+  long want = (n_items + items_per_block - 1) / items_per_block;
+  long cap = (long)rt().sm_count * 8;
+  if (cap > kMaxRedBlocks) cap = kMaxRedBlocks;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+} // namespace qmg
+
+using namespace qmg;
+
+extern "C" {
+
+int qmg_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int qmg_init(int device)
+{
+  Runtime& r = rt();
+  if (r.ready && (device < 0 || device == r.device)) return 0;
+  if (r.ready) qmg_finalize();
+  int n = qmg_device_count();
+  if (n <= 0) return fail_msg("no CUDA device visible: libqmg_b200 has no CPU fallback");
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  QMG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  QMG_CUDA(cudaGetDeviceProperties(&prop, device));
+  r.device = device;
+  r.sm_count = prop.multiProcessorCount;
+  if (ensure_partials((size_t)kMaxRedBlocks * kMaxRedWidth) == nullptr) return 1;
+  QMG_CUDA(cudaMalloc(&r.d_counter, sizeof(unsigned int)));
+  QMG_CUDA(cudaMemset(r.d_counter, 0, sizeof(unsigned int)));
+  QMG_CUDA(cudaMalloc(&r.d_result, sizeof(double) * 2 * kMaxPtrs));
+  QMG_CUDA(cudaMallocHost(&r.h_result, sizeof(double) * 2 * kMaxPtrs));
+  QMG_CUDA(cudaMalloc(&r.d_ptrs, sizeof(void*) * kMaxPtrs));
+  QMG_CUDA(cudaMalloc(&r.d_scalars, sizeof(double) * 2 * kMaxPtrs));
+  QMG_CUDA(cudaDeviceSynchronize());
+  r.ready = true;
+  return 0;
+}
+
+int qmg_finalize(void)
+{
+  Runtime& r = rt();
+  if (!r.ready) return 0;
+  cudaStreamSynchronize(r.stream);
+  cudaFree(r.d_partials); cudaFree(r.d_counter); cudaFree(r.d_result); cudaFree(r.d_ptrs); cudaFree(r.d_scalars);
+  cudaFreeHost(r.h_result);
+  r.d_partials = nullptr; r.partials_cap = 0; r.d_counter = nullptr; r.d_result = nullptr; r.h_result = nullptr; r.d_ptrs = nullptr; r.d_scalars = nullptr;
+  r.ready = false;
+  return 0;
+}
+
+int qmg_set_stream(void* cuda_stream) { QMG_REQUIRE_INIT(); rt().stream = (cudaStream_t)cuda_stream; return 0; }
+void* qmg_get_stream(void) { return (void*)rt().stream; }
+int qmg_sync(void) { QMG_REQUIRE_INIT(); QMG_CUDA(cudaStreamSynchronize(rt().stream)); return 0; }
+const char* qmg_last_error(void) { return rt().error.c_str(); }
+int qmg_sm_count(void) { return rt().sm_count; }
+long qmg_kernel_launches(void) { return rt().launches; }
+
+int qmg_malloc(void** dptr, size_t bytes)
+{
+  QMG_REQUIRE_INIT();
+  if (bytes == 0) bytes = 16;
+  QMG_CUDA(cudaMalloc(dptr, bytes));
+  return 0;
+}
+int qmg_free(void* dptr) { if (dptr) { QMG_CUDA(cudaFree(dptr)); } return 0; }
+int qmg_memcpy_h2d(void* dst, const void* src, size_t bytes)
+{
+  QMG_REQUIRE_INIT();
+  QMG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, rt().stream));
+  QMG_CUDA(cudaStreamSynchronize(rt().stream));
+  return 0;
+}
+int qmg_memcpy_d2h(void* dst, const void* src, size_t bytes)
+{
+  QMG_REQUIRE_INIT();
+  QMG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, rt().stream));
+  QMG_CUDA(cudaStreamSynchronize(rt().stream));
+  return 0;
+}
+int qmg_memcpy_d2d(void* dst, const void* src, size_t bytes)
+{
+  QMG_REQUIRE_INIT();
+  QMG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, rt().stream));
+  return 0;
+}
+int qmg_malloc_host(void** hptr, size_t bytes) { QMG_REQUIRE_INIT(); QMG_CUDA(cudaMallocHost(hptr, bytes ? bytes : 16)); return 0; }
+int qmg_free_host(void* hptr) { if (hptr) { QMG_CUDA(cudaFreeHost(hptr)); } return 0; }
+
+} // extern "C"

@@ -1,0 +1,309 @@
+// K1: the stencil apply -- THE hot kernel.
+//
+//   out(x) (=|+=) [clover(x) + diag shifts] in(x) + sum_mu hopping_mu(x) in(x+mu)
+//
+// replaces Stencil2D::apply_M and its pieces
+// (/root/reference/stencil/stencil_2d.h:666-936): one fused pass instead of
+// 1 zero + 1 clover cMATxpy + 8 cshift + 8 half-volume cMATxpy + 2 caxpy.
+//
+// Mapping: one lane per stored matrix ELEMENT.  Lane (site, c1, c2) streams
+// clover[c1][c2] and the four hopping_mu[c1][c2] of its site -- consecutive lanes
+// read consecutive 16-byte elements, so every warp-level load covers one
+// contiguous 512-byte span (4 lines) and each link is fetched from HBM exactly
+// once -- multiplies by in(neighbour)[c2] (re-used across c1 and across
+// neighbouring sites through L1/L2) and the nc partial products of a row are
+// summed with a log2(nc)-step xor-shuffle tree.  The c2 == 0 lane writes
+// out[site][c1].  No shared memory, no divergence inside a row.
+//
+// HBM-bound: 16*(nc^2*(n_clover+4) + 2nc) algorithmic bytes per site
+// (Wilson 384 B, coarse nc=8 5376 B) for 8*nc^2*(n_clover+4) flops.
+#include "qmg_lattice.cuh"
+
+namespace qmg {
+
+struct StencilKArgs
+{
+  const cd* clover;     // nullptr if absent / not applied
+  const cd* hop;        // nullptr if absent / not applied
+  const cd* in;
+  cd* out;
+  const cd* dotw;       // fused <out|dotw> or nullptr
+  const cd* halo_ym;    // input row y=-1 from the lower rank, or nullptr (periodic)
+  const cd* halo_yp;    // input row y=Y from the upper rank, or nullptr
+  Geom g;
+  long size_cm;         // V*nc*nc: stride between hopping directions
+  cd diag[2][2];        // [parity][dof half]: shift +- eo_shift +- dof_shift (+1 for identity clover)
+  int use_diag;
+  int hop_to[2];        // hop_to[p]: apply hopping into parity p
+  int dir_mask;
+  int accumulate;
+  int p_begin;          // first parity written (grid.z runs over n_par parities)
+};
+
+template <int NC, bool REDUCE>
+__global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, double* partials, unsigned int* counter, double* result)
+{
+  constexpr int LPS = NC * NC;   // lanes per site
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;   // element inside the row
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int p = a.p_begin + blockIdx.z;
+  const int k = col / LPS;
+  const int c = col % LPS;
+  const int c1 = c / NC, c2 = c % NC;
+  const bool active = (k < a.g.xh) && (y < a.g.Y);
+
+  cd acc = cmake(0.0, 0.0);
+  size_t site = 0;
+  if (active)
+  {
+    const unsigned h = (unsigned)y * a.g.xh + k;
+    site = (size_t)p * a.g.half + h;
+    const int q = 1 - p;
+
+    if (a.clover != nullptr || (a.use_diag && c1 == c2))
+    {
+      const cd v0 = ld_keep(a.in + site * NC + c2);
+      if (a.clover != nullptr) cfma(acc, ld_stream(a.clover + site * LPS + c), v0);
+      if (a.use_diag && c1 == c2) cfma(acc, a.diag[p][(2 * c2 >= NC && NC > 1) ? 1 : 0], v0);
+    }
+
+    if (a.hop != nullptr && a.hop_to[p])
+    {
+      const cd* in_q = a.in + (size_t)q * a.g.half * NC;
+#pragma unroll
+      for (int mu = 0; mu < 4; mu++)
+      {
+        if (!((a.dir_mask >> mu) & 1)) continue;
+        const cd* src;
+        if (mu == 1 && a.halo_yp != nullptr && y == a.g.Y - 1) src = a.halo_yp + ((size_t)q * a.g.xh + k) * NC + c2;
+        else if (mu == 3 && a.halo_ym != nullptr && y == 0) src = a.halo_ym + ((size_t)q * a.g.xh + k) * NC + c2;
+        else src = in_q + (size_t)nbr_h(a.g, p, y, k, mu) * NC + c2;
+        cfma(acc, ld_stream(a.hop + (size_t)mu * a.size_cm + site * LPS + c), ld_keep(src));
+      }
+    }
+  }
+
+  // sum the nc partial products of each matrix row (lanes c2 = 0..NC-1 are consecutive)
+#pragma unroll
+  for (int o = NC / 2; o > 0; o >>= 1) { cd t = shfl_xor_c(acc, o); acc = cadd(acc, t); }
+
+  double red[3] = {0.0, 0.0, 0.0};
+  if (active && c2 == 0)
+  {
+    const size_t idx = site * NC + c1;
+    if (a.accumulate) acc = cadd(acc, a.out[idx]);
+    a.out[idx] = acc;
+    if (REDUCE)
+    {
+      red[2] = acc.x * acc.x + acc.y * acc.y;
+      if (a.dotw != nullptr)
+      {
+        const cd w = ld_keep(a.dotw + idx);
+        red[0] = acc.x * w.x + acc.y * w.y;
+        red[1] = acc.x * w.y - acc.y * w.x;
+      }
+    }
+  }
+  if (REDUCE)
+  {
+    // flatten the block for the shared reduction helpers
+    __shared__ double smem[8 * 3];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = (nthreads + 31) >> 5;
+#pragma unroll
+    for (int w = 0; w < 3; w++) red[w] = warp_sum(red[w]);
+    if (lane == 0) { smem[warp * 3 + 0] = red[0]; smem[warp * 3 + 1] = red[1]; smem[warp * 3 + 2] = red[2]; }
+    __syncthreads();
+    __shared__ bool is_last;
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (warp == 0)
+    {
+#pragma unroll
+      for (int w = 0; w < 3; w++) { double t = (lane < nwarp) ? smem[lane * 3 + w] : 0.0; red[w] = warp_sum(t); }
+      if (lane == 0)
+      {
+        partials[(size_t)bid * 3 + 0] = red[0]; partials[(size_t)bid * 3 + 1] = red[1]; partials[(size_t)bid * 3 + 2] = red[2];
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == nblocks - 1);
+      }
+    }
+    __syncthreads();
+    if (is_last)
+    {
+      __threadfence();
+      double accr[3] = {0.0, 0.0, 0.0};
+      for (unsigned int b = tid; b < nblocks; b += nthreads)
+      {
+        accr[0] += __ldcg(&partials[(size_t)b * 3 + 0]);
+        accr[1] += __ldcg(&partials[(size_t)b * 3 + 1]);
+        accr[2] += __ldcg(&partials[(size_t)b * 3 + 2]);
+      }
+#pragma unroll
+      for (int w = 0; w < 3; w++) accr[w] = warp_sum(accr[w]);
+      __syncthreads();
+      if (lane == 0) { smem[warp * 3 + 0] = accr[0]; smem[warp * 3 + 1] = accr[1]; smem[warp * 3 + 2] = accr[2]; }
+      __syncthreads();
+      if (warp == 0)
+      {
+#pragma unroll
+        for (int w = 0; w < 3; w++) { double t = (lane < nwarp) ? smem[lane * 3 + w] : 0.0; accr[w] = warp_sum(t); }
+        if (lane == 0) { result[0] = accr[0]; result[1] = accr[1]; result[2] = accr[2]; *counter = 0u; }
+      }
+    }
+  }
+}
+
+// Any nc (DWF Ls = 6, 12, 24, 32 give nc = 12, 24, 48, 64): one thread per
+// (site, row), looping over the columns.  Slow path, same arithmetic.
+__global__ void __launch_bounds__(256) stencil_kernel_generic(const StencilKArgs a, int nc, int n_par)
+{
+  const long rows = (long)n_par * a.g.half * nc;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < rows; t += (long)gridDim.x * blockDim.x)
+  {
+    const int c1 = (int)(t % nc);
+    const long s = t / nc;
+    const int p = a.p_begin + (int)(s / a.g.half);
+    const unsigned h = (unsigned)(s % a.g.half);
+    const int y = h / a.g.xh, k = h % a.g.xh;
+    const size_t site = (size_t)p * a.g.half + h;
+    const int q = 1 - p;
+    const size_t lps = (size_t)nc * nc;
+    cd acc = cmake(0.0, 0.0);
+    if (a.clover != nullptr)
+      for (int c2 = 0; c2 < nc; c2++) cfma(acc, a.clover[site * lps + (size_t)c1 * nc + c2], a.in[site * nc + c2]);
+    if (a.use_diag) cfma(acc, a.diag[p][(2 * c1 >= nc && nc > 1) ? 1 : 0], a.in[site * nc + c1]);
+    if (a.hop != nullptr && a.hop_to[p])
+    {
+      const cd* in_q = a.in + (size_t)q * a.g.half * nc;
+      for (int mu = 0; mu < 4; mu++)
+      {
+        if (!((a.dir_mask >> mu) & 1)) continue;
+        const cd* src;
+        if (mu == 1 && a.halo_yp != nullptr && y == a.g.Y - 1) src = a.halo_yp + ((size_t)q * a.g.xh + k) * nc;
+        else if (mu == 3 && a.halo_ym != nullptr && y == 0) src = a.halo_ym + ((size_t)q * a.g.xh + k) * nc;
+        else src = in_q + (size_t)nbr_h(a.g, p, y, k, mu) * nc;
+        const cd* m = a.hop + (size_t)mu * a.size_cm + site * lps + (size_t)c1 * nc;
+        for (int c2 = 0; c2 < nc; c2++) cfma(acc, m[c2], src[c2]);
+      }
+    }
+    const size_t idx = site * nc + c1;
+    if (a.accumulate) acc = cadd(acc, a.out[idx]);
+    a.out[idx] = acc;
+  }
+}
+
+static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs, StencilKArgs& a, int& n_par)
+{
+  if (st == nullptr) return fail_msg("qmg_stencil_apply: null stencil");
+  if (st->X < 2 || st->Y < 2 || (st->X & 1) || (st->Y & 1)) return fail_msg("qmg_stencil_apply: X and Y must be even and >= 2");
+  if (st->nc < 1) return fail_msg("qmg_stencil_apply: nc < 1");
+  if ((const void*)lhs == (const void*)rhs && (pieces & (QMG_APPLY_CLOVER | QMG_APPLY_SHIFT | QMG_APPLY_IDENTITY_CLOVER)))
+    return fail_msg("qmg_stencil_apply: in-place apply is only defined for pure hopping pieces");
+  a.clover = (pieces & QMG_APPLY_CLOVER) ? reinterpret_cast<const cd*>(st->clover) : nullptr;
+  const bool want_hop = pieces & (QMG_APPLY_HOP_TO_EVEN | QMG_APPLY_HOP_TO_ODD);
+  a.hop = want_hop ? reinterpret_cast<const cd*>(st->hopping) : nullptr;
+  a.in = reinterpret_cast<const cd*>(rhs);
+  a.out = reinterpret_cast<cd*>(lhs);
+  a.dotw = nullptr;
+  a.halo_ym = reinterpret_cast<const cd*>(st->halo_ym);
+  a.halo_yp = reinterpret_cast<const cd*>(st->halo_yp);
+  a.g.xh = st->X / 2; a.g.Y = st->Y; a.g.half = (unsigned)(st->X / 2) * st->Y;
+  a.size_cm = (long)st->X * st->Y * st->nc * st->nc;
+  const bool sh = pieces & QMG_APPLY_SHIFT;
+  const double id = (pieces & QMG_APPLY_IDENTITY_CLOVER) ? 1.0 : 0.0;
+  for (int p = 0; p < 2; p++)
+    for (int hf = 0; hf < 2; hf++)
+    {
+      const double se = p ? -1.0 : 1.0, sd = hf ? -1.0 : 1.0;
+      // dof_shift only exists for even nc (stencil_2d.h:897)
+      const double dr = (st->nc % 2 == 0) ? st->dof_shift[0] : 0.0, di = (st->nc % 2 == 0) ? st->dof_shift[1] : 0.0;
+      a.diag[p][hf] = sh ? cmake(id + st->shift[0] + se * st->eo_shift[0] + sd * dr, st->shift[1] + se * st->eo_shift[1] + sd * di)
+                         : cmake(id, 0.0);
+    }
+  a.use_diag = (sh && (st->shift[0] != 0.0 || st->shift[1] != 0.0 || st->eo_shift[0] != 0.0 || st->eo_shift[1] != 0.0 ||
+                       st->dof_shift[0] != 0.0 || st->dof_shift[1] != 0.0)) || id != 0.0;
+  a.hop_to[0] = (pieces & QMG_APPLY_HOP_TO_EVEN) ? 1 : 0;
+  a.hop_to[1] = (pieces & QMG_APPLY_HOP_TO_ODD) ? 1 : 0;
+  a.dir_mask = dir_mask & 15;
+  a.accumulate = (pieces & QMG_APPLY_ACCUMULATE) ? 1 : 0;
+  a.p_begin = 0; n_par = 2;
+  if (pieces & QMG_APPLY_EVEN_ROWS_ONLY) { a.p_begin = 0; n_par = 1; }
+  if (pieces & QMG_APPLY_ODD_ROWS_ONLY) { a.p_begin = 1; n_par = 1; }
+  return 0;
+}
+
+template <int NC>
+static int launch_stencil(const StencilKArgs& a, int n_par, bool reduce)
+{
+  Runtime& r = rt();
+  const int row_elems = a.g.xh * NC * NC;
+  int bx = 256;
+  while (bx > 32 && bx / 2 >= row_elems) bx /= 2;
+  int by = 256 / bx;
+  if (by > a.g.Y) by = a.g.Y;
+  dim3 block(bx, by, 1);
+  dim3 grid((row_elems + bx - 1) / bx, (a.g.Y + by - 1) / by, n_par);
+  if (grid.y > 65535) return fail_msg("qmg_stencil_apply: Y too large for the launch grid");
+  if (reduce)
+  {
+    double* partials = ensure_partials((size_t)grid.x * grid.y * grid.z * 3);
+    if (partials == nullptr) return 1;
+    stencil_kernel<NC, true><<<grid, block, 0, r.stream>>>(a, partials, r.d_counter, r.d_result);
+  }
+  else
+    stencil_kernel<NC, false><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+
+static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduce)
+{
+  switch (nc)
+  {
+    case 1: return launch_stencil<1>(a, n_par, reduce);
+    case 2: return launch_stencil<2>(a, n_par, reduce);
+    case 4: return launch_stencil<4>(a, n_par, reduce);
+    case 8: return launch_stencil<8>(a, n_par, reduce);
+    case 16: return launch_stencil<16>(a, n_par, reduce);
+    case 32: return launch_stencil<32>(a, n_par, reduce);
+    default: break;
+  }
+  if (reduce) return fail_msg("qmg_stencil_apply_dot: fused reduction needs nc in {1,2,4,8,16,32}");
+  Runtime& r = rt();
+  const long rows = (long)n_par * a.g.half * nc;
+  long blocks = (rows + 255) / 256, cap = (long)r.sm_count * 8;
+  stencil_kernel_generic<<<(int)(blocks < cap ? blocks : cap), 256, 0, r.stream>>>(a, nc, n_par);
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+
+} // namespace qmg
+
+using namespace qmg;
+
+extern "C" {
+
+int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs)
+{
+  QMG_REQUIRE_INIT();
+  StencilKArgs a; int n_par;
+  int rc = build_args(st, pieces, dir_mask, lhs, rhs, a, n_par);
+  if (rc) return rc;
+  return dispatch_stencil(a, st->nc, n_par, false);
+}
+
+int qmg_stencil_apply_dot(const qmg_stencil_desc* st, int pieces, qmg_cplx* lhs, const qmg_cplx* rhs, const qmg_cplx* dot_with, double* result3)
+{
+  QMG_REQUIRE_INIT();
+  StencilKArgs a; int n_par;
+  int rc = build_args(st, pieces, 15, lhs, rhs, a, n_par);
+  if (rc) return rc;
+  a.dotw = reinterpret_cast<const cd*>(dot_with);
+  rc = dispatch_stencil(a, st->nc, n_par, true);
+  if (rc) return rc;
+  return fetch_result(result3, 3);
+}
+
+} // extern "C"

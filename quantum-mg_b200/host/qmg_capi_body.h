@@ -1,0 +1,523 @@
+// Flat C driver API written ONLY against the reference's public class API
+// (Lattice2D, Stencil2D and its operators, TransferMG, CoarseOperator2D,
+// StatefulMultigridMG, the apply_stencil_2D_* wrappers and the quantum-linalg
+// solver entry points).  The same text is compiled twice:
+//
+//   * quantum-mg_b200/host/qmg_host_capi.cpp  -> libqmg_host.so
+//       against include/qmg/ (the B200 host classes; vectors live in HBM)
+//   * oracle/ref_capi.cpp                     -> oracle/_ref/libqmg_ref.so
+//       against the UNMODIFIED headers under /root/reference plus the
+//       clean-room quantum-linalg shim (plain host memory; test oracle only)
+//
+// so a parity test is literally "same driver, two back ends".  The including
+// file defines CAPI(name) (symbol prefix) and the staging helpers
+//   capi_alloc(n) / capi_free(p)         storage usable by the class API
+//   capi_put(dst, host_src, n)           host array  -> class-API storage
+//   capi_get(host_dst, src, n)           class-API storage -> host array
+// which are memcpy for the reference build and H2D/D2H copies for the GPU build.
+//
+// All array arguments of this API are HOST pointers to interleaved complex<double>.
+
+#include <chrono>
+#include <vector>
+
+typedef std::complex<double> capi_cd;
+
+namespace capi {
+
+// RAII staging of one host array into class-API storage.
+struct Stage
+{
+  capi_cd* p; capi_cd* host; long n; bool write_back;
+  Stage(const capi_cd* h, long n_, bool in, bool out) : p(0), host((capi_cd*)h), n(n_), write_back(out)
+  {
+    p = capi_alloc(n);
+    if (in && h != 0) capi_put(p, h, n);
+  }
+  ~Stage() { if (write_back && host != 0) capi_get(host, p, n); capi_free(p); }
+  operator capi_cd*() { return p; }
+private:
+  Stage(const Stage&); Stage& operator=(const Stage&);
+};
+
+struct LatticeH { Lattice2D* lat; };
+struct StencilH { Stencil2D* op; bool owned; };
+struct TransferH { TransferMG* t; Lattice2D* fine; Lattice2D* coarse; };
+struct MgH
+{
+  StatefulMultigridMG* mg;
+  StatefulMultigridMG::CoarsestSolveMG* coarsest;
+  std::vector<StatefulMultigridMG::LevelSolveMG*> levels;
+};
+
+inline capi_cd* stencil_array(Stencil2D* s, int which, long& n)
+{
+  const long cm = s->lat->get_size_cm();
+  switch (which)
+  {
+    case 0: n = cm; return s->clover;
+    case 1: n = 4 * cm; return s->hopping;
+    case 2: n = cm; return s->dagger_clover;
+    case 3: n = 4 * cm; return s->dagger_hopping;
+    case 4: n = cm; return s->rbjacobi_clover;
+    case 5: n = 4 * cm; return s->rbjacobi_hopping;
+    case 6: n = cm; return s->rbjacobi_cinv;
+    case 7: n = cm; return s->rbj_dagger_clover;
+    case 8: n = 4 * cm; return s->rbj_dagger_hopping;
+    case 9: n = cm; return s->rbj_dagger_cinv;
+  }
+  n = 0; return 0;
+}
+
+} // namespace capi
+
+extern "C" {
+
+// ------------------------------------------------------------------ lattice --
+void* CAPI(lattice_new)(int X, int Y, int nc) { capi::LatticeH* h = new capi::LatticeH; h->lat = new Lattice2D(X, Y, nc); return h; }
+void CAPI(lattice_free)(void* h_) { capi::LatticeH* h = (capi::LatticeH*)h_; delete h->lat; delete h; }
+int CAPI(lattice_coord_to_index)(void* h, int x, int y) { return ((capi::LatticeH*)h)->lat->coord_to_index(x, y); }
+void CAPI(lattice_index_to_coord)(void* h, int i, int* xy) { ((capi::LatticeH*)h)->lat->index_to_coord(i, xy[0], xy[1]); }
+// sizes: volume, size_cv, size_cm, size_gauge, size_hopping, size_corner
+void CAPI(lattice_sizes)(void* h_, int* out)
+{
+  Lattice2D* l = ((capi::LatticeH*)h_)->lat;
+  out[0] = l->get_volume(); out[1] = l->get_size_cv(); out[2] = l->get_size_cm();
+  out[3] = l->get_size_gauge(); out[4] = l->get_size_hopping(); out[5] = l->get_size_corner();
+}
+int CAPI(lattice_cm_index)(void* h, int x, int y, int c1, int c2) { return ((capi::LatticeH*)h)->lat->cm_coord_to_index(x, y, c1, c2); }
+int CAPI(lattice_hopping_index)(void* h, int x, int y, int c1, int c2, int mu) { return ((capi::LatticeH*)h)->lat->hopping_coord_to_index(x, y, c1, c2, mu); }
+int CAPI(lattice_gauge_index)(void* h, int x, int y, int c1, int c2, int mu) { return ((capi::LatticeH*)h)->lat->gauge_coord_to_index(x, y, c1, c2, mu); }
+void CAPI(lattice_cv_index_to_coord)(void* h, int i, int* xyc) { ((capi::LatticeH*)h)->lat->cv_index_to_coord(i, xyc[0], xyc[1], xyc[2]); }
+
+// cshift<complex<double>> (cshift/cshift_2d.h:225); lhs is in/out (only half is written per source parity)
+void CAPI(cshift)(capi_cd* lhs, const capi_cd* rhs, int cdir, int eo, int dof, void* lat_)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  const long n = (long)lat->get_volume() * dof;
+  capi::Stage dl(lhs, n, true, true), dr(rhs, n, true, false);
+  cshift((capi_cd*)dl, (capi_cd*)dr, (qmg_cshift_dir)cdir, (qmg_eo)eo, dof, lat);
+}
+
+// ------------------------------------------------------------------ stencils --
+// gauge: host array of size_gauge complex links on the nc=1 lattice (u1/u1_utils.h layout)
+void* CAPI(wilson_new)(void* lat_, double mass_re, double mass_im, const capi_cd* gauge, double wilson_coeff)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage g(gauge, 2L * lat->get_volume(), true, false);
+  capi::StencilH* h = new capi::StencilH;
+  h->op = new Wilson2D(lat, capi_cd(mass_re, mass_im), (capi_cd*)g, wilson_coeff); h->owned = true;
+  return h;
+}
+void* CAPI(staggered_new)(void* lat_, double mass_re, double mass_im, const capi_cd* gauge)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage g(gauge, 2L * lat->get_volume(), true, false);
+  capi::StencilH* h = new capi::StencilH;
+  h->op = new Staggered2D(lat, capi_cd(mass_re, mass_im), (capi_cd*)g); h->owned = true;
+  return h;
+}
+void* CAPI(laplace_new)(void* lat_, double msq_re, double msq_im, const capi_cd* gauge)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage g(gauge, 2L * lat->get_volume(), true, false);
+  capi::StencilH* h = new capi::StencilH;
+  h->op = new GaugedLaplace2D(lat, capi_cd(msq_re, msq_im), (capi_cd*)g); h->owned = true;
+  return h;
+}
+void* CAPI(dwf_new)(void* lat_, double mass_re, double mass_im, const capi_cd* gauge, int Ls, double M5)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage g(gauge, 2L * lat->get_volume(), true, false);
+  Stencil2D* op = createDwfLs(lat, capi_cd(mass_re, mass_im), (capi_cd*)g, Ls, M5);
+  if (op == 0) return 0;
+  capi::StencilH* h = new capi::StencilH; h->op = op; h->owned = true;
+  return h;
+}
+// A bare stencil with caller-supplied blocks (CoarseOperator2D's first ctor, operators/coarse.h:76).
+void* CAPI(generic_new)(void* lat_, int is_chiral, int def_chirality, const double* shifts6, const capi_cd* clover, const capi_cd* hopping)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  int pieces = 0;
+  if (clover != 0) pieces |= QMG_PIECE_CLOVER;
+  if (hopping != 0) pieces |= QMG_PIECE_HOPPING;
+  CoarseOperator2D* op = new CoarseOperator2D(lat, pieces, is_chiral != 0, (QMGDefaultChirality)def_chirality,
+                                              capi_cd(shifts6[0], shifts6[1]), capi_cd(shifts6[2], shifts6[3]), capi_cd(shifts6[4], shifts6[5]));
+  if (clover != 0) capi_put(op->clover, clover, lat->get_size_cm());
+  if (hopping != 0) capi_put(op->hopping, hopping, lat->get_size_hopping());
+  op->generated = true;
+  capi::StencilH* h = new capi::StencilH; h->op = op; h->owned = true;
+  return h;
+}
+void CAPI(stencil_free)(void* h_) { capi::StencilH* h = (capi::StencilH*)h_; if (h->owned) delete h->op; delete h; }
+
+// which: 0 clover 1 hopping 2 dagger_clover 3 dagger_hopping 4 rbjacobi_clover 5 rbjacobi_hopping
+//        6 rbjacobi_cinv 7 rbj_dagger_clover 8 rbj_dagger_hopping 9 rbj_dagger_cinv ; returns element count (0 if absent)
+long CAPI(stencil_get)(void* h_, int which, capi_cd* out)
+{
+  long n; capi_cd* p = capi::stencil_array(((capi::StencilH*)h_)->op, which, n);
+  if (p == 0) return 0;
+  if (out != 0) capi_get(out, p, n);
+  return n;
+}
+// the n18 mutation: cxpy(noise, stencil->clover, cm_size)
+// (tests/n18_rbjacobi_stencil_test/rbjacobi_stencil_test.cpp:137)
+void CAPI(stencil_add_to)(void* h_, int which, const capi_cd* noise)
+{
+  long n; capi_cd* p = capi::stencil_array(((capi::StencilH*)h_)->op, which, n);
+  if (p == 0) return;
+  capi::Stage dn(noise, n, true, false);
+  cxpy((capi_cd*)dn, p, (int)n);
+}
+// shifts: out[0..5] = shift, eo_shift, dof_shift
+void CAPI(stencil_get_shifts)(void* h_, double* out)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  out[0] = real(s->get_shift()); out[1] = imag(s->get_shift());
+  out[2] = real(s->get_shift_eo()); out[3] = imag(s->get_shift_eo());
+  out[4] = real(s->get_shift_dof()); out[5] = imag(s->get_shift_dof());
+}
+void CAPI(stencil_update_shifts)(void* h_, const double* s6)
+{
+  ((capi::StencilH*)h_)->op->update_shifts(capi_cd(s6[0], s6[1]), capi_cd(s6[2], s6[3]), capi_cd(s6[4], s6[5]));
+}
+// which: 1 dagger, 2 rbjacobi, 4 rbj_dagger (bitmask, built in that order)
+void CAPI(stencil_build)(void* h_, int which)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  if (which & 1) s->build_dagger_stencil();
+  if (which & 2) s->build_rbjacobi_stencil();
+  if (which & 4) s->build_rbj_dagger_stencil();
+}
+int CAPI(stencil_built)(void* h_)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  return (s->built_dagger ? 1 : 0) | (s->built_rbjacobi ? 2 : 0) | (s->built_rbj_dagger ? 4 : 0);
+}
+
+// lhs = M_type rhs through the function-pointer wrappers apply_stencil_2D_* (stencil_2d.h:2571-2716)
+void CAPI(stencil_apply)(void* h_, int type, capi_cd* lhs, const capi_cd* rhs)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  const long n = s->lat->get_size_cv();
+  capi::Stage dl(lhs, n, true, true), dr(rhs, n, true, false);
+  matrix_op_cplx fn = Stencil2D::get_apply_function((QMGStencilType)type);
+  if (fn != 0) fn((capi_cd*)dl, (capi_cd*)dr, (void*)s);
+}
+
+// The accumulate-into-lhs member functions (stencil_2d.h:666-936, 1848).
+// piece: 0 apply_M  1 clover  2 eo  3 oe  4 hopping  5 hopping(dir)  6 shift  7 eo(dir)  8 oe(dir)
+//        9 ee  10 oo  11 rbjacobi_cinv  12 apply_M(type=dir)
+void CAPI(stencil_apply_piece)(void* h_, int piece, int dir, capi_cd* lhs, const capi_cd* rhs)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  const long n = s->lat->get_size_cv();
+  capi::Stage dl(lhs, n, true, true), dr(rhs, n, true, false);
+  capi_cd* l = dl; capi_cd* r = dr;
+  switch (piece)
+  {
+    case 0: s->apply_M(l, r); break;
+    case 1: s->apply_M_clover(l, r); break;
+    case 2: s->apply_M_eo(l, r); break;
+    case 3: s->apply_M_oe(l, r); break;
+    case 4: s->apply_M_hopping(l, r); break;
+    case 5: s->apply_M_hopping(l, r, (stencil_dir_index)dir); break;
+    case 6: s->apply_M_shift(l, r); break;
+    case 7: s->apply_M_eo(l, r, (stencil_dir_index)dir); break;
+    case 8: s->apply_M_oe(l, r, (stencil_dir_index)dir); break;
+    case 9: s->apply_M_ee(l, r); break;
+    case 10: s->apply_M_oo(l, r); break;
+    case 11: s->apply_M_rbjacobi_cinv(l, r); break;
+    case 12: s->apply_M(l, r, (QMGStencilType)dir); break;
+  }
+}
+void CAPI(stencil_prepare)(void* h_, int type, capi_cd* b_prep, const capi_cd* b)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  const long n = s->lat->get_size_cv();
+  capi::Stage dp(b_prep, n, true, true), db(b, n, true, false);
+  s->prepare_M((capi_cd*)dp, (capi_cd*)db, (QMGStencilType)type);
+}
+void CAPI(stencil_reconstruct)(void* h_, int type, capi_cd* x, const capi_cd* y, const capi_cd* b)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  const long n = s->lat->get_size_cv();
+  capi::Stage dx(x, n, true, true), dy(y, n, true, false), db(b, n, true, false);
+  s->reconstruct_M((capi_cd*)dx, (capi_cd*)dy, (capi_cd*)db, (QMGStencilType)type);
+}
+// op: 0 gamma5(a) in place  1 gamma5(b <- a)  2 sigma1(a) in place  3 sigma1(b <- a)
+//     4 chiral_projection(a, up)  5 chiral_projection(a, down)  6 projection_copy(a -> b, up)  7 (down)
+//     8 chiral_projection_both(a -> up in place, b <- down)   9.. apply_sigma(b <- a, type = op - 9)
+void CAPI(stencil_chiral)(void* h_, int op, capi_cd* a, capi_cd* b)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  const long n = s->lat->get_size_cv();
+  capi::Stage da(a, n, true, true), db(b, n, b != 0, b != 0);
+  switch (op)
+  {
+    case 0: s->gamma5((capi_cd*)da); break;
+    case 1: s->gamma5((capi_cd*)db, (capi_cd*)da); break;
+    case 2: s->sigma1((capi_cd*)da); break;
+    case 3: s->sigma1((capi_cd*)db, (capi_cd*)da); break;
+    case 4: s->chiral_projection((capi_cd*)da, true); break;
+    case 5: s->chiral_projection((capi_cd*)da, false); break;
+    case 6: s->chiral_projection_copy((capi_cd*)da, (capi_cd*)db, true); break;
+    case 7: s->chiral_projection_copy((capi_cd*)da, (capi_cd*)db, false); break;
+    case 8: s->chiral_projection_both((capi_cd*)da, (capi_cd*)db); break;
+    default: s->apply_sigma((capi_cd*)db, (capi_cd*)da, (QMGSigmaType)(op - 9)); break;
+  }
+}
+
+// Wall-clock seconds for `reps` wrapper applies of type `type` (after `warm` untimed ones).
+double CAPI(stencil_time_apply)(void* h_, int type, int warm, int reps, const capi_cd* rhs)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  const long n = s->lat->get_size_cv();
+  capi::Stage dl(0, n, false, false), dr(rhs, n, true, false);
+  matrix_op_cplx fn = Stencil2D::get_apply_function((QMGStencilType)type);
+  for (int i = 0; i < warm; i++) fn((capi_cd*)dl, (capi_cd*)dr, (void*)s);
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < reps; i++) fn((capi_cd*)dl, (capi_cd*)dr, (void*)s);
+  capi_barrier();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ------------------------------------------------------------------- solvers --
+// solver: 0 CG  1 CG(restart=iparam)  2 GCR  3 GCR(restart)  4 MR(omega=dparam)  5 BiCGstab-L(L=iparam)
+//         6 Richardson(omega=dparam, check_freq=iparam)
+// n = number of complex unknowns handed to the solver (size_cv, or size_cv/2 for Schur systems)
+// info: resSq, iter, success, ops_count
+void CAPI(solve)(void* h_, int solver, int type, capi_cd* x, const capi_cd* b, int n, int max_iter, double tol, int iparam, double dparam, int verbosity, double* info)
+{
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  const long full = s->lat->get_size_cv();
+  capi::Stage dx(x, full, true, true), db(b, full, true, false);
+  matrix_op_cplx fn = Stencil2D::get_apply_function((QMGStencilType)type);
+  inversion_verbose_struct verb((inversion_verbose_level)verbosity, "[CAPI-SOLVE]: ");
+  inversion_info inv;
+  switch (solver)
+  {
+    case 0: inv = minv_vector_cg((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, fn, (void*)s, &verb); break;
+    case 1: inv = minv_vector_cg_restart((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, iparam, fn, (void*)s, &verb); break;
+    case 2: inv = minv_vector_gcr((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, fn, (void*)s, &verb); break;
+    case 3: inv = minv_vector_gcr_restart((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, iparam, fn, (void*)s, &verb); break;
+    case 4: inv = minv_vector_minres((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, dparam, fn, (void*)s, &verb); break;
+    case 5: inv = minv_vector_bicgstab_l((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, iparam, fn, (void*)s, &verb); break;
+    case 6: inv = minv_vector_richardson((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, dparam, iparam, fn, (void*)s, &verb); break;
+  }
+  info[0] = inv.resSq; info[1] = inv.iter; info[2] = inv.success ? 1.0 : 0.0; info[3] = inv.ops_count;
+}
+
+// ------------------------------------------------------------------ transfer --
+// nullvecs: host, contiguous [nvec = coarse nc][fine size_cv]
+void* CAPI(transfer_new)(void* fine_, void* coarse_, const capi_cd* nullvecs, int do_block_ortho, int save_decomp, int doubling)
+{
+  Lattice2D* fine = ((capi::LatticeH*)fine_)->lat; Lattice2D* coarse = ((capi::LatticeH*)coarse_)->lat;
+  const int nvec = coarse->get_nc(); const long n = fine->get_size_cv();
+  std::vector<capi_cd*> v(nvec);
+  for (int i = 0; i < nvec; i++) { v[i] = capi_alloc(n); capi_put(v[i], nullvecs + (long)i * n, n); }
+  capi::TransferH* h = new capi::TransferH;
+  h->t = new TransferMG(fine, coarse, &v[0], do_block_ortho != 0, save_decomp != 0, (QMGDoublingType)doubling);
+  h->fine = fine; h->coarse = coarse;
+  for (int i = 0; i < nvec; i++) capi_free(v[i]);
+  return h;
+}
+void* CAPI(transfer_new_asym)(void* fine_, void* coarse_, const capi_cd* prolong_vecs, const capi_cd* restrict_vecs, int do_block_bi_ortho, int save_decomp, int doubling)
+{
+  Lattice2D* fine = ((capi::LatticeH*)fine_)->lat; Lattice2D* coarse = ((capi::LatticeH*)coarse_)->lat;
+  const int nvec = coarse->get_nc(); const long n = fine->get_size_cv();
+  std::vector<capi_cd*> p(nvec), r(nvec);
+  for (int i = 0; i < nvec; i++)
+  {
+    p[i] = capi_alloc(n); capi_put(p[i], prolong_vecs + (long)i * n, n);
+    r[i] = capi_alloc(n); capi_put(r[i], restrict_vecs + (long)i * n, n);
+  }
+  capi::TransferH* h = new capi::TransferH;
+  h->t = new TransferMG(fine, coarse, &p[0], &r[0], do_block_bi_ortho != 0, save_decomp != 0, (QMGDoublingType)doubling);
+  h->fine = fine; h->coarse = coarse;
+  for (int i = 0; i < nvec; i++) { capi_free(p[i]); capi_free(r[i]); }
+  return h;
+}
+void CAPI(transfer_free)(void* h_) { capi::TransferH* h = (capi::TransferH*)h_; delete h->t; delete h; }
+// which: 0 prolong (null_vectors), 1 restrict (restrict_null_vectors); out: [nvec][fine size_cv]
+int CAPI(transfer_get_nullvecs)(void* h_, int which, capi_cd* out)
+{
+  capi::TransferH* h = (capi::TransferH*)h_;
+  capi_cd** src = which == 0 ? h->t->null_vectors : h->t->restrict_null_vectors;
+  if (src == 0) return 0;
+  const int nvec = h->coarse->get_nc(); const long n = h->fine->get_size_cv();
+  for (int i = 0; i < nvec; i++) capi_get(out + (long)i * n, src[i], n);
+  return nvec;
+}
+// fine += P coarse (accumulates, transfer.h:455)
+void CAPI(transfer_prolong)(void* h_, const capi_cd* coarse, capi_cd* fine)
+{
+  capi::TransferH* h = (capi::TransferH*)h_;
+  capi::Stage dc(coarse, h->coarse->get_size_cv(), true, false), df(fine, h->fine->get_size_cv(), true, true);
+  h->t->prolong_c2f((capi_cd*)dc, (capi_cd*)df);
+}
+// coarse += R fine (accumulates, transfer.h:487)
+void CAPI(transfer_restrict)(void* h_, const capi_cd* fine, capi_cd* coarse)
+{
+  capi::TransferH* h = (capi::TransferH*)h_;
+  capi::Stage df(fine, h->fine->get_size_cv(), true, false), dc(coarse, h->coarse->get_size_cv(), true, true);
+  h->t->restrict_f2c((capi_cd*)df, (capi_cd*)dc);
+}
+int CAPI(transfer_props)(void* h_)
+{
+  TransferMG* t = ((capi::TransferH*)h_)->t;
+  return (t->is_symmetric() ? 1 : 0) | (t->has_decompositions() ? 2 : 0) | (t->is_initialized() ? 4 : 0) | ((int)t->get_doubling() << 4);
+}
+void CAPI(transfer_get_cholesky)(void* h_, capi_cd* out)
+{
+  capi::TransferH* h = (capi::TransferH*)h_;
+  capi::Stage d(out, h->coarse->get_size_cm(), false, true);
+  h->t->copy_cholesky((capi_cd*)d);
+}
+void CAPI(transfer_get_LU)(void* h_, capi_cd* outL, capi_cd* outU)
+{
+  capi::TransferH* h = (capi::TransferH*)h_;
+  capi::Stage dL(outL, h->coarse->get_size_cm(), false, true), dU(outU, h->coarse->get_size_cm(), false, true);
+  h->t->copy_LU((capi_cd*)dL, (capi_cd*)dU);
+}
+
+// Galerkin coarse operator (operators/coarse.h:90): returns a stencil handle on the coarse lattice.
+void* CAPI(coarse_new)(void* coarse_lat_, void* fine_stencil_, void* fine_lat_, void* transfer_, int is_chiral, int use_rbjacobi, int build_extra)
+{
+  Lattice2D* clat = ((capi::LatticeH*)coarse_lat_)->lat; Lattice2D* flat = ((capi::LatticeH*)fine_lat_)->lat;
+  capi::StencilH* h = new capi::StencilH;
+  h->op = new CoarseOperator2D(clat, ((capi::StencilH*)fine_stencil_)->op, flat, ((capi::TransferH*)transfer_)->t,
+                               is_chiral != 0, use_rbjacobi != 0, (CoarseOperator2D::QMGCoarseBuildStencil)build_extra);
+  h->owned = true;
+  return h;
+}
+
+// ----------------------------------------------------------------- multigrid --
+void* CAPI(mg_new)(void* lat0_, void* stencil0_, int coarsest_type, double coarsest_tol, int coarsest_iters, int coarsest_restart)
+{
+  capi::MgH* h = new capi::MgH;
+  h->coarsest = new StatefulMultigridMG::CoarsestSolveMG;
+  h->coarsest->coarsest_stencil_app = (QMGStencilType)coarsest_type;
+  h->coarsest->coarsest_tol = coarsest_tol;
+  h->coarsest->coarsest_iters = coarsest_iters;
+  h->coarsest->coarsest_restart_freq = coarsest_restart;
+  h->mg = new StatefulMultigridMG(((capi::LatticeH*)lat0_)->lat, ((capi::StencilH*)stencil0_)->op, h->coarsest);
+  return h;
+}
+void CAPI(mg_free)(void* h_)
+{
+  capi::MgH* h = (capi::MgH*)h_;
+  delete h->mg;
+  for (size_t i = 0; i < h->levels.size(); i++) delete h->levels[i];
+  delete h->coarsest;
+  delete h;
+}
+// iparams: fine_stencil_app, intermediate_iters, intermediate_restart, pre_iters, post_iters, pre_cgne, post_cgne
+// dparams: intermediate_tol, pre_tol, post_tol
+// nvecs (optional): host [coarse nc][fine size_cv] raw null vectors kept by the MG object
+void CAPI(mg_push_level)(void* h_, void* new_lat_, void* transfer_, const int* iparams, const double* dparams,
+                         int build_stencil, int is_chiral, int build_from, int build_extra, const capi_cd* nvecs)
+{
+  capi::MgH* h = (capi::MgH*)h_;
+  Lattice2D* nl = ((capi::LatticeH*)new_lat_)->lat;
+  capi::TransferH* th = (capi::TransferH*)transfer_;
+  StatefulMultigridMG::LevelSolveMG* ls = new StatefulMultigridMG::LevelSolveMG;
+  ls->fine_stencil_app = (QMGStencilType)iparams[0];
+  ls->intermediate_iters = iparams[1];
+  ls->intermediate_restart_freq = iparams[2];
+  ls->pre_iters = iparams[3];
+  ls->post_iters = iparams[4];
+  ls->pre_cgne = iparams[5] != 0;
+  ls->post_cgne = iparams[6] != 0;
+  ls->intermediate_tol = dparams[0];
+  ls->pre_tol = dparams[1];
+  ls->post_tol = dparams[2];
+  h->levels.push_back(ls);
+  std::vector<capi_cd*> v;
+  if (nvecs != 0)
+  {
+    const int nvec = nl->get_nc(); const long n = th->fine->get_size_cv();
+    v.resize(nvec);
+    for (int i = 0; i < nvec; i++) { v[i] = capi_alloc(n); capi_put(v[i], nvecs + (long)i * n, n); }
+  }
+  h->mg->push_level(nl, th->t, ls, build_stencil != 0, is_chiral != 0, (MultigridMG::QMGMultigridPrecondStencil)build_from,
+                    (CoarseOperator2D::QMGCoarseBuildStencil)build_extra, v.empty() ? 0 : &v[0]);
+  for (size_t i = 0; i < v.size(); i++) capi_free(v[i]);
+}
+int CAPI(mg_num_levels)(void* h_) { return ((capi::MgH*)h_)->mg->get_num_levels(); }
+// borrowed stencil handle of level i (free with stencil_free; the operator itself stays owned by the MG object)
+void* CAPI(mg_get_stencil)(void* h_, int level)
+{
+  Stencil2D* s = ((capi::MgH*)h_)->mg->get_stencil(level);
+  if (s == 0) return 0;
+  capi::StencilH* sh = new capi::StencilH; sh->op = s; sh->owned = false;
+  return sh;
+}
+// one application of the K-cycle preconditioner at level 0 (stateful_multigrid.h:734)
+void CAPI(mg_precond)(void* h_, capi_cd* lhs, const capi_cd* rhs, int verbosity)
+{
+  capi::MgH* h = (capi::MgH*)h_;
+  const long n = h->mg->get_lattice(0)->get_size_cv();
+  capi::Stage dl(lhs, n, true, true), dr(rhs, n, true, false);
+  inversion_verbose_struct verb((inversion_verbose_level)verbosity, "[CAPI-MG]: ");
+  h->mg->set_multigrid_level(0);
+  StatefulMultigridMG::mg_preconditioner((capi_cd*)dl, (capi_cd*)dr, (int)n, (void*)h->mg, &verb);
+}
+// outer solve: VPGCR(restart) on level 0 preconditioned by the K-cycle
+// (tests/n13_wilson_kcycle/wilson_kcycle.cpp:459).  restart = -1: unrestarted.
+// info: resSq, iter, success, ops_count, seconds
+void CAPI(mg_solve)(void* h_, int outer_type, capi_cd* x, const capi_cd* b, int max_iter, double tol, int restart, int verbosity, double* info)
+{
+  capi::MgH* h = (capi::MgH*)h_;
+  Stencil2D* s0 = h->mg->get_stencil(0);
+  const long full = h->mg->get_lattice(0)->get_size_cv();
+  const int n = (int)((QMGStencilType)outer_type == QMG_MATVEC_RIGHT_SCHUR ? full / 2 : full);
+  capi::Stage dx(x, full, true, true), db(b, full, true, false);
+  inversion_verbose_struct verb((inversion_verbose_level)verbosity, "[CAPI-MG-OUTER]: ");
+  verb.precond_verbosity = (inversion_verbose_level)verbosity;
+  verb.precond_verb_prefix = "[CAPI-MG-PREC]: ";
+  matrix_op_cplx fn = Stencil2D::get_apply_function((QMGStencilType)outer_type);
+  h->mg->set_multigrid_level(0);
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  inversion_info inv;
+  if (restart == -1)
+    inv = minv_vector_gcr_var_precond((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, fn, (void*)s0,
+                                      StatefulMultigridMG::mg_preconditioner, (void*)h->mg, &verb);
+  else
+    inv = minv_vector_gcr_var_precond_restart((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, restart, fn, (void*)s0,
+                                              StatefulMultigridMG::mg_preconditioner, (void*)h->mg, &verb);
+  capi_barrier();
+  info[4] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  info[0] = inv.resSq; info[1] = inv.iter; info[2] = inv.success ? 1.0 : 0.0; info[3] = inv.ops_count;
+}
+// out: nullvec, krylov, presmooth, postsmooth op counts, total ops, krylov iterations
+void CAPI(mg_tracker)(void* h_, int level, int* out)
+{
+  StatefulMultigridMG* mg = ((capi::MgH*)h_)->mg;
+  out[0] = mg->get_tracker_count(QMG_DSLASH_TYPE_NULLVEC, level);
+  out[1] = mg->get_tracker_count(QMG_DSLASH_TYPE_KRYLOV, level);
+  out[2] = mg->get_tracker_count(QMG_DSLASH_TYPE_PRESMOOTH, level);
+  out[3] = mg->get_tracker_count(QMG_DSLASH_TYPE_POSTSMOOTH, level);
+  out[4] = mg->get_total_count(level);
+  out[5] = mg->get_iterations_count(level);
+}
+void CAPI(mg_reset_tracker)(void* h_) { ((capi::MgH*)h_)->mg->reset_tracker(); }
+// emulated/explicit level operator (multigrid.h:465), prolong / restrict through the MG object
+void CAPI(mg_apply_stencil)(void* h_, int level, int type, capi_cd* lhs, const capi_cd* rhs)
+{
+  capi::MgH* h = (capi::MgH*)h_;
+  const long n = h->mg->get_lattice(level)->get_size_cv();
+  capi::Stage dl(lhs, n, true, true), dr(rhs, n, true, false);
+  h->mg->apply_stencil((capi_cd*)dl, (capi_cd*)dr, level, (QMGStencilType)type);
+}
+int CAPI(mg_storage_counts)(void* h_, int level, int* out)
+{
+  StatefulMultigridMG* mg = ((capi::MgH*)h_)->mg;
+  out[0] = mg->get_storage_number_allocated(level);
+  out[1] = mg->get_storage_number_checked(level);
+  return 0;
+}
+
+} // extern "C"

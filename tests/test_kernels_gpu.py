@@ -1,0 +1,281 @@
+"""Parity of the sm_100a kernels, called through the C ABI (include/qmg_b200.h), against the
+oracle: the reference's own unmodified headers (oracle/_ref/libqmg_ref.so) and the committed
+golden outputs.  Tolerance: 1e-12 relative L2 in fp64 (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import capi
+import latutil
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not capi.have_ref():
+        pytest.skip("oracle/_ref/libqmg_ref.so not built")
+    return capi.Backend("ref")
+
+
+def dev(qmg, a):
+    return qmg.to_device(a)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def make_op(ref, qmg, kind, L):
+    """Build the same operator through the oracle (class API) and through the fill kernels."""
+    if kind == "wilson":
+        lat = ref.lattice(L, L, 2)
+        g = latutil.load_gauge(L)
+        op = lat.wilson(-0.055, g)
+        cl, hp = qmg.fill_wilson(L, L, dev(qmg, g))
+        d = qmg.stencil_desc(L, L, 2, cl, hp, shift=-0.055)
+    elif kind == "staggered":
+        lat = ref.lattice(L, L, 1)
+        g = latutil.load_gauge(L)
+        op = lat.staggered(0.1, g)
+        cl, hp = None, qmg.fill_staggered(L, L, dev(qmg, g))
+        d = qmg.stencil_desc(L, L, 1, None, hp, shift=0.1)
+    elif kind == "laplace":
+        lat = ref.lattice(L, L, 1)
+        g = latutil.load_gauge(L)
+        op = lat.laplace(0.01, g)
+        cl, hp = qmg.fill_laplace(L, L, dev(qmg, g))
+        d = qmg.stencil_desc(L, L, 1, cl, hp, shift=0.01)
+    elif kind.startswith("dwf"):
+        Ls = int(kind[3:])
+        lat = ref.lattice(L, L, 2 * Ls)
+        g = latutil.load_gauge(L)
+        op = lat.dwf(0.05, g, Ls, -1.0)
+        cl, hp = qmg.fill_dwf(L, L, Ls, dev(qmg, g), 0.05)
+        d = qmg.stencil_desc(L, L, 2 * Ls, cl, hp, shift=op.shifts()[0])
+    else:
+        raise ValueError(kind)
+    return lat, op, cl, hp, d
+
+
+@pytest.mark.parametrize("kind,L", [("wilson", 64), ("wilson", 32), ("staggered", 32), ("laplace", 32), ("dwf2", 32), ("dwf4", 32), ("dwf6", 32)])
+def test_fill_and_apply(ref, qmg_gpu, kind, L):
+    qmg = qmg_gpu
+    lat, op, cl, hp, d = make_op(ref, qmg, kind, L)
+    if cl is not None:
+        assert latutil.rel_l2(host(cl), op.get("clover")) < TOL
+    assert latutil.rel_l2(host(hp), op.get("hopping")) < TOL
+    rhs = latutil.gaussian_cv(lat.size_cv, 7)
+    want = op.apply(rhs, 0)
+    out = qmg.cvec(lat.size_cv)
+    qmg.stencil_apply(d, out, dev(qmg, rhs))
+    assert latutil.rel_l2(host(out), want) < TOL
+    op.free()
+
+
+def test_golden_n11(qmg_gpu):
+    """Committed outputs of the reference on l64t64b60, mass -0.055 (tests/n11_wilson_test/wilson_test.cpp:37-43)."""
+    qmg = qmg_gpu
+    gold = np.load(os.path.join(latutil.GOLDEN, "golden_outputs.npz"))
+    L = 64
+    g = latutil.load_gauge(L)
+    cl, hp = qmg.fill_wilson(L, L, dev(qmg, g))
+    d = qmg.stencil_desc(L, L, 2, cl, hp, shift=-0.055)
+    n = L * L * 2
+    rhs = latutil.gaussian_cv(n, int(gold["n11_wilson64_gauss_rhs_seed"][0]))
+    out = qmg.cvec(n)
+    qmg.stencil_apply(d, out, dev(qmg, rhs))
+    assert latutil.rel_l2(host(out), gold["n11_wilson64_gauss_out"]) < TOL
+    pt = np.zeros(n, np.complex128)
+    pt[int(latutil.site_index(32, 32, L, L)) * 2] = 1.0
+    qmg.stencil_apply(d, out, dev(qmg, pt))
+    assert latutil.rel_l2(host(out), gold["n11_wilson64_point_out"]) < TOL
+
+
+def random_stencil(L, nc, seed):
+    rng = np.random.default_rng(seed)
+    V = L * L
+    cl = (rng.normal(size=V * nc * nc) + 1j * rng.normal(size=V * nc * nc))
+    hp = (rng.normal(size=4 * V * nc * nc) + 1j * rng.normal(size=4 * V * nc * nc))
+    # keep the site blocks well conditioned for the rbjacobi inverse
+    cl = cl.reshape(V, nc, nc) + 4.0 * nc * np.eye(nc)[None]
+    return cl.ravel().astype(np.complex128), hp.astype(np.complex128)
+
+
+@pytest.mark.parametrize("nc", [1, 2, 4, 8, 6, 16])
+def test_generic_stencil_pieces(ref, qmg_gpu, nc):
+    """Coarse-operator-shaped dense blocks with all three shifts; every apply_M piece (stencil_2d.h:666-936)."""
+    qmg = qmg_gpu
+    L = 16
+    lat = ref.lattice(L, L, nc)
+    cl, hp = random_stencil(L, nc, 100 + nc)
+    sh, eo, df = 0.3 - 0.1j, 0.05 + 0.02j, (0.07 - 0.03j if nc % 2 == 0 else 0.0)
+    op = lat.generic(cl, hp, sh, eo, df)
+    dcl, dhp = dev(qmg, cl), dev(qmg, hp)
+    d = qmg.stencil_desc(L, L, nc, dcl, dhp, sh, eo, df)
+    rhs = latutil.gaussian_cv(lat.size_cv, 5)
+    drhs = dev(qmg, rhs)
+    acc0 = latutil.gaussian_cv(lat.size_cv, 6)
+    # full apply through the zeroing wrapper
+    out = qmg.cvec(lat.size_cv)
+    qmg.stencil_apply(d, out, drhs)
+    assert latutil.rel_l2(host(out), op.apply(rhs, 0)) < TOL
+    # accumulate flavour == Stencil2D::apply_M
+    out = dev(qmg, acc0)
+    qmg.stencil_apply(d, out, drhs, qmg.APPLY_ALL | qmg.APPLY_ACCUMULATE)
+    assert latutil.rel_l2(host(out), op.apply_piece(0, rhs, lhs=acc0)) < TOL
+    # pieces: clover, eo, oe, hopping, shift
+    for piece, flags in ((1, qmg.APPLY_CLOVER), (2, qmg.APPLY_HOP_TO_EVEN), (3, qmg.APPLY_HOP_TO_ODD),
+                         (4, qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_HOP_TO_ODD), (6, qmg.APPLY_SHIFT)):
+        out = dev(qmg, acc0)
+        qmg.stencil_apply(d, out, drhs, flags | qmg.APPLY_ACCUMULATE)
+        assert latutil.rel_l2(host(out), op.apply_piece(piece, rhs, lhs=acc0)) < TOL, piece
+    # single directions (coarse.h probes)
+    for mu in range(4):
+        out = dev(qmg, acc0)
+        qmg.stencil_apply(d, out, drhs, qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_HOP_TO_ODD | qmg.APPLY_ACCUMULATE, 1 << mu)
+        assert latutil.rel_l2(host(out), op.apply_piece(5, rhs, dir=mu, lhs=acc0)) < TOL, mu
+    op.free()
+
+
+@pytest.mark.parametrize("nc", [2, 8])
+def test_variant_builders(ref, qmg_gpu, nc):
+    """build_dagger_stencil (stencil_2d.h:1080) and build_rbjacobi_stencil (:1452) against the reference."""
+    import ctypes as C
+    qmg = qmg_gpu
+    L = 16
+    lat = ref.lattice(L, L, nc)
+    cl, hp = random_stencil(L, nc, 200 + nc)
+    sh, eo, df = 0.3 - 0.1j, 0.05 + 0.02j, 0.07 - 0.03j
+    op = lat.generic(cl, hp, sh, eo, df)
+    op.build(dagger=True, rbjacobi=True)
+    dcl, dhp = dev(qmg, cl), dev(qmg, hp)
+    d = qmg.stencil_desc(L, L, nc, dcl, dhp, sh, eo, df)
+    dag_cl, dag_hp = qmg.cvec(cl.size), qmg.cvec(hp.size)
+    qmg.check(qmg.lib().qmg_build_dagger(L, L, nc, qmg.ptr(dcl), qmg.ptr(dhp), qmg.ptr(dag_cl), qmg.ptr(dag_hp)))
+    assert latutil.rel_l2(host(dag_cl), op.get("dagger_clover")) < TOL
+    assert latutil.rel_l2(host(dag_hp), op.get("dagger_hopping")) < TOL
+    cinv, rcl, rhp = qmg.cvec(cl.size), qmg.cvec(cl.size), qmg.cvec(hp.size)
+    qmg.check(qmg.lib().qmg_build_rbjacobi(C.byref(d), qmg.ptr(cinv), qmg.ptr(rcl), qmg.ptr(rhp)))
+    assert latutil.rel_l2(host(cinv), op.get("rbjacobi_cinv")) < 1e-11
+    assert latutil.rel_l2(host(rcl), op.get("rbjacobi_clover")) < TOL
+    assert latutil.rel_l2(host(rhp), op.get("rbjacobi_hopping")) < 1e-11
+    # rbjacobi apply: identity clover is not read (stencil_2d.h:1685)
+    rhs = latutil.gaussian_cv(lat.size_cv, 9)
+    d2 = qmg.stencil_desc(L, L, nc, None, rhp)
+    out = qmg.cvec(lat.size_cv)
+    qmg.stencil_apply(d2, out, dev(qmg, rhs), qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_HOP_TO_ODD | qmg.APPLY_IDENTITY_CLOVER)
+    assert latutil.rel_l2(host(out), op.apply(rhs, 2)) < 1e-11
+    op.free()
+
+
+def test_cshift_known_answer(ref, qmg_gpu):
+    """tests/n00_cshift: values = site number on a 6x4 lattice, all four directions, nc 1 and 2."""
+    qmg = qmg_gpu
+    X, Y = 6, 4
+    for nc in (1, 2):
+        lat = ref.lattice(X, Y, nc)
+        xs, ys = latutil.site_coords(X, Y)
+        v = np.repeat((ys * X + xs).astype(np.complex128), nc) + 1j * np.tile(np.arange(nc), X * Y)
+        for cdir, (dx, dy) in ((2, (1, 0)), (3, (0, 1)), (4, (-1, 0)), (5, (0, -1))):
+            out = qmg.cvec(v.size)
+            qmg.check(qmg.lib().qmg_cshift(qmg.ptr(out), qmg.ptr(dev(qmg, v)), cdir, 3, nc, X, Y))
+            got = host(out)
+            want = np.repeat(((((ys + dy) % Y) * X + (xs + dx) % X)).astype(np.complex128), nc) + 1j * np.tile(np.arange(nc), X * Y)
+            assert np.array_equal(got, want)
+            assert np.array_equal(lat.cshift(v, cdir, 3, nc), want)   # the oracle agrees with the known answer
+
+
+def test_halo_slabs_equal_periodic(qmg_gpu):
+    """y-slab sharding: two half-height slabs fed with each other's boundary rows
+    reproduce the single-lattice periodic apply bit for bit."""
+    qmg = qmg_gpu
+    L = 32
+    g = latutil.load_gauge(L)
+    cl, hp = qmg.fill_wilson(L, L, dev(qmg, g))
+    d = qmg.stencil_desc(L, L, 2, cl, hp, shift=-0.055)
+    n = L * L * 2
+    rhs = latutil.gaussian_cv(n, 3)
+    full = qmg.cvec(n)
+    qmg.stencil_apply(d, full, dev(qmg, rhs))
+    full = host(full)
+    import shard
+    nr = 2
+    pieces = []
+    for r in range(nr):
+        sl = shard.Slab(L, L, nr, r)
+        lcl = dev(qmg, sl.take(host(cl), 4))
+        lhp = np.concatenate([sl.take(host(hp)[mu * L * L * 4:(mu + 1) * L * L * 4], 4) for mu in range(4)])
+        lrhs = sl.take(rhs, 2)
+        ym = sl.halo_row(rhs, 2, -1)
+        yp = sl.halo_row(rhs, 2, sl.Yl)
+        dl = qmg.stencil_desc(L, sl.Yl, 2, lcl, dev(qmg, lhp), shift=-0.055, halo_ym=dev(qmg, ym), halo_yp=dev(qmg, yp))
+        out = qmg.cvec(lrhs.size)
+        qmg.stencil_apply(dl, out, dev(qmg, lrhs))
+        pieces.append((sl, host(out)))
+    got = np.zeros(n, np.complex128)
+    for sl, o in pieces:
+        sl.put(got, o, 2)
+    assert np.array_equal(got, full)
+
+
+def test_blas(qmg_gpu):
+    import ctypes as C
+    qmg = qmg_gpu
+    n = 100003
+    x, y = latutil.gaussian_cv(n, 1), latutil.gaussian_cv(n, 2)
+    dx, dy = dev(qmg, x), dev(qmg, y)
+    assert abs(qmg.dot(dx, dy) - np.vdot(x, y)) < 1e-12 * n
+    assert abs(qmg.norm2sq(dx) - np.vdot(x, x).real) < 1e-12 * n
+    a, b = 0.3 - 0.7j, -1.1 + 0.2j
+    lib = qmg.lib()
+    cd = C.c_double
+    qmg.check(lib.qmg_caxpy(cd(a.real), cd(a.imag), qmg.ptr(dx), qmg.ptr(dy), C.c_long(n)))
+    y = y + a * x
+    assert latutil.rel_l2(host(dy), y) < 1e-15
+    qmg.check(lib.qmg_caxpby(cd(a.real), cd(a.imag), qmg.ptr(dx), cd(b.real), cd(b.imag), qmg.ptr(dy), C.c_long(n)))
+    y = a * x + b * y
+    assert latutil.rel_l2(host(dy), y) < 1e-15
+    # fused Krylov update: x += a p ; r -= a q ; |r|^2
+    p_, q_, xx, rr = (latutil.gaussian_cv(n, s) for s in (3, 4, 5, 6))
+    dp, dq, dxx, drr = (dev(qmg, v) for v in (p_, q_, xx, rr))
+    out = C.c_double()
+    qmg.check(lib.qmg_update_xr_norm(cd(a.real), cd(a.imag), qmg.ptr(dp), qmg.ptr(dq), qmg.ptr(dxx), qmg.ptr(drr), C.c_long(n), C.byref(out)))
+    assert latutil.rel_l2(host(dxx), xx + a * p_) < 1e-15
+    assert latutil.rel_l2(host(drr), rr - a * q_) < 1e-15
+    assert abs(out.value - np.vdot(rr - a * q_, rr - a * q_).real) < 1e-12 * n
+    # empty input: reductions return 0 (the reference's loops simply do not execute)
+    qmg.check(lib.qmg_norm2sq(qmg.ptr(dx), C.c_long(0), C.byref(out)))
+    assert out.value == 0.0
+    # multi-dot / multi-axpy (GCR orthogonalisation)
+    vs = [latutil.gaussian_cv(n, 10 + j) for j in range(11)]
+    dvs = [dev(qmg, v) for v in vs]
+    arr = (C.c_void_p * len(dvs))(*[t.data_ptr() for t in dvs])
+    res = (C.c_double * (2 * len(dvs)))()
+    qmg.check(lib.qmg_multi_dot(arr, len(dvs), qmg.ptr(dx), C.c_long(n), res))
+    for j, v in enumerate(vs):
+        assert abs(complex(res[2 * j], res[2 * j + 1]) - np.vdot(v, x)) < 1e-12 * n
+    coef = latutil.gaussian_cv(len(vs), 77)
+    ca = (C.c_double * (2 * len(vs)))(*np.stack([coef.real, coef.imag], 1).ravel())
+    yy = latutil.gaussian_cv(n, 99)
+    dyy = dev(qmg, yy)
+    qmg.check(lib.qmg_multi_axpy(ca, arr, len(dvs), qmg.ptr(dyy), C.c_long(n)))
+    assert latutil.rel_l2(host(dyy), yy + sum(c * v for c, v in zip(coef, vs))) < 1e-14
+
+
+def test_fused_apply_dot(ref, qmg_gpu):
+    qmg = qmg_gpu
+    L = 64
+    g = latutil.load_gauge(L)
+    cl, hp = qmg.fill_wilson(L, L, dev(qmg, g))
+    d = qmg.stencil_desc(L, L, 2, cl, hp, shift=-0.055)
+    n = L * L * 2
+    rhs = latutil.gaussian_cv(n, 21)
+    drhs = dev(qmg, rhs)
+    out = qmg.cvec(n)
+    dotv, nrm = qmg.stencil_apply_dot(d, out, drhs, drhs)
+    o = host(out)
+    assert abs(nrm - np.vdot(o, o).real) < 1e-12 * nrm
+    assert abs(dotv - np.vdot(o, rhs)) < 1e-12 * abs(np.vdot(o, rhs))
