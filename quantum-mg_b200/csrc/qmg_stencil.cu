@@ -37,16 +37,19 @@ struct StencilKArgs
   int hop_to[2];        // hop_to[p]: apply hopping into parity p
   int dir_mask;
   int accumulate;
-  int p_begin;          // first parity written (grid.z runs over n_par parities)
+  int p_begin;          // first parity written
+  int n_par;            // parities written; the parity is the FASTEST block index so that the even and the odd
+                        // output rows y are in flight together and each input row is fetched from HBM once
 };
 
 template <int NC, bool REDUCE>
 __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, double* partials, unsigned int* counter, double* result)
 {
   constexpr int LPS = NC * NC;   // lanes per site
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;   // element inside the row
+  const int bxi = (a.n_par == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int col = bxi * blockDim.x + threadIdx.x;   // element inside the row
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int p = a.p_begin + blockIdx.z;
+  const int p = a.p_begin + ((a.n_par == 2) ? (blockIdx.x & 1) : 0);
   const int k = col / LPS;
   const int c = col % LPS;
   const int c1 = c / NC, c2 = c % NC;
@@ -231,6 +234,7 @@ static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   a.p_begin = 0; n_par = 2;
   if (pieces & QMG_APPLY_EVEN_ROWS_ONLY) { a.p_begin = 0; n_par = 1; }
   if (pieces & QMG_APPLY_ODD_ROWS_ONLY) { a.p_begin = 1; n_par = 1; }
+  a.n_par = n_par;
   return 0;
 }
 
@@ -244,7 +248,7 @@ static int launch_stencil(const StencilKArgs& a, int n_par, bool reduce)
   int by = 256 / bx;
   if (by > a.g.Y) by = a.g.Y;
   dim3 block(bx, by, 1);
-  dim3 grid((row_elems + bx - 1) / bx, (a.g.Y + by - 1) / by, n_par);
+  dim3 grid(((row_elems + bx - 1) / bx) * n_par, (a.g.Y + by - 1) / by, 1);
   if (grid.y > 65535) return fail_msg("qmg_stencil_apply: Y too large for the launch grid");
   if (reduce)
   {

@@ -279,3 +279,91 @@ def test_fused_apply_dot(ref, qmg_gpu):
     o = host(out)
     assert abs(nrm - np.vdot(o, o).real) < 1e-12 * nrm
     assert abs(dotv - np.vdot(o, rhs)) < 1e-12 * abs(np.vdot(o, rhs))
+
+
+# ------------------------------------------------------------------ transfer / coarse operator --
+TRANSFER_CASES = [
+    # (fine X, fine Y, ncf, coarse X, coarse Y, ncc)
+    (16, 16, 2, 4, 4, 8),     # Wilson level 0 -> 1: 4x4 blocks, 32 fine dof per aggregate
+    (8, 8, 8, 2, 2, 8),       # level 1 -> 2: 128 fine dof per aggregate
+    (8, 8, 1, 4, 4, 2),       # 2x2 blocks of a scalar field (n07-style), 4 dof per aggregate
+    (4, 4, 2, 1, 1, 6),       # n05: 4x4 -> a single coarse site, 6 null vectors
+    (12, 6, 1, 4, 2, 3),      # odd block size (3x3), nvec not a power of two
+    (16, 8, 2, 4, 2, 12),     # more than 8 null vectors: two passes
+]
+
+
+def _transfer_pair(ref, qmg, case, seed=0, block_ortho=True):
+    Xf, Yf, ncf, Xc, Yc, ncc = case
+    fl, cl = ref.lattice(Xf, Yf, ncf), ref.lattice(Xc, Yc, ncc)
+    nv = np.stack([latutil.gaussian_cv(fl.size_cv, seed + 50 + v) for v in range(ncc)])
+    tr = capi.Transfer(fl, cl, nv, block_ortho=block_ortho, save_decomp=block_ortho)
+    td = qmg.transfer_desc(Xf, Yf, ncf, Xc, Yc, ncc)
+    dnv = [dev(qmg, nv[v]) for v in range(ncc)]
+    return fl, cl, nv, tr, td, dnv
+
+
+@pytest.mark.parametrize("case", TRANSFER_CASES)
+def test_block_ortho_prolong_restrict(ref, qmg_gpu, case):
+    """transfer.h:514-607 (run twice, :160-173), :455-511; identities of tests/n05_prolong_restrict_test (:85-103)."""
+    qmg = qmg_gpu
+    fl, cl, nv, tr, td, dnv = _transfer_pair(ref, qmg, case)
+    chol = qmg.cvec(cl.size_cm)
+    qmg.block_orthonormalize(td, dnv, chol)
+    qmg.block_orthonormalize(td, dnv, None)
+    want = tr.nullvecs()
+    for v in range(cl.nc):
+        assert latutil.rel_l2(host(dnv[v]), want[v]) < 1e-11, v
+    assert latutil.rel_l2(host(chol), tr.cholesky()) < 1e-11
+    # P and R = P^dagger, accumulating into non-zero destinations
+    cvec, fvec = latutil.gaussian_cv(cl.size_cv, 1), latutil.gaussian_cv(fl.size_cv, 2)
+    f0, c0 = latutil.gaussian_cv(fl.size_cv, 3), latutil.gaussian_cv(cl.size_cv, 4)
+    df = dev(qmg, f0)
+    qmg.prolong(td, dnv, dev(qmg, cvec), df)
+    assert latutil.rel_l2(host(df), tr.prolong(cvec, f0)) < 1e-11
+    dc = dev(qmg, c0)
+    qmg.restrict(td, dnv, dev(qmg, fvec), dc)
+    assert latutil.rel_l2(host(dc), tr.restrict(fvec, c0)) < 1e-11
+    # n05 identities: (1 - P^dag P) v_c = 0 and (1 - P P^dag) on the span of the null vectors
+    df = qmg.cvec(fl.size_cv)
+    qmg.prolong(td, dnv, dev(qmg, cvec), df)
+    dc = qmg.cvec(cl.size_cv)
+    qmg.restrict(td, dnv, df, dc)
+    assert latutil.rel_l2(host(dc), cvec) < 1e-12
+    tr.free()
+
+
+@pytest.mark.parametrize("case,kind", [(TRANSFER_CASES[0], "wilson"), (TRANSFER_CASES[1], "generic"), (TRANSFER_CASES[2], "laplace"),
+                                        (TRANSFER_CASES[3], "wilson"), ((8, 8, 1, 2, 2, 4), "staggered"), ((8, 4, 2, 2, 2, 4), "generic")])
+def test_coarse_build(ref, qmg_gpu, case, kind):
+    """CoarseOperator2D build (coarse.h:90-471) == direct Galerkin R A P; tests/n08_distance1_build_test."""
+    qmg = qmg_gpu
+    Xf, Yf, ncf, Xc, Yc, ncc = case
+    fl, cl, nv, tr, td, dnv = _transfer_pair(ref, qmg, case, seed=7)
+    rng = np.random.default_rng(5)
+    ph = rng.normal(0, 0.4, size=Xf * Yf * 2)
+    g = latutil.phases_to_gauge(ph, Xf, Yf)
+    if kind == "wilson":
+        op = fl.wilson(-0.05, g)
+    elif kind == "laplace":
+        op = fl.laplace(0.1, g)
+    elif kind == "staggered":
+        op = fl.staggered(0.1, g)
+    else:
+        c_, h_ = random_stencil(Xf, ncf, 31) if Xf == Yf else (None, None)
+        if c_ is None:
+            V = Xf * Yf
+            c_ = latutil.gaussian_cv(V * ncf * ncf, 41)
+            h_ = latutil.gaussian_cv(4 * V * ncf * ncf, 42)
+        op = fl.generic(c_, h_, 0.2, 0.0, 0.0)
+    fcl, fhp = op.get("clover"), op.get("hopping")
+    dcl = None if fcl is None else dev(qmg, fcl)
+    dhp = None if fhp is None else dev(qmg, fhp)
+    fd = qmg.stencil_desc(Xf, Yf, ncf, dcl, dhp)
+    want = tr.coarse_operator(op, is_chiral=False)
+    onv = [dev(qmg, v) for v in tr.nullvecs()]
+    ccl, chp = qmg.coarse_build(td, fd, onv)
+    assert latutil.rel_l2(host(ccl), want.get("clover")) < 1e-11
+    wh = want.get("hopping")
+    assert np.linalg.norm(host(chp) - wh) < 1e-11 * max(1.0, np.linalg.norm(wh))
+    want.free(); tr.free(); op.free()
