@@ -1,0 +1,382 @@
+// quantum-mg on B200 -- StatefulMultigridMG: the recursive K-cycle preconditioner
+// (/root/reference/multigrid/stateful_multigrid.h:43-1060).  Control flow stays on the host, as in the reference;
+// every vector it touches is a device vector from the per-level pools and every operation inside is a kernel of
+// libqmg_b200.so: MR pre-/post-smoothing, residual, restrict, recursive flexible-GCR (or coarsest GCR / CG) solve,
+// prolong and correction.  Operator applications are counted per level and phase exactly like the reference
+// (DslashTrackerMG), which is the observable the parity tests compare.
+#ifndef QMG_B200_STATEFUL_MULTIGRID
+#define QMG_B200_STATEFUL_MULTIGRID
+
+#include <iostream>
+#include <string>
+#include <vector>
+#include "blas/generic_vector.h"
+#include "inverters/generic_minres.h"
+#include "inverters/generic_cg.h"
+#include "inverters/generic_gcr.h"
+#include "inverters/generic_gcr_var_precond.h"
+#include "interfaces/arpack/generic_arpack.h"
+#include "lattice/lattice.h"
+#include "transfer/transfer.h"
+#include "stencil/stencil_2d.h"
+#include "multigrid/multigrid.h"
+
+enum QMGDslashType
+{
+  QMG_DSLASH_TYPE_NULLVEC = 0,
+  QMG_DSLASH_TYPE_KRYLOV = 1,
+  QMG_DSLASH_TYPE_PRESMOOTH = 2,
+  QMG_DSLASH_TYPE_POSTSMOOTH = 3,
+};
+
+class StatefulMultigridMG : public MultigridMG
+{
+private:
+  StatefulMultigridMG(StatefulMultigridMG const&);
+  StatefulMultigridMG& operator=(StatefulMultigridMG const&);
+  int current_level;
+
+public:
+  // how the level below a transfer is solved and smoothed (stateful_multigrid.h:62-114)
+  struct LevelSolveMG
+  {
+    QMGStencilType fine_stencil_app;   // original, right Jacobi or Schur
+    double intermediate_tol; int intermediate_iters; int intermediate_restart_freq;
+    double pre_tol; int pre_iters; bool pre_cgne;
+    double post_tol; int post_iters; bool post_cgne;
+    LevelSolveMG()
+      : fine_stencil_app(QMG_MATVEC_ORIGINAL), intermediate_tol(1e-20), intermediate_iters(10000000), intermediate_restart_freq(32),
+        pre_tol(1e-20), pre_iters(1000000), pre_cgne(false), post_tol(1e-20), post_iters(1000000), post_cgne(false) { }
+  };
+
+  // operator applications per phase and Krylov iterations of one level (stateful_multigrid.h:118-200)
+  class DslashTrackerMG
+  {
+    DslashTrackerMG(DslashTrackerMG const&);
+    DslashTrackerMG& operator=(DslashTrackerMG const&);
+    int counts[4];
+    int iterations;
+    int total;
+  public:
+    DslashTrackerMG() { reset_tracker(); }
+    void add_tracker_count(QMGDslashType type, int accum) { counts[type] += accum; total += accum; }
+    void add_iterations_count(int accum) { iterations += accum; }
+    void shift_all_to_nullvec()
+    {
+      counts[QMG_DSLASH_TYPE_NULLVEC] += counts[QMG_DSLASH_TYPE_KRYLOV] + counts[QMG_DSLASH_TYPE_PRESMOOTH] + counts[QMG_DSLASH_TYPE_POSTSMOOTH];
+      counts[QMG_DSLASH_TYPE_KRYLOV] = counts[QMG_DSLASH_TYPE_PRESMOOTH] = counts[QMG_DSLASH_TYPE_POSTSMOOTH] = 0;
+      iterations = 0;
+    }
+    int get_tracker_count(QMGDslashType type) { return counts[type]; }
+    int get_total_count() { return total; }
+    int get_iterations_count() { return iterations; }
+    void reset_tracker() { counts[0] = counts[1] = counts[2] = counts[3] = 0; total = 0; iterations = 0; }
+  };
+
+  // the coarsest solve (stateful_multigrid.h:204-241); deflation needs ARPACK and is outside this build (NO_ARPACK)
+  struct CoarsestSolveMG
+  {
+    QMGStencilType coarsest_stencil_app;
+    double coarsest_tol; int coarsest_iters; int coarsest_restart_freq;
+    double normal_shift;
+    CoarsestSolveMG() : coarsest_stencil_app(QMG_MATVEC_ORIGINAL), coarsest_tol(1e-20), coarsest_iters(100000000), coarsest_restart_freq(32), normal_shift(0.0) { }
+  };
+
+protected:
+  std::vector<LevelSolveMG*> level_solve_list;
+  std::vector<DslashTrackerMG*> dslash_tracker_list;
+  CoarsestSolveMG* coarsest_solve;
+
+  static void check_level_solve(LevelSolveMG* s, const char* where)
+  {
+    if (s->fine_stencil_app != QMG_MATVEC_ORIGINAL && s->fine_stencil_app != QMG_MATVEC_RIGHT_JACOBI && s->fine_stencil_app != QMG_MATVEC_RIGHT_SCHUR)
+      std::cout << "[QMG-ERROR]: In StatefulMultigridMG:;" << where << ", LevelSolveMG::fine_stencil_app should only be original, right jacobi, or schur.\n";
+  }
+  void pushed(LevelSolveMG* s) { level_solve_list.push_back(s); dslash_tracker_list.push_back(new DslashTrackerMG()); }
+  bool tracker_ok(int i, const char* what)
+  {
+    if (i >= 0 && i < num_levels) return true;
+    std::cout << "[QMG-ERROR]: Out of range: Cannot " << what << " at level " << i << ".\n";
+    return false;
+  }
+
+public:
+  StatefulMultigridMG(Lattice2D* in_lat, Stencil2D* in_stencil, CoarsestSolveMG* in_coarsest_solve)
+    : MultigridMG(in_lat, in_stencil), current_level(0), coarsest_solve(in_coarsest_solve)
+  { dslash_tracker_list.push_back(new DslashTrackerMG()); }
+  ~StatefulMultigridMG() { for (size_t i = 0; i < dslash_tracker_list.size(); i++) delete dslash_tracker_list[i]; }
+
+  // ---- the level cursor the preconditioner callback reads (the object is stateful and not re-entrant)
+  void set_multigrid_level(int level)
+  {
+    if (level >= 0 && level < get_num_levels()) current_level = level;
+    else std::cout << "[QMG-ERROR]: Out of range: StatefulMultigridMG->current_level " << level << " is outside of [0,max_level-1].\n";
+  }
+  void go_finer()
+  {
+    if (current_level > 0) current_level--;
+    else std::cout << "[QMG-ERROR]: Out of range: Cannot go finer than the top level in StatefulMultigridMG.\n";
+  }
+  void go_coarser()
+  {
+    if (current_level < get_num_levels() - 2) current_level++;
+    else std::cout << "[QMG-ERROR]: Out of range: Cannot go coarser than the second-coarsest level in StatefulMultigridMG.\n";
+  }
+  int get_multigrid_level() { return current_level; }
+  LevelSolveMG* get_level_solve(int i)
+  {
+    if (i >= 0 && i < get_num_levels() - 1 && level_solve_list[i] != 0) return level_solve_list[i];
+    std::cout << "[QMG-ERROR]: Out of range: LevelSolveMG level " << i << " does not exist in StatefulMultigridMG object.\n";
+    return 0;
+  }
+  LevelSolveMG* get_level_solve() { return get_level_solve(current_level); }
+  CoarsestSolveMG* get_coarsest_solve() { return coarsest_solve; }
+
+  // ---- level management: the MultigridMG overloads, each with and without a LevelSolveMG (stateful_multigrid.h:374-496)
+  void push_level(Lattice2D* new_lat, TransferMG* new_transfer, bool build_stencil = false, bool is_chiral = false,
+                  QMGMultigridPrecondStencil build_stencil_from = QMG_MULTIGRID_PRECOND_ORIGINAL,
+                  CoarseOperator2D::QMGCoarseBuildStencil build_extra = CoarseOperator2D::QMG_COARSE_BUILD_ORIGINAL, complex<double>** nvecs = 0)
+  { MultigridMG::push_level(new_lat, new_transfer, build_stencil, is_chiral, build_stencil_from, build_extra, nvecs); pushed(0); }
+  void push_level(Lattice2D* new_lat, TransferMG* new_transfer, bool build_stencil, bool is_chiral, QMGMultigridPrecondStencil build_stencil_from, complex<double>** nvecs)
+  { MultigridMG::push_level(new_lat, new_transfer, build_stencil, is_chiral, build_stencil_from, nvecs); pushed(0); }
+  void push_level(Lattice2D* new_lat, TransferMG* new_transfer, complex<double>** nvecs)
+  { MultigridMG::push_level(new_lat, new_transfer, nvecs); pushed(0); }
+  void push_level(Lattice2D* new_lat, TransferMG* new_transfer, LevelSolveMG* in_solve, bool build_stencil = false, bool is_chiral = false,
+                  QMGMultigridPrecondStencil build_stencil_from = QMG_MULTIGRID_PRECOND_ORIGINAL,
+                  CoarseOperator2D::QMGCoarseBuildStencil build_extra = CoarseOperator2D::QMG_COARSE_BUILD_ORIGINAL, complex<double>** nvecs = 0)
+  {
+    MultigridMG::push_level(new_lat, new_transfer, build_stencil, is_chiral, build_stencil_from, build_extra, nvecs);
+    check_level_solve(in_solve, "push_level");
+    pushed(in_solve);
+  }
+  void push_level(Lattice2D* new_lat, TransferMG* new_transfer, LevelSolveMG* in_solve, bool build_stencil, bool is_chiral,
+                  QMGMultigridPrecondStencil build_stencil_from, complex<double>** nvecs)
+  {
+    MultigridMG::push_level(new_lat, new_transfer, build_stencil, is_chiral, build_stencil_from, nvecs);
+    check_level_solve(in_solve, "push_level");
+    pushed(in_solve);
+  }
+  void push_level(Lattice2D* new_lat, TransferMG* new_transfer, LevelSolveMG* in_solve, complex<double>** nvecs)
+  {
+    MultigridMG::push_level(new_lat, new_transfer, nvecs);
+    check_level_solve(in_solve, "push_level");
+    pushed(in_solve);
+  }
+  void pop_level()
+  {
+    if (num_levels == 1) { MultigridMG::pop_level(); return; }
+    level_solve_list.pop_back();
+    delete dslash_tracker_list.back();
+    dslash_tracker_list.pop_back();
+    MultigridMG::pop_level();
+  }
+  void update_level(int level, Lattice2D* new_lat, TransferMG* new_transfer, LevelSolveMG* in_solve, bool build_stencil = false, bool is_chiral = false,
+                    QMGMultigridPrecondStencil build_stencil_from = QMG_MULTIGRID_PRECOND_ORIGINAL,
+                    CoarseOperator2D::QMGCoarseBuildStencil build_extra = CoarseOperator2D::QMG_COARSE_BUILD_ORIGINAL, complex<double>** nvecs = 0)
+  {
+    if (in_solve->fine_stencil_app != QMG_MATVEC_ORIGINAL && in_solve->fine_stencil_app != QMG_MATVEC_RIGHT_JACOBI && in_solve->fine_stencil_app != QMG_MATVEC_RIGHT_SCHUR)
+    { check_level_solve(in_solve, "update_level"); return; }
+    MultigridMG::update_level(level, new_lat, new_transfer, build_stencil, is_chiral, build_stencil_from, build_extra, nvecs);
+    if (level >= 1 && level < num_levels) level_solve_list[level - 1] = in_solve;
+  }
+  void update_level(int level, Lattice2D* new_lat, TransferMG* new_transfer, LevelSolveMG* in_solve, bool build_stencil, bool is_chiral,
+                    QMGMultigridPrecondStencil build_stencil_from, complex<double>** nvecs)
+  { update_level(level, new_lat, new_transfer, in_solve, build_stencil, is_chiral, build_stencil_from, CoarseOperator2D::QMG_COARSE_BUILD_ORIGINAL, nvecs); }
+
+  // ---- counters (stateful_multigrid.h:500-609)
+  void add_tracker_count(QMGDslashType type, int accum, int i) { if (tracker_ok(i, "update tracker")) dslash_tracker_list[i]->add_tracker_count(type, accum); }
+  void add_iterations_count(int accum, int i) { if (tracker_ok(i, "update tracker")) dslash_tracker_list[i]->add_iterations_count(accum); }
+  void shift_all_to_nullvec(int i) { if (tracker_ok(i, "shift to null vectors")) dslash_tracker_list[i]->shift_all_to_nullvec(); }
+  int get_tracker_count(QMGDslashType type, int i) { return tracker_ok(i, "query tracker") ? dslash_tracker_list[i]->get_tracker_count(type) : -1; }
+  int get_total_count(int i) { return tracker_ok(i, "query tracker") ? dslash_tracker_list[i]->get_total_count() : -1; }
+  int get_iterations_count(int i) { return tracker_ok(i, "query tracker") ? dslash_tracker_list[i]->get_iterations_count() : -1; }
+  std::vector<double> query_average_iterations()
+  {
+    std::vector<double> avg(num_levels);
+    avg[0] = dslash_tracker_list[0]->get_iterations_count();
+    for (int i = 1; i < num_levels; i++)
+      avg[i] = ((double)dslash_tracker_list[i]->get_iterations_count()) / ((double)dslash_tracker_list[i - 1]->get_iterations_count());
+    return avg;
+  }
+  void reset_tracker(int i = -1)
+  {
+    if (i == -1) for (int j = 0; j < num_levels; j++) dslash_tracker_list[j]->reset_tracker();
+    else if (tracker_ok(i, "reset tracker")) dslash_tracker_list[i]->reset_tracker();
+  }
+
+protected:
+  // A + sigma for the shifted coarsest normal-equation solve (stateful_multigrid.h:716-729)
+  struct ShiftedFunctionStruct { matrix_op_cplx function; void* extra_data; complex<double> extra_shift; int length; };
+  static void shift_function(complex<double>* out, complex<double>* in, void* data)
+  {
+    ShiftedFunctionStruct* s = (ShiftedFunctionStruct*)data;
+    s->function(out, in, s->extra_data);
+    caxpy(s->extra_shift, in, out, s->length);
+  }
+
+  // z = MR_smooth(A_type, b) from a zero start; with cgne the smoother runs on A A^dag and z = A^dag z'.  Returns the operator applications spent.
+  static int smooth(Stencil2D* op, ArrayStorageMG<complex<double> >* pool, QMGStencilType type, bool cgne, int iters, double tol,
+                    complex<double>* z, complex<double>* b, int n_solve, long n_full)
+  {
+    if (cgne && (type == QMG_MATVEC_ORIGINAL || type == QMG_MATVEC_RIGHT_JACOBI))
+    {
+      const bool orig = (type == QMG_MATVEC_ORIGINAL);
+      complex<double>* zp = pool->check_out();
+      zero_vector(zp, n_full);
+      inversion_info inv = minv_vector_minres(zp, b, n_solve, iters, tol, 0.85,
+                                              Stencil2D::get_apply_function(orig ? QMG_MATVEC_M_MDAGGER : QMG_MATVEC_RBJ_M_MDAGGER), (void*)op);
+      op->apply_M(z, zp, orig ? QMG_MATVEC_DAGGER : QMG_MATVEC_RBJ_DAGGER);
+      pool->check_in(zp);
+      return 2 * inv.ops_count + 1;
+    }
+    inversion_info inv = minv_vector_minres(z, b, n_solve, iters, tol, 0.85, Stencil2D::get_apply_function(type), (void*)op);
+    return inv.ops_count;
+  }
+
+public:
+  // One K-cycle application at the current level: lhs ~ A^-1 rhs.  Signature of a quantum-linalg preconditioner;
+  // extra_data is the StatefulMultigridMG (stateful_multigrid.h:734).
+  static void mg_preconditioner(complex<double>* lhs, complex<double>* rhs, int size, void* extra_data, inversion_verbose_struct* verb)
+  {
+    (void)size;
+    StatefulMultigridMG* mg = (StatefulMultigridMG*)extra_data;
+    const int level = mg->get_multigrid_level();
+    const int nlev = mg->get_num_levels();
+
+    LevelSolveMG* ls = mg->get_level_solve();
+    if (ls == 0) { std::cout << "[QMG-MG-SOLVE-ERROR]: Level solve for level " << level << " does not exist.\n"; return; }
+    const QMGStencilType ftype = ls->fine_stencil_app;
+    const long nf = mg->get_lattice(level)->get_size_cv();
+    const int nf_solve = (int)(ftype == QMG_MATVEC_RIGHT_SCHUR ? nf / 2 : nf);
+    if (nlev == 1) { copy_vector(lhs, rhs, nf_solve); return; }
+
+    Stencil2D* fine = mg->get_stencil(level);
+    Stencil2D* coarse = mg->get_stencil(level + 1);
+    TransferMG* transfer = mg->get_transfer(level);
+    ArrayStorageMG<complex<double> >* fpool = mg->get_storage(level);
+    ArrayStorageMG<complex<double> >* cpool = mg->get_storage(level + 1);
+    const long nc = mg->get_lattice(level + 1)->get_size_cv();
+    matrix_op_cplx fine_op = Stencil2D::get_apply_function(ftype);
+
+    // what the solvers below this level print with
+    inversion_verbose_struct verb2(VERB_SUMMARY, std::string(" "));
+    if (verb == 0 || verb->verbosity == VERB_NONE) { verb2.verbosity = VERB_NONE; verb2.precond_verbosity = VERB_NONE; }
+    else verb2.precond_verbosity = VERB_SUMMARY;
+    verb2.verb_prefix = std::string(2 * (level + 1), ' ') + "[QMG-MG-SOLVE-INFO]: Level " + std::to_string(level + 1) + " ";
+
+    // the solve one level down: an intermediate level (recursive K-cycle) or the coarsest
+    const bool coarsest = (level == nlev - 2);
+    QMGStencilType ctype; int c_iters; double c_tol; int c_restart;
+    if (!coarsest)
+    {
+      LevelSolveMG* next = mg->get_level_solve(level + 1);
+      ctype = next->fine_stencil_app; c_iters = next->intermediate_iters; c_tol = next->intermediate_tol; c_restart = next->intermediate_restart_freq;
+    }
+    else
+    {
+      CoarsestSolveMG* cs = mg->get_coarsest_solve();
+      ctype = cs->coarsest_stencil_app; c_iters = cs->coarsest_iters; c_tol = cs->coarsest_tol; c_restart = cs->coarsest_restart_freq;
+    }
+    matrix_op_cplx coarse_op = Stencil2D::get_apply_function(ctype);
+    const int nc_solve = (int)(ctype == QMG_MATVEC_RIGHT_SCHUR ? nc / 2 : nc);
+
+    // 1. pre-smooth: z1 ~ A^-1 rhs, r1 = rhs - A z1
+    complex<double>* z1 = fpool->check_out();
+    complex<double>* r1 = fpool->check_out();
+    zero_vector(z1, nf);
+    if (ls->pre_iters > 0)
+    {
+      const int ops = smooth(fine, fpool, ftype, ls->pre_cgne, ls->pre_iters, ls->pre_tol, z1, rhs, nf_solve, nf);
+      mg->add_tracker_count(QMG_DSLASH_TYPE_PRESMOOTH, ops, level);
+      complex<double>* Az = fpool->check_out();
+      fine_op(Az, z1, (void*)fine);
+      mg->add_tracker_count(QMG_DSLASH_TYPE_PRESMOOTH, 1, level);
+      caxpbyz(1.0, rhs, -1.0, Az, r1, nf_solve);
+      fpool->check_in(Az);
+    }
+    else
+    {
+      copy_vector(r1, rhs, nf_solve);
+      copy_vector(z1, rhs, nf_solve);
+    }
+
+    // 2. restrict the residual and bring it to the form the coarse system is solved in
+    complex<double>* r_c = cpool->check_out();
+    zero_vector(r_c, nc);
+    transfer->restrict_f2c(r1, r_c);
+    fpool->check_in(r1);
+    const double rnorm = sqrt(norm2sq(r_c, nc));
+    complex<double>* r_c_prep = cpool->check_out();
+    zero_vector(r_c_prep, nc);
+    coarse->prepare_M(r_c_prep, r_c, ctype);
+    const double rnorm_prep = sqrt(norm2sq(r_c_prep, nc));
+    const double tol = c_tol * rnorm / rnorm_prep;
+
+    // 3. coarse solve from a zero start
+    complex<double>* e_c = cpool->check_out();
+    zero_vector(e_c, nc);
+    inversion_info inv;
+    if (coarsest)
+    {
+      const bool normal = (ctype == QMG_MATVEC_M_MDAGGER || ctype == QMG_MATVEC_MDAGGER_M || ctype == QMG_MATVEC_RBJ_M_MDAGGER || ctype == QMG_MATVEC_RBJ_MDAGGER_M);
+      ShiftedFunctionStruct shifted;
+      matrix_op_cplx op = coarse_op; void* op_data = (void*)coarse;
+      if (normal && mg->get_coarsest_solve()->normal_shift != 0.0)
+      {
+        shifted.function = coarse_op; shifted.extra_data = (void*)coarse;
+        shifted.extra_shift = mg->get_coarsest_solve()->normal_shift; shifted.length = nc_solve;
+        op = shift_function; op_data = (void*)&shifted;
+      }
+      if (!normal)
+        inv = (c_restart == -1) ? minv_vector_gcr(e_c, r_c_prep, nc_solve, c_iters, tol, op, op_data, &verb2)
+                                : minv_vector_gcr_restart(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, op, op_data, &verb2);
+      else
+        inv = (c_restart == -1) ? minv_vector_cg(e_c, r_c_prep, nc_solve, c_iters, tol, op, op_data, &verb2)
+                                : minv_vector_cg_restart(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, op, op_data, &verb2);
+    }
+    else
+    {
+      mg->go_coarser();
+      inv = (c_restart == -1) ? minv_vector_gcr_var_precond(e_c, r_c_prep, nc_solve, c_iters, tol, coarse_op, (void*)coarse, mg_preconditioner, (void*)mg, &verb2)
+                              : minv_vector_gcr_var_precond_restart(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, coarse_op, (void*)coarse, mg_preconditioner, (void*)mg, &verb2);
+      mg->go_finer();
+    }
+    mg->add_tracker_count(QMG_DSLASH_TYPE_KRYLOV, inv.ops_count, level + 1);
+    mg->add_iterations_count(inv.iter, level + 1);
+    cpool->check_in(r_c_prep);
+
+    // 4. undo the preparation, prolong, correct: lhs = z1 + P e
+    complex<double>* e_full = cpool->check_out();
+    zero_vector(e_full, nc);
+    coarse->reconstruct_M(e_full, e_c, r_c, ctype);
+    cpool->check_in(r_c);
+    cpool->check_in(e_c);
+    complex<double>* z2 = fpool->check_out();
+    zero_vector(z2, nf);
+    transfer->prolong_c2f(e_full, z2);
+    if (ctype == QMG_MATVEC_RIGHT_SCHUR) zero_vector(z2 + nf / 2, nf / 2);   // stateful_multigrid.h:1012
+    cpool->check_in(e_full);
+    cxpyz(z1, z2, lhs, nf_solve);
+    fpool->check_in(z1);
+    fpool->check_in(z2);
+
+    // 5. post-smooth on the new residual
+    if (ls->post_iters > 0)
+    {
+      complex<double>* Ax = fpool->check_out();
+      complex<double>* r2 = fpool->check_out();
+      fine_op(Ax, lhs, (void*)fine);
+      caxpbyz(1.0, rhs, -1.0, Ax, r2, nf_solve);
+      fpool->check_in(Ax);
+      complex<double>* z3 = fpool->check_out();
+      zero_vector(z3, nf);
+      const int ops = smooth(fine, fpool, ftype, ls->post_cgne, ls->post_iters, ls->post_tol, z3, r2, nf_solve, nf);
+      mg->add_tracker_count(QMG_DSLASH_TYPE_POSTSMOOTH, ops, level);
+      cxpy(z3, lhs, nf_solve);
+      fpool->check_in(r2);
+      fpool->check_in(z3);
+    }
+  }
+};
+
+#endif

@@ -43,10 +43,18 @@ long qmg_kernel_launches(void);           /* kernels launched by this library so
 
 /* allocate_vector / deallocate_vector (qlinalg; stencil/stencil_2d.h:220,299) */
 int qmg_malloc(void** dptr, size_t bytes);
-int qmg_free(void* dptr);
+int qmg_free(void* dptr);                 /* parks the block in a size-keyed cache; qmg_trim returns parked blocks to the driver */
+int qmg_trim(void);
+size_t qmg_cached_bytes(void);
 int qmg_memcpy_h2d(void* dst, const void* src, size_t bytes);
 int qmg_memcpy_d2h(void* dst, const void* src, size_t bytes);
 int qmg_memcpy_d2d(void* dst, const void* src, size_t bytes);
+/* Allocation mode of qmg_malloc: 0 = cudaMalloc (default), 1 = cudaMallocManaged with the device as preferred
+ * location, so that UNMODIFIED reference drivers, which index vectors from host code
+ * (e.g. tests/n11_wilson_test/wilson_test.cpp:96), still run.  Also selectable with the environment
+ * variable QMG_MANAGED=1 read at qmg_init. */
+int qmg_set_alloc_mode(int managed);
+int qmg_get_alloc_mode(void);
 int qmg_malloc_host(void** hptr, size_t bytes);   /* pinned host staging */
 int qmg_free_host(void* hptr);
 
@@ -125,6 +133,13 @@ int qmg_cxty(const qmg_cplx* x, qmg_cplx* y, long n);                           
 int qmg_conj(qmg_cplx* x, long n);                                                     /* conj_vector */
 int qmg_cinvx(qmg_cplx* x, long n);                                                    /* cinvx */
 int qmg_polar(qmg_cplx* x, long n);                                                    /* polar: x = exp(i Re x) */
+/* per-element maps used by the block (bi-)orthonormalisation (transfer/transfer.h:360-376,583,736):
+ * op 0: x -> |x|            (abs_vector)
+ *    1: x -> 1/sqrt(Re x)   (inv_real_sqrt)
+ *    2: x -> 1/|x|          (inv_abs_sqrt)
+ *    3: x -> e^{i arg x}/sqrt|x|  (inv_phase_abs_sqrt)
+ *    4: x -> arg x          (arg_vector) */
+int qmg_elementwise(int op, qmg_cplx* x, long n);
 /* strided flavours (the *_blas family, operators/wilson.h:79-125): element k at x[k*stride] */
 int qmg_zero_strided(qmg_cplx* x, long stride, long n);
 int qmg_constant_strided(qmg_cplx* x, long stride, double re, double im, long n);
@@ -138,6 +153,8 @@ int qmg_dot(const qmg_cplx* x, const qmg_cplx* y, long n, double* result2);     
 int qmg_norm2sq(const qmg_cplx* x, long n, double* result);                            /* norm2sq */
 int qmg_diffnorm2sq(const qmg_cplx* x, const qmg_cplx* y, long n, double* result);     /* diffnorm2sq */
 int qmg_norminf(const qmg_cplx* x, long n, double* result);                            /* norminf */
+/* <x|y> and |x|^2 in one pass: result3 = { Re<x|y>, Im<x|y>, |x|^2 }  (MR / GCR: alpha = <Ap|r>/<Ap|Ap>) */
+int qmg_dot_norm(const qmg_cplx* x, const qmg_cplx* y, long n, double* result3);
 /* k dot products against one vector in one pass: result[2j..] = <xs[j]|y> (GCR orthogonalisation). xs: HOST array of k device pointers. */
 int qmg_multi_dot(const qmg_cplx* const* xs_host, int k, const qmg_cplx* y, long n, double* result2k);
 /* fused Krylov updates */
@@ -145,6 +162,8 @@ int qmg_multi_dot(const qmg_cplx* const* xs_host, int k, const qmg_cplx* y, long
 int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p, const qmg_cplx* q, qmg_cplx* x, qmg_cplx* r, long n, double* result);
 /* y += sum_j a_j xs[j]   (GCR: p_k += sum beta_i p_i) ; a: HOST 2k doubles; xs: HOST array of k device pointers */
 int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y, long n);
+/* y = x0 + sum_j a_j xs[j]   (GCR: p_k = r + sum beta_i p_i without a separate copy); x0 == y allowed */
+int qmg_multi_axpyz(const double* a_host, const qmg_cplx* const* xs_host, int k, const qmg_cplx* x0, qmg_cplx* y, long n);
 /* gaussian fill, counter-based (Philox) so results do not depend on the launch shape */
 int qmg_gaussian(qmg_cplx* x, long n, uint64_t seed, uint64_t stream_id, double dev);
 

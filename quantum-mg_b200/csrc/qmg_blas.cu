@@ -158,6 +158,23 @@ int qmg_polar(qmg_cplx* x_, long n)
   return launch_ew(n, [=] __device__(long i) { double s, c; sincos(x[i].x, &s, &c); x[i] = cmake(c, s); });
 }
 
+int qmg_elementwise(int op, qmg_cplx* x_, long n)
+{
+  QMG_REQUIRE_INIT();
+  cd* x = CD(x_);
+  switch (op)
+  {
+    case 0: return launch_ew(n, [=] __device__(long i) { x[i] = cmake(hypot(x[i].x, x[i].y), 0.0); });
+    case 1: return launch_ew(n, [=] __device__(long i) { x[i] = cmake(1.0 / sqrt(x[i].x), 0.0); });
+    case 2: return launch_ew(n, [=] __device__(long i) { x[i] = cmake(1.0 / hypot(x[i].x, x[i].y), 0.0); });
+    case 3: return launch_ew(n, [=] __device__(long i) {
+      const double r = 1.0 / sqrt(hypot(x[i].x, x[i].y)), th = atan2(x[i].y, x[i].x);
+      double s, c; sincos(th, &s, &c); x[i] = cmake(r * c, r * s); });
+    case 4: return launch_ew(n, [=] __device__(long i) { x[i] = cmake(atan2(x[i].y, x[i].x), 0.0); });
+    default: return fail_msg("qmg_elementwise: unknown op");
+  }
+}
+
 int qmg_zero_strided(qmg_cplx* x_, long stride, long n)
 {
   QMG_REQUIRE_INIT();
@@ -215,6 +232,18 @@ int qmg_dot(const qmg_cplx* x_, const qmg_cplx* y_, long n, double* result2)
     acc[0] += a.x * b.x + a.y * b.y;
     acc[1] += a.x * b.y - a.y * b.x;
   }, result2);
+}
+
+int qmg_dot_norm(const qmg_cplx* x_, const qmg_cplx* y_, long n, double* result3)
+{
+  QMG_REQUIRE_INIT();
+  const cd* x = CCD(x_); const cd* y = CCD(y_);
+  return launch_reduce<3>(n, [=] __device__(long i, double (&acc)[3]) {
+    cd a = x[i], b = y[i];
+    acc[0] += a.x * b.x + a.y * b.y;
+    acc[1] += a.x * b.y - a.y * b.x;
+    acc[2] += a.x * a.x + a.y * a.y;
+  }, result3);
 }
 
 int qmg_norm2sq(const qmg_cplx* x_, long n, double* result)
@@ -326,8 +355,9 @@ static int multi_dot_pass(const qmg_cplx* const* xs, int k, const cd* y, long n,
 }
 
 template <int K>
-static int multi_axpy_pass(const double* a_host, const qmg_cplx* const* xs, int k, cd* y, long n)
+static int multi_axpy_pass(const double* a_host, const qmg_cplx* const* xs, int k, cd* y, long n, const cd* x0 = nullptr)
 {
+  if (x0 == nullptr) x0 = y;
   PtrPack<K> pk; CoefPack<K> ck;
   for (int j = 0; j < K; j++)
   {
@@ -335,7 +365,7 @@ static int multi_axpy_pass(const double* a_host, const qmg_cplx* const* xs, int 
     ck.a[j] = j < k ? cmake(a_host[2 * j], a_host[2 * j + 1]) : cmake(0.0, 0.0);
   }
   return launch_ew(n, [=] __device__(long i) {
-    cd t = y[i];
+    cd t = x0[i];
 #pragma unroll
     for (int j = 0; j < K; j++) cfma(t, ck.a[j], pk.p[j][i]);
     y[i] = t;
@@ -364,23 +394,31 @@ int qmg_multi_dot(const qmg_cplx* const* xs_host, int k, const qmg_cplx* y_, lon
   return 0;
 }
 
-int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y_, long n)
+int qmg_multi_axpyz(const double* a_host, const qmg_cplx* const* xs_host, int k, const qmg_cplx* x0_, qmg_cplx* y_, long n)
 {
   QMG_REQUIRE_INIT();
   cd* y = CD(y_);
+  const cd* x0 = CCD(x0_);
+  if (k <= 0) return (x0 != nullptr && x0 != y) ? qmg_copy(y_, x0_, n) : 0;
   int done = 0;
   while (done < k)
   {
     int left = k - done, rc, take;
-    if (left >= 8) { take = 8; rc = multi_axpy_pass<8>(a_host + 2 * done, xs_host + done, take, y, n); }
-    else if (left > 4) { take = left; rc = multi_axpy_pass<8>(a_host + 2 * done, xs_host + done, take, y, n); }
-    else if (left > 2) { take = left; rc = multi_axpy_pass<4>(a_host + 2 * done, xs_host + done, take, y, n); }
-    else if (left == 2) { take = 2; rc = multi_axpy_pass<2>(a_host + 2 * done, xs_host + done, take, y, n); }
-    else { take = 1; rc = multi_axpy_pass<1>(a_host + 2 * done, xs_host + done, take, y, n); }
+    if (left >= 8) { take = 8; rc = multi_axpy_pass<8>(a_host + 2 * done, xs_host + done, take, y, n, x0); }
+    else if (left > 4) { take = left; rc = multi_axpy_pass<8>(a_host + 2 * done, xs_host + done, take, y, n, x0); }
+    else if (left > 2) { take = left; rc = multi_axpy_pass<4>(a_host + 2 * done, xs_host + done, take, y, n, x0); }
+    else if (left == 2) { take = 2; rc = multi_axpy_pass<2>(a_host + 2 * done, xs_host + done, take, y, n, x0); }
+    else { take = 1; rc = multi_axpy_pass<1>(a_host + 2 * done, xs_host + done, take, y, n, x0); }
     if (rc) return rc;
     done += take;
+    x0 = nullptr;   // later passes continue in place
   }
   return 0;
+}
+
+int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y_, long n)
+{
+  return qmg_multi_axpyz(a_host, xs_host, k, nullptr, y_, n);
 }
 
 int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p_, const qmg_cplx* q_, qmg_cplx* x_, qmg_cplx* r_, long n, double* result)

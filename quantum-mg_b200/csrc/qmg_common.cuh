@@ -16,6 +16,7 @@ struct Runtime
   int sm_count = 148;
   cudaStream_t stream = 0;
   long launches = 0;
+  int managed = 0;                  // qmg_malloc hands out managed memory (reference drivers index vectors on the host)
   // reduction scratch: per-block partials + a completion counter, and a pinned result slot
   double* d_partials = nullptr;     // at least kMaxRedBlocks * kMaxRedWidth doubles (grown on demand)
   size_t partials_cap = 0;          // capacity of d_partials in doubles

@@ -1,10 +1,37 @@
 // Runtime plumbing of libqmg_b200: device selection, stream, memory, error text.
 #include "qmg_common.cuh"
 #include <string.h>
+#include <stdlib.h>
+#include <map>
+#include <unordered_map>
+#include <vector>
 
 namespace qmg {
 
 Runtime& rt() { static Runtime r; return r; }
+
+// Size-keyed cache of device blocks.  The Krylov solvers allocate and release their work vectors on every call
+// (like the reference's allocate_vector / deallocate_vector); cudaMalloc / cudaFree would serialise the device each
+// time, so released blocks are parked here and handed back to the next request of the same size.  All work is
+// issued on one stream, so reuse is ordered after the last kernel that touched the block.
+struct BlockCache
+{
+  std::map<size_t, std::vector<void*> > idle;
+  std::unordered_map<void*, size_t> size_of;
+  size_t idle_bytes = 0;
+};
+static BlockCache& cache() { static BlockCache c; return c; }
+
+static int cache_trim()
+{
+  BlockCache& c = cache();
+  cudaStreamSynchronize(rt().stream);
+  for (auto& kv : c.idle)
+    for (void* p : kv.second) { c.size_of.erase(p); cudaFree(p); }
+  c.idle.clear();
+  c.idle_bytes = 0;
+  return 0;
+}
 
 int fail(const char* what, cudaError_t e, const char* file, int line)
 {
@@ -86,6 +113,8 @@ int qmg_init(int device)
   QMG_CUDA(cudaMalloc(&r.d_ptrs, sizeof(void*) * kMaxPtrs));
   QMG_CUDA(cudaMalloc(&r.d_scalars, sizeof(double) * 2 * kMaxPtrs));
   QMG_CUDA(cudaDeviceSynchronize());
+  const char* env = getenv("QMG_MANAGED");
+  if (env != nullptr && env[0] == '1') r.managed = 1;
   r.ready = true;
   return 0;
 }
@@ -94,7 +123,7 @@ int qmg_finalize(void)
 {
   Runtime& r = rt();
   if (!r.ready) return 0;
-  cudaStreamSynchronize(r.stream);
+  cache_trim();
   cudaFree(r.d_partials); cudaFree(r.d_counter); cudaFree(r.d_result); cudaFree(r.d_ptrs); cudaFree(r.d_scalars);
   cudaFreeHost(r.h_result);
   r.d_partials = nullptr; r.partials_cap = 0; r.d_counter = nullptr; r.d_result = nullptr; r.h_result = nullptr; r.d_ptrs = nullptr; r.d_scalars = nullptr;
@@ -113,10 +142,46 @@ int qmg_malloc(void** dptr, size_t bytes)
 {
   QMG_REQUIRE_INIT();
   if (bytes == 0) bytes = 16;
-  QMG_CUDA(cudaMalloc(dptr, bytes));
+  bytes = (bytes + 255) & ~(size_t)255;
+  BlockCache& c = cache();
+  auto it = c.idle.find(bytes);
+  if (it != c.idle.end() && !it->second.empty())
+  {
+    *dptr = it->second.back();
+    it->second.pop_back();
+    c.idle_bytes -= bytes;
+    return 0;
+  }
+  cudaError_t e;
+  for (int attempt = 0; attempt < 2; attempt++)
+  {
+    if (rt().managed) e = cudaMallocManaged(dptr, bytes, cudaMemAttachGlobal);
+    else e = cudaMalloc(dptr, bytes);
+    if (e == cudaSuccess) break;
+    cudaGetLastError();
+    if (attempt == 0) cache_trim();   // give parked blocks back to the driver and try once more
+  }
+  if (e != cudaSuccess) return qmg::fail("device allocation", e, __FILE__, __LINE__);
+  if (rt().managed)
+  {
+    cudaMemAdvise(*dptr, bytes, cudaMemAdviseSetPreferredLocation, rt().device);
+    cudaGetLastError();   // advice is best effort
+  }
+  c.size_of[*dptr] = bytes;
   return 0;
 }
-int qmg_free(void* dptr) { if (dptr) { QMG_CUDA(cudaFree(dptr)); } return 0; }
+int qmg_free(void* dptr)
+{
+  if (dptr == nullptr) return 0;
+  BlockCache& c = cache();
+  auto it = c.size_of.find(dptr);
+  if (it == c.size_of.end()) { QMG_CUDA(cudaFree(dptr)); return 0; }   // not ours (allocated before a finalize)
+  c.idle[it->second].push_back(dptr);
+  c.idle_bytes += it->second;
+  return 0;
+}
+int qmg_trim(void) { return cache_trim(); }
+size_t qmg_cached_bytes(void) { return cache().idle_bytes; }
 int qmg_memcpy_h2d(void* dst, const void* src, size_t bytes)
 {
   QMG_REQUIRE_INIT();
@@ -137,6 +202,8 @@ int qmg_memcpy_d2d(void* dst, const void* src, size_t bytes)
   QMG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, rt().stream));
   return 0;
 }
+int qmg_set_alloc_mode(int managed) { QMG_REQUIRE_INIT(); rt().managed = managed ? 1 : 0; return 0; }
+int qmg_get_alloc_mode(void) { return rt().managed; }
 int qmg_malloc_host(void** hptr, size_t bytes) { QMG_REQUIRE_INIT(); QMG_CUDA(cudaMallocHost(hptr, bytes ? bytes : 16)); return 0; }
 int qmg_free_host(void* hptr) { if (hptr) { QMG_CUDA(cudaFreeHost(hptr)); } return 0; }
 

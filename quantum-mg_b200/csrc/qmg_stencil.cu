@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(256) stencil_kernel_generic(const StencilKArgs
 static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs, StencilKArgs& a, int& n_par)
 {
   if (st == nullptr) return fail_msg("qmg_stencil_apply: null stencil");
-  if (st->X < 2 || st->Y < 2 || (st->X & 1) || (st->Y & 1)) return fail_msg("qmg_stencil_apply: X and Y must be even and >= 2");
+  const bool single_site = (st->X == 1 && st->Y == 1);   // a volume-1 coarsest level: clover + shift only (stencil_2d.h:868-887)
+  if (!single_site && (st->X < 2 || st->Y < 2 || (st->X & 1) || (st->Y & 1))) return fail_msg("qmg_stencil_apply: X and Y must be even and >= 2 (or a single site)");
   if (st->nc < 1) return fail_msg("qmg_stencil_apply: nc < 1");
   if ((const void*)lhs == (const void*)rhs && (pieces & (QMG_APPLY_CLOVER | QMG_APPLY_SHIFT | QMG_APPLY_IDENTITY_CLOVER)))
     return fail_msg("qmg_stencil_apply: in-place apply is only defined for pure hopping pieces");
@@ -213,6 +214,7 @@ static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   a.halo_ym = reinterpret_cast<const cd*>(st->halo_ym);
   a.halo_yp = reinterpret_cast<const cd*>(st->halo_yp);
   a.g.xh = st->X / 2; a.g.Y = st->Y; a.g.half = (unsigned)(st->X / 2) * st->Y;
+  if (single_site) { a.g.xh = 1; a.g.Y = 1; a.g.half = 1; a.hop = nullptr; }
   a.size_cm = (long)st->X * st->Y * st->nc * st->nc;
   const bool sh = pieces & QMG_APPLY_SHIFT;
   const double id = (pieces & QMG_APPLY_IDENTITY_CLOVER) ? 1.0 : 0.0;
@@ -234,6 +236,7 @@ static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   a.p_begin = 0; n_par = 2;
   if (pieces & QMG_APPLY_EVEN_ROWS_ONLY) { a.p_begin = 0; n_par = 1; }
   if (pieces & QMG_APPLY_ODD_ROWS_ONLY) { a.p_begin = 1; n_par = 1; }
+  if (single_site) { a.p_begin = 0; n_par = 1; }
   a.n_par = n_par;
   return 0;
 }

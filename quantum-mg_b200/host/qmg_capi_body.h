@@ -19,6 +19,7 @@
 // All array arguments of this API are HOST pointers to interleaved complex<double>.
 
 #include <chrono>
+#include <random>
 #include <vector>
 
 typedef std::complex<double> capi_cd;
@@ -518,6 +519,177 @@ int CAPI(mg_storage_counts)(void* h_, int level, int* out)
   out[0] = mg->get_storage_number_allocated(level);
   out[1] = mg->get_storage_number_checked(level);
   return 0;
+}
+
+// ------------------------------------------------------- whole K-cycle driver --
+// The setup and solve of tests/n13_wilson_kcycle/wilson_kcycle.cpp (:226-471) as one call each, so that large
+// lattices never round-trip vectors through the caller: Wilson operator from the given gauge field; per level
+// coarse_dof/2 null vectors from BiCGstab-L(6) solves of A e = -A eta (eta gaussian from std::mt19937(seed), 500
+// iterations, tol 5e-5), orthogonalised, chirally doubled and normalised; TransferMG with block
+// orthonormalisation and QMG_DOUBLE_PROJECTION; Galerkin coarse operators; MR(pre, post) smoothing.
+// iparams: n_refine, x_block, y_block, coarse_dof, pre_iters, post_iters, inner_iters, inner_restart,
+//          coarsest_iters, coarsest_restart, null_max_iter, null_L, fine_stencil_app (all levels), coarsest_stencil_app
+// dparams: inner_tol, coarsest_tol, null_tol, pre_tol, post_tol
+namespace capi {
+struct KCycleH
+{
+  std::vector<Lattice2D*> lats;
+  Stencil2D* op;
+  std::vector<TransferMG*> transfers;
+  std::vector<StatefulMultigridMG::LevelSolveMG*> level_solves;
+  StatefulMultigridMG::CoarsestSolveMG* coarsest;
+  StatefulMultigridMG* mg;
+  std::mt19937 generator;
+  double setup_seconds;
+  int null_ops;
+};
+}
+
+void* CAPI(kcycle_new)(int X, int Y, double mass, const capi_cd* gauge, const int* ip, const double* dp, unsigned seed, int verbosity)
+{
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  capi::KCycleH* h = new capi::KCycleH;
+  h->generator.seed(seed);
+  h->null_ops = 0;
+  const int n_refine = ip[0], xb = ip[1], yb = ip[2], coarse_dof = ip[3];
+  const QMGStencilType level_app = (QMGStencilType)ip[12];
+  h->lats.push_back(new Lattice2D(X, Y, 2));
+  {
+    capi::Stage g(gauge, 2L * X * Y, true, false);
+    h->op = new Wilson2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
+  }
+  const bool need_rbj = (level_app != QMG_MATVEC_ORIGINAL) || ((QMGStencilType)ip[13] != QMG_MATVEC_ORIGINAL);
+  if (need_rbj) h->op->build_rbjacobi_stencil();
+  h->coarsest = new StatefulMultigridMG::CoarsestSolveMG;
+  h->coarsest->coarsest_stencil_app = (QMGStencilType)ip[13];
+  h->coarsest->coarsest_tol = dp[1];
+  h->coarsest->coarsest_iters = ip[8];
+  h->coarsest->coarsest_restart_freq = ip[9];
+  h->mg = new StatefulMultigridMG(h->lats[0], h->op, h->coarsest);
+  inversion_verbose_struct verb((inversion_verbose_level)verbosity, "[CAPI-NULLVEC]: ");
+  int cx = X, cy = Y;
+  for (int i = 1; i <= n_refine; i++)
+  {
+    cx /= xb; cy /= yb;
+    h->lats.push_back(new Lattice2D(cx, cy, coarse_dof));
+    Lattice2D* fl = h->lats[i - 1];
+    const long nf = fl->get_size_cv();
+    Stencil2D* fop = h->mg->get_stencil(i - 1);
+    std::vector<capi_cd*> nv(coarse_dof);
+    for (int j = 0; j < coarse_dof; j++) { nv[j] = capi_alloc(nf); zero_vector(nv[j], nf); }
+    for (int j = 0; j < coarse_dof / 2; j++)
+    {
+      capi_cd* eta = h->mg->get_storage(i - 1)->check_out();
+      gaussian(eta, nf, h->generator);
+      for (int k = 0; k < j; k++) orthogonal(eta, nv[k], nf);
+      capi_cd* Aeta = h->mg->get_storage(i - 1)->check_out();
+      zero_vector(Aeta, nf);
+      fop->apply_M(Aeta, eta);
+      cax(-1.0, Aeta, nf);
+      inversion_info inv = minv_vector_bicgstab_l(nv[j], Aeta, nf, ip[10], dp[2], ip[11], apply_stencil_2D_M, (void*)fop, &verb);
+      h->null_ops += inv.ops_count + 1;
+      cxpy(eta, nv[j], nf);
+      h->mg->get_storage(i - 1)->check_in(eta);
+      h->mg->get_storage(i - 1)->check_in(Aeta);
+      for (int k = 0; k < j; k++) orthogonal(nv[j], nv[k], nf);
+    }
+    for (int j = 0; j < coarse_dof / 2; j++)
+    {
+      fop->chiral_projection_both(nv[j], nv[j + coarse_dof / 2]);
+      normalize(nv[j], nf);
+      normalize(nv[j + coarse_dof / 2], nf);
+    }
+    h->transfers.push_back(new TransferMG(fl, h->lats[i], &nv[0], true, false, QMG_DOUBLE_PROJECTION));
+    StatefulMultigridMG::LevelSolveMG* ls = new StatefulMultigridMG::LevelSolveMG;
+    ls->fine_stencil_app = level_app;
+    ls->intermediate_tol = dp[0]; ls->intermediate_iters = ip[6]; ls->intermediate_restart_freq = ip[7];
+    ls->pre_tol = dp[3]; ls->pre_iters = ip[4];
+    ls->post_tol = dp[4]; ls->post_iters = ip[5];
+    h->level_solves.push_back(ls);
+    h->mg->push_level(h->lats[i], h->transfers[i - 1], ls, true, true,
+                      level_app == QMG_MATVEC_ORIGINAL ? MultigridMG::QMG_MULTIGRID_PRECOND_ORIGINAL : MultigridMG::QMG_MULTIGRID_PRECOND_RIGHT_BLOCK_JACOBI,
+                      need_rbj ? CoarseOperator2D::QMG_COARSE_BUILD_RBJACOBI : CoarseOperator2D::QMG_COARSE_BUILD_ORIGINAL, (capi_cd**)0);
+    for (int j = 0; j < coarse_dof; j++) capi_free(nv[j]);
+  }
+  capi_barrier();
+  h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return h;
+}
+void CAPI(kcycle_free)(void* h_)
+{
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  delete h->mg;
+  for (size_t i = 0; i < h->transfers.size(); i++) delete h->transfers[i];
+  for (size_t i = 0; i < h->level_solves.size(); i++) delete h->level_solves[i];
+  delete h->coarsest;
+  delete h->op;
+  for (size_t i = 0; i < h->lats.size(); i++) delete h->lats[i];
+  delete h;
+}
+// Outer solve A x = b with restarted flexible GCR preconditioned by the K-cycle (n13 :459-471).
+// b: host array, or NULL for a gaussian right-hand side drawn from the handle's generator (as n13 :419 does).
+// x_out: host array for the solution or NULL.  outer_type selects the system the outer solver sees (n19: Schur).
+// info: resSq, iter, success, ops_count, solve seconds, explicit |b - A x| / |b| on the ORIGINAL system, setup seconds, null-vector ops
+void CAPI(kcycle_solve)(void* h_, const capi_cd* b, capi_cd* x_out, int outer_type, int max_iter, double tol, int restart, int verbosity, double* info)
+{
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  Lattice2D* l0 = h->lats[0];
+  const long n = l0->get_size_cv();
+  const QMGStencilType type = (QMGStencilType)outer_type;
+  capi_cd* bd = h->mg->check_out(0);
+  if (b != 0) capi_put(bd, b, n); else gaussian(bd, n, h->generator);
+  const double bnorm = sqrt(norm2sq(bd, n));
+  capi_cd* x = h->mg->check_out(0);
+  capi_cd* bprep = h->mg->check_out(0);
+  capi_cd* xfull = h->mg->check_out(0);
+  zero_vector(x, n); zero_vector(bprep, n); zero_vector(xfull, n);
+  h->op->prepare_M(bprep, bd, type);
+  inversion_verbose_struct verb((inversion_verbose_level)verbosity, "[CAPI-KCYCLE]: ");
+  verb.precond_verbosity = (inversion_verbose_level)verbosity;
+  verb.precond_verb_prefix = "[CAPI-KCYCLE-PREC]: ";
+  h->mg->set_multigrid_level(0);
+  h->mg->reset_tracker();
+  const int nsolve = (int)(type == QMG_MATVEC_RIGHT_SCHUR ? n / 2 : n);
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  inversion_info inv = minv_vector_gcr_var_precond_restart(x, bprep, nsolve, max_iter, tol, restart, Stencil2D::get_apply_function(type), (void*)h->op,
+                                                           StatefulMultigridMG::mg_preconditioner, (void*)h->mg, &verb);
+  capi_barrier();
+  info[4] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  h->op->reconstruct_M(xfull, x, bd, type);
+  capi_cd* Ax = bprep;
+  zero_vector(Ax, n);
+  h->op->apply_M(Ax, xfull);
+  info[5] = sqrt(diffnorm2sq(bd, Ax, n)) / bnorm;
+  info[0] = inv.resSq; info[1] = inv.iter; info[2] = inv.success ? 1.0 : 0.0; info[3] = inv.ops_count;
+  info[6] = h->setup_seconds; info[7] = h->null_ops;
+  if (x_out != 0) capi_get(x_out, xfull, n);
+  h->mg->check_in(bd, 0); h->mg->check_in(x, 0); h->mg->check_in(bprep, 0); h->mg->check_in(xfull, 0);
+}
+void* CAPI(kcycle_mg)(void* h_)
+{
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  capi::MgH* m = new capi::MgH; m->mg = h->mg; m->coarsest = 0;   // borrowed view for mg_tracker & co; never pass to mg_free
+  return m;
+}
+// Wall-clock seconds of `reps` K-cycle applications (mg_preconditioner at level 0) on a gaussian vector.
+double CAPI(kcycle_time_precond)(void* h_, int warm, int reps)
+{
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  const long n = h->lats[0]->get_size_cv();
+  capi_cd* r = h->mg->check_out(0); capi_cd* z = h->mg->check_out(0);
+  gaussian(r, n, h->generator);
+  inversion_verbose_struct verb;
+  h->mg->set_multigrid_level(0);
+  for (int i = 0; i < warm; i++) { zero_vector(z, n); StatefulMultigridMG::mg_preconditioner(z, r, (int)n, (void*)h->mg, &verb); }
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < reps; i++) { zero_vector(z, n); StatefulMultigridMG::mg_preconditioner(z, r, (int)n, (void*)h->mg, &verb); }
+  capi_barrier();
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  h->mg->check_in(r, 0); h->mg->check_in(z, 0);
+  return sec;
 }
 
 } // extern "C"

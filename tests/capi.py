@@ -291,3 +291,45 @@ class Multigrid:
         if self.h is not None:
             self.be.fn("mg_free")(self.h)
             self.h = None
+
+
+class KCycle:
+    """The whole n13-style setup + solve as native calls (kcycle_* in qmg_capi_body.h)."""
+
+    def __init__(self, be, L, mass, gauge, n_refine=1, block=4, coarse_dof=8, pre_iters=2, post_iters=2, inner_tol=0.2, inner_iters=1000,
+                 inner_restart=32, coarsest_tol=0.2, coarsest_iters=1000, coarsest_restart=32, null_max_iter=500, null_tol=5e-5, null_L=6,
+                 level_app=0, coarsest_app=0, pre_tol=1e-15, post_tol=1e-15, seed=1337, verbosity=0, Y=None):
+        self.be, self.X, self.Y = be, L, (L if Y is None else Y)
+        for name in ("kcycle_new", "kcycle_mg"):
+            be.fn(name).restype = C.c_void_p
+        be.fn("kcycle_time_precond").restype = C.c_double
+        ip = (C.c_int * 14)(n_refine, block, block, coarse_dof, pre_iters, post_iters, inner_iters, inner_restart, coarsest_iters,
+                            coarsest_restart, null_max_iter, null_L, level_app, coarsest_app)
+        dp = (C.c_double * 5)(inner_tol, coarsest_tol, null_tol, pre_tol, post_tol)
+        g = carr(gauge)
+        self.n_levels = n_refine + 1
+        self.h = C.c_void_p(be.fn("kcycle_new")(self.X, self.Y, C.c_double(mass), _c(g), ip, dp, C.c_uint(seed), verbosity))
+        self._mg = C.c_void_p(be.fn("kcycle_mg")(self.h))
+
+    def solve(self, b=None, outer_type=0, max_iter=1000, tol=1e-10, restart=32, verbosity=0, want_x=False):
+        n = self.X * self.Y * 2
+        bb = None if b is None else carr(b)
+        x = np.zeros(n, CD) if want_x else None
+        info = (C.c_double * 8)()
+        self.be.fn("kcycle_solve")(self.h, _c(bb), _c(x), outer_type, max_iter, C.c_double(tol), restart, verbosity, info)
+        out = dict(resSq=info[0], iter=int(info[1]), success=bool(info[2]), ops=int(info[3]), seconds=info[4], check_relres=info[5],
+                   setup_seconds=info[6], null_ops=int(info[7]))
+        return (x, out) if want_x else out
+
+    def tracker(self, level):
+        out = (C.c_int * 6)()
+        self.be.fn("mg_tracker")(self._mg, level, out)
+        return dict(nullvec=out[0], krylov=out[1], presmooth=out[2], postsmooth=out[3], total=out[4], iters=out[5])
+
+    def time_precond(self, warm=1, reps=3):
+        return self.be.fn("kcycle_time_precond")(self.h, warm, reps) / reps
+
+    def free(self):
+        if self.h is not None:
+            self.be.fn("kcycle_free")(self.h)
+            self.h = None

@@ -1,0 +1,365 @@
+"""Parity of the B200 host classes (include/qmg: the reference's class API over device memory) against the
+oracle (the reference's unmodified headers, oracle/_ref).  The SAME driver text (quantum-mg_b200/host/qmg_capi_body.h)
+is compiled against both, so each test is "same calls, two back ends".
+Tolerances: 1e-12 relative L2 for stencil applies (BASELINE.json north_star), 1e-10/1e-11 where an nc x nc inverse
+or a Gram-Schmidt sits in between; solver iteration counts +-1."""
+import numpy as np
+import pytest
+
+import capi
+import latutil
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not capi.have_ref():
+        pytest.skip("oracle/_ref/libqmg_ref.so not built")
+    return capi.Backend("ref")
+
+
+@pytest.fixture(scope="module")
+def gpu(qmg_gpu):
+    return capi.Backend("gpu")
+
+
+def both(ref, gpu, fn):
+    return fn(ref), fn(gpu)
+
+
+def test_cshift_n00(ref, gpu):
+    """tests/n00_cshift: site-number lattice, every direction and source parity, nc = 1, 2."""
+    X, Y = 6, 4
+    xs, ys = latutil.site_coords(X, Y)
+    for nc in (1, 2):
+        v = np.repeat((ys * X + xs).astype(np.complex128), nc)
+        for cdir in (2, 3, 4, 5):
+            for eo in (1, 2, 3):
+                a, b = both(ref, gpu, lambda be: be.lattice(X, Y, nc).cshift(v, cdir, eo, nc, lhs=-np.ones_like(v)))
+                assert np.array_equal(a, b), (nc, cdir, eo)
+
+
+OPS = {
+    "wilson": lambda lat, g: lat.wilson(-0.055, g),
+    "staggered": lambda lat, g: lat.staggered(0.1, g),
+    "laplace": lambda lat, g: lat.laplace(0.01, g),
+    "dwf4": lambda lat, g: lat.dwf(0.05, g, 4, -1.0),
+}
+NC = {"wilson": 2, "staggered": 1, "laplace": 1, "dwf4": 8}
+
+
+@pytest.mark.parametrize("kind", ["wilson", "staggered", "laplace", "dwf4"])
+def test_operator_fill_apply_variants(ref, gpu, kind):
+    """Operator construction from U(1) links, all nine QMGStencilType applies (stencil_2d.h:2418), every accumulate piece,
+    prepare_M / reconstruct_M round trip."""
+    L = 32
+    g = latutil.load_gauge(L)
+    lr, lg = ref.lattice(L, L, NC[kind]), gpu.lattice(L, L, NC[kind])
+    a, b = OPS[kind](lr, g), OPS[kind](lg, g)
+    for name in ("clover", "hopping"):
+        x, y = a.get(name), b.get(name)
+        assert (x is None) == (y is None)
+        if x is not None:
+            assert latutil.rel_l2(y, x) < TOL
+    assert a.shifts() == b.shifts()
+    rhs = latutil.gaussian_cv(lr.size_cv, 1)
+    acc = latutil.gaussian_cv(lr.size_cv, 2)
+    for piece in (0, 1, 2, 3, 4, 6, 9, 10):
+        assert latutil.rel_l2(b.apply_piece(piece, rhs, lhs=acc), a.apply_piece(piece, rhs, lhs=acc)) < TOL, piece
+    for piece in (5, 7, 8):
+        for mu in range(4):
+            assert latutil.rel_l2(b.apply_piece(piece, rhs, dir=mu, lhs=acc), a.apply_piece(piece, rhs, dir=mu, lhs=acc)) < TOL, (piece, mu)
+    a.build(dagger=True, rbjacobi=(kind != "staggered" or True), rbj_dagger=True)
+    b.build(dagger=True, rbjacobi=True, rbj_dagger=True)
+    assert a.built() == b.built()
+    for name in capi.Stencil.NAMES[2:]:
+        x, y = a.get(name), b.get(name)
+        assert (x is None) == (y is None), name
+        if x is not None:
+            assert latutil.rel_l2(y, x) < 1e-11, name
+    for t in range(9):
+        want, got = a.apply(rhs, t), b.apply(rhs, t)
+        assert latutil.rel_l2(got, want) < 1e-11, t
+        # accumulate flavour apply_M(lhs, rhs, type)
+        assert latutil.rel_l2(b.apply_piece(12, rhs, dir=t, lhs=acc), a.apply_piece(12, rhs, dir=t, lhs=acc)) < 1e-11, t
+        pa, pb = a.prepare(rhs, t), b.prepare(rhs, t)
+        assert latutil.rel_l2(pb, pa) < 1e-11, t
+        ra, rb = a.reconstruct(rhs, acc, t), b.reconstruct(rhs, acc, t)
+        assert latutil.rel_l2(rb, ra) < 1e-11, t
+    assert latutil.rel_l2(b.apply_piece(11, rhs, lhs=acc), a.apply_piece(11, rhs, lhs=acc)) < 1e-11
+    a.free(); b.free()
+
+
+@pytest.mark.parametrize("kind", ["wilson", "staggered", "dwf4"])
+def test_chirality(ref, gpu, kind):
+    """gamma5 / sigma1 / chiral projections / apply_sigma (wilson.h:74-148, staggered.h:140-186, dwf.h:104-147)."""
+    L = 16
+    g = latutil.phases_to_gauge(np.random.default_rng(3).normal(0, 0.4, size=L * L * 2), L, L)
+    a, b = OPS[kind](ref.lattice(L, L, NC[kind]), g), OPS[kind](gpu.lattice(L, L, NC[kind]), g)
+    v, w = latutil.gaussian_cv(L * L * NC[kind], 1), latutil.gaussian_cv(L * L * NC[kind], 2)
+    for op in range(0, 13):
+        if op in (13,):
+            continue
+        ra, rb = a.chiral(op, v, w), b.chiral(op, v, w)
+        for x, y in zip(ra, rb):
+            if x is not None:
+                assert np.allclose(y, x, rtol=0, atol=1e-14), (kind, op)
+    a.free(); b.free()
+
+
+def test_n18_noise_on_clover(ref, gpu):
+    """tests/n18_rbjacobi_stencil_test/rbjacobi_stencil_test.cpp:133-231: noise is added to the PUBLIC clover pointer,
+    then GCR runs on the original, right-block-Jacobi and Schur systems and the solution is reconstructed."""
+    L = 32
+    g = latutil.load_gauge(L)
+    noise = 0.1 * latutil.gaussian_cv(L * L * 4, 18)
+    b_src = latutil.gaussian_cv(L * L * 2, 19)
+    res = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        op = be.lattice(L, L, 2).wilson(0.1, g)
+        op.add_to("clover", noise)
+        op.build(rbjacobi=True)
+        out = {}
+        for t, n in ((0, None), (2, None), (3, L * L)):
+            bp = op.prepare(b_src, t)
+            y, info = op.solve(2, bp, type=t, n=n, max_iter=500, tol=1e-9)
+            x = op.reconstruct(y, b_src, t)
+            check = np.linalg.norm(op.apply(x, 0) - b_src) / np.linalg.norm(b_src)
+            out[t] = (x, info, check)
+        res[name] = out
+        op.free()
+    for t in (0, 2, 3):
+        xr, ir, cr = res["ref"][t]
+        xg, ig, cg = res["gpu"][t]
+        assert ir["success"] and ig["success"]
+        assert abs(ir["iter"] - ig["iter"]) <= 1, (t, ir, ig)
+        assert cg < 5e-9 and cr < 5e-9
+        assert latutil.rel_l2(xg, xr) < 1e-7
+
+
+@pytest.mark.parametrize("solver,kind,type,kw", [
+    (0, "laplace", 0, dict(tol=1e-8)),                               # n03: CG on the Laplace operator
+    (2, "wilson", 0, dict(tol=1e-8, max_iter=400)),                  # n11: GCR
+    (3, "wilson", 0, dict(tol=1e-8, iparam=16, max_iter=3000)),      # n11: GCR(16)
+    (4, "wilson", 0, dict(tol=1e-3, dparam=0.85, max_iter=200)),     # MR(omega) as used by the smoother
+    (5, "wilson", 0, dict(tol=5e-5, iparam=6, max_iter=500)),        # n13: BiCGstab-6 null-vector solve
+    (6, "wilson", 0, dict(tol=1e-10, dparam=0.33, iparam=250, max_iter=10)),  # n22: Richardson relaxation
+    (0, "wilson", 5, dict(tol=1e-8, max_iter=4000)),                 # n17: CGNR on M^dag M
+    (1, "wilson", 4, dict(tol=1e-8, iparam=64, max_iter=4000)),      # n17: restarted CGNE on M M^dag
+])
+def test_solvers_iteration_parity(ref, gpu, solver, kind, type, kw):
+    L = 32
+    g = latutil.load_gauge(L)
+    b_src = np.zeros(L * L * NC[kind], np.complex128)
+    b_src[latutil.site_index(L // 2, L // 2, L, L) * NC[kind]] = 1.0
+    x0 = latutil.gaussian_cv(b_src.size, 5)
+    out = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        op = OPS[kind](be.lattice(L, L, NC[kind]), g) if kind != "wilson" else be.lattice(L, L, 2).wilson(0.05, g)
+        op.build(dagger=True)
+        bp = op.prepare(b_src, type)
+        out[name] = op.solve(solver, bp, type=type, x0=x0, **kw)
+        op.free()
+    (xr, ir), (xg, ig) = out["ref"], out["gpu"]
+    assert ir["success"] == ig["success"]
+    assert abs(ir["iter"] - ig["iter"]) <= 1, (ir, ig)
+    assert abs(ir["ops"] - ig["ops"]) <= 2
+    assert latutil.rel_l2(xg, xr) < 1e-6
+    assert abs(np.sqrt(ig["resSq"]) - np.sqrt(ir["resSq"])) <= 1e-3 * np.sqrt(ir["resSq"]) + 1e-14
+
+
+TRANSFER_CASES = [(16, 16, 2, 4, 4, 8), (8, 8, 8, 2, 2, 8), (8, 8, 1, 4, 4, 2), (4, 4, 2, 1, 1, 6)]
+
+
+@pytest.mark.parametrize("case", TRANSFER_CASES)
+def test_transfer_class(ref, gpu, case):
+    """TransferMG (transfer.h:118-179): block-orthonormalised copies, P, R, Cholesky factor; n05 / n06 identities."""
+    Xf, Yf, ncf, Xc, Yc, ncc = case
+    nv = np.stack([latutil.gaussian_cv(Xf * Yf * ncf, 70 + v) for v in range(ncc)])
+    cv, fv = latutil.gaussian_cv(Xc * Yc * ncc, 1), latutil.gaussian_cv(Xf * Yf * ncf, 2)
+    out = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        fl, cl = be.lattice(Xf, Yf, ncf), be.lattice(Xc, Yc, ncc)
+        tr = capi.Transfer(fl, cl, nv, block_ortho=True, save_decomp=True, doubling=1)
+        out[name] = (tr.nullvecs(), tr.cholesky(), tr.prolong(cv, fv), tr.restrict(fv, cv), tr.props())
+        tr.free()
+    for i in range(4):
+        assert latutil.rel_l2(out["gpu"][i], out["ref"][i]) < 1e-11, i
+    assert out["gpu"][4] == out["ref"][4]
+    # Sigma^dag Sigma = block Gram matrix of the ORIGINAL vectors (tests/n06_transfer_decomp)
+    chol = out["gpu"][1].reshape(Xc * Yc, ncc, ncc)
+    if Xc * Yc == 1:
+        gram = nv.conj() @ nv.T
+        assert np.allclose(chol[0].conj().T @ chol[0], gram, rtol=1e-10, atol=1e-10)
+
+
+def test_transfer_asymmetric(ref, gpu):
+    """Separate restrict vectors with block bi-orthonormalisation and saved L, U (transfer.h:185-225, 610-769; n05 :121-139)."""
+    Xf, Yf, ncf, Xc, Yc, ncc = 8, 8, 2, 2, 2, 4
+    pv = np.stack([latutil.gaussian_cv(Xf * Yf * ncf, 80 + v) for v in range(ncc)])
+    rv = pv + 0.3 * np.stack([latutil.gaussian_cv(Xf * Yf * ncf, 90 + v) for v in range(ncc)])
+    cv = latutil.gaussian_cv(Xc * Yc * ncc, 1)
+    out = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        fl, cl = be.lattice(Xf, Yf, ncf), be.lattice(Xc, Yc, ncc)
+        tr = capi.Transfer(fl, cl, pv, block_ortho=True, save_decomp=True, restrict_vecs=rv)
+        L_, U_ = tr.LU()
+        out[name] = (tr.nullvecs(0), tr.nullvecs(1), L_, U_, tr.restrict(tr.prolong(cv)), tr.props())
+        tr.free()
+    for i in range(4):
+        assert latutil.rel_l2(out["gpu"][i], out["ref"][i]) < 1e-10, i
+    assert latutil.rel_l2(out["gpu"][4], cv) < 1e-11      # (1 - R P) v_c = 0
+    assert out["gpu"][5] == out["ref"][5]
+
+
+@pytest.mark.parametrize("use_rbj,extra", [(False, 0), (False, 5), (True, 2)])
+def test_coarse_operator_class(ref, gpu, use_rbj, extra):
+    """CoarseOperator2D built through the class API (coarse.h:90-471), incl. building from the rbjacobi fine stencil
+    and the extra dagger / rbjacobi / rbj-dagger sets; then R A P == A_c on a random vector (tests/n08)."""
+    L, Lc = 16, 4
+    g = latutil.phases_to_gauge(np.random.default_rng(8).normal(0, 0.4, size=L * L * 2), L, L)
+    nv = np.stack([latutil.gaussian_cv(L * L * 2, 30 + v) for v in range(8)])
+    x = latutil.gaussian_cv(Lc * Lc * 8, 3)
+    out = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        fl, cl = be.lattice(L, L, 2), be.lattice(Lc, Lc, 8)
+        op = fl.wilson(0.02, g)
+        if use_rbj:
+            op.build(rbjacobi=True)
+        tr = capi.Transfer(fl, cl, nv, doubling=1)
+        co = tr.coarse_operator(op, is_chiral=True, use_rbjacobi=use_rbj, build_extra=extra)
+        arrays = [co.get(n) for n in capi.Stencil.NAMES]
+        rap = tr.restrict(op.apply(tr.prolong(x), 2 if use_rbj else 0))
+        out[name] = (arrays, co.apply(x, 0), rap, co.shifts(), co.built(), co.chiral(8, x, x))
+        co.free(); tr.free(); op.free()
+    for n, xa, ya in zip(capi.Stencil.NAMES, out["ref"][0], out["gpu"][0]):
+        assert (xa is None) == (ya is None), n
+        if xa is not None:
+            assert np.linalg.norm(ya - xa) < 1e-10 * max(1.0, np.linalg.norm(xa)), n
+    assert latutil.rel_l2(out["gpu"][1], out["ref"][1]) < 1e-11
+    # Galerkin identity: the explicit coarse stencil (+ inherited shift) equals R A P
+    assert latutil.rel_l2(out["gpu"][1], out["gpu"][2]) < 1e-11
+    assert out["gpu"][3] == out["ref"][3] and out["gpu"][4] == out["ref"][4]
+    for a_, b_ in zip(out["ref"][5], out["gpu"][5]):
+        assert np.allclose(a_, b_, atol=1e-14)
+
+
+def _n13_nullvecs(be, lat, op, coarse_dof, seed):
+    """Null vectors as tests/n13_wilson_kcycle/wilson_kcycle.cpp:338-385 generates them (through backend `be`)."""
+    rng = np.random.default_rng(seed)
+    n = lat.size_cv
+    nv = np.zeros((coarse_dof, n), np.complex128)
+    for j in range(coarse_dof // 2):
+        eta = rng.normal(size=n) + 1j * rng.normal(size=n)
+        for k in range(j):
+            eta -= np.vdot(nv[k], eta) / np.vdot(nv[k], nv[k]) * nv[k]
+        e, _ = op.solve(5, -op.apply(eta, 0), max_iter=500, tol=5e-5, iparam=6)
+        nv[j] = e + eta
+        for k in range(j):
+            nv[j] -= np.vdot(nv[k], nv[j]) / np.vdot(nv[k], nv[k]) * nv[k]
+    for j in range(coarse_dof // 2):
+        up, down = op.chiral(8, nv[j], nv[j])
+        nv[j], nv[j + coarse_dof // 2] = up / np.linalg.norm(up), down / np.linalg.norm(down)
+    return nv
+
+
+def _build_mg(be, L, g, mass, nvs, level_app=0, coarsest_app=0, build_from=0, build_extra=0, block=4, coarse_dof=8):
+    lat0 = be.lattice(L, L, 2)
+    op = lat0.wilson(mass, g)
+    if level_app != 0 or coarsest_app != 0:
+        op.build(rbjacobi=True)
+    mg = capi.Multigrid(lat0, op, coarsest_type=coarsest_app, coarsest_tol=0.2, coarsest_iters=1000, coarsest_restart=32)
+    lats, cur = [lat0], L
+    for nv in nvs:
+        cur //= block
+        lc = be.lattice(cur, cur, coarse_dof)
+        tr = capi.Transfer(lats[-1], lc, nv, block_ortho=True, save_decomp=False, doubling=1)
+        mg.push_level(lc, tr, fine_stencil_app=level_app, inner_tol=0.2, inner_iters=1000, inner_restart=32, pre_iters=2, post_iters=2,
+                      build_stencil=True, is_chiral=True, build_from=build_from, build_extra=build_extra, nvecs=nv)
+        lats.append(lc)
+    return mg, op, lats
+
+
+@pytest.mark.parametrize("L,levels", [(64, 2), (64, 3)])
+def test_n13_kcycle_parity(ref, gpu, L, levels):
+    """tests/n13_wilson_kcycle: identical raw null vectors fed to both back ends; outer VPGCR(32) to 1e-10.
+    Outer iteration count +-1, per-level operator counts close, same solution (north_star parity gates)."""
+    g = latutil.load_gauge(L)
+    mass = -0.075
+    # raw null vectors level by level from the ORACLE, then reused verbatim on the GPU
+    nvs = []
+    mg_r, op_r, lats_r = _build_mg(ref, L, g, mass, [])
+    for lev in range(levels - 1):
+        st = mg_r.stencil(lev)
+        nv = _n13_nullvecs(ref, lats_r[lev], st, 8, seed=100 + lev)
+        nvs.append(nv)
+        mg_r.free()
+        mg_r, op_r, lats_r = _build_mg(ref, L, g, mass, nvs)
+    mg_g, op_g, lats_g = _build_mg(gpu, L, g, mass, nvs)
+    assert mg_g.num_levels() == mg_r.num_levels() == levels
+    # coarse operators agree level by level
+    for lev in range(1, levels):
+        for name in ("clover", "hopping"):
+            xa, ya = mg_r.stencil(lev).get(name), mg_g.stencil(lev).get(name)
+            assert np.linalg.norm(ya - xa) < 1e-10 * np.linalg.norm(xa), (lev, name)
+    b = latutil.gaussian_cv(L * L * 2, 13)
+    # one preconditioner application
+    zr, zg = mg_r.precond(b), mg_g.precond(b)
+    assert latutil.rel_l2(zg, zr) < 1e-6
+    mg_r.reset_tracker(); mg_g.reset_tracker()
+    xr, ir = mg_r.solve(b, tol=1e-10, restart=32)
+    xg, ig = mg_g.solve(b, tol=1e-10, restart=32)
+    assert ir["success"] and ig["success"]
+    assert abs(ir["iter"] - ig["iter"]) <= 1, (ir, ig)
+    assert np.sqrt(ig["resSq"]) / np.linalg.norm(b) < 1e-10
+    assert latutil.rel_l2(xg, xr) < 1e-8
+    check = np.linalg.norm(op_g.apply(xg, 0) - b) / np.linalg.norm(b)
+    assert check < 2e-10
+    for lev in range(levels):
+        tr_, tg_ = mg_r.tracker(lev), mg_g.tracker(lev)
+        assert abs(tr_["total"] - tg_["total"]) <= 0.1 * tr_["total"] + 8, (lev, tr_, tg_)
+    assert mg_g.be.fn("mg_storage_counts")(mg_g.h, 0, (capi.C.c_int * 2)()) == 0
+    mg_r.free(); mg_g.free()
+
+
+def test_n19_schur_kcycle_parity(ref, gpu):
+    """tests/n19_wilson_kcycle_precond: every level solved as the Schur system of the right-block-Jacobi operator,
+    coarse stencils built from the rbjacobi fine stencil, outer tolerance 1e-8."""
+    L = 64
+    g = latutil.load_gauge(L)
+    mass = -0.07
+    SCHUR = 3
+    mg_r, op_r, lats_r = _build_mg(ref, L, g, mass, [], level_app=SCHUR, coarsest_app=SCHUR)
+    nv = _n13_nullvecs(ref, lats_r[0], op_r, 8, seed=19)
+    mg_r.free()
+    out = {}
+    b = latutil.gaussian_cv(L * L * 2, 19)
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        mg, op, lats = _build_mg(be, L, g, mass, [nv], level_app=SCHUR, coarsest_app=SCHUR, build_from=1, build_extra=2)
+        bp = op.prepare(b, SCHUR)
+        y, info = mg.solve(bp, outer_type=SCHUR, tol=1e-8, restart=32)
+        x = op.reconstruct(y, b, SCHUR)
+        out[name] = (x, info, np.linalg.norm(op.apply(x, 0) - b) / np.linalg.norm(b))
+        mg.free()
+    (xr, ir, cr), (xg, ig, cg) = out["ref"], out["gpu"]
+    assert ir["success"] and ig["success"]
+    assert abs(ir["iter"] - ig["iter"]) <= 1, (ir, ig)
+    assert cg < 5e-8
+    assert latutil.rel_l2(xg, xr) < 1e-6
+
+
+def test_native_kcycle_driver(ref, gpu):
+    """kcycle_new / kcycle_solve: the n13 flow with everything generated on the device (same mt19937 draws as the oracle).
+    Null vectors come out of 500-iteration BiCGstab-L solves, so only iteration counts (+-2) and residuals are compared."""
+    L = 64
+    g = latutil.load_gauge(L)
+    res = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        kc = capi.KCycle(be, L, -0.075, g, n_refine=2)
+        res[name] = kc.solve(tol=1e-10)
+        kc.free()
+    assert res["gpu"]["success"] and res["ref"]["success"]
+    assert abs(res["gpu"]["iter"] - res["ref"]["iter"]) <= 2, res
+    assert res["gpu"]["check_relres"] < 2e-10
