@@ -83,6 +83,35 @@ def cpu_reference_apply(L, reps, warm=1):
     return BYTES_PER_SITE * L * L / sec / 1e9, sec
 
 
+def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=None):
+    """3-level (n_refine=2) Wilson K-cycle as tests/n13_wilson_kcycle sets it up (4x4 blocks, 8 coarse dof, BiCGstab-6 null
+    vectors, MR(2,2) smoothing, inner tol 0.2), mass -0.075, gaussian right-hand side; returns the solve record."""
+    import capi
+    import latutil
+    be = capi.Backend(backend)
+    if gauge is None:
+        try:
+            gauge = latutil.load_gauge(L)          # the reference's own thermalised config where one exists (64, 128, 256)
+            cfg = "tests/common_cfgs_u1 l%dt%db60" % (L, L)
+        except Exception:
+            gauge = latutil.synthetic_gauge(L, L, beta=6.0, seed=seed)
+            cfg = "synthetic gaussian phases, beta 6.0, seed %d" % seed
+    else:
+        cfg = "synthetic"
+    t0 = time.perf_counter()
+    kc = capi.KCycle(be, L, -0.075, gauge, n_refine=n_refine, seed=seed)
+    out = kc.solve(tol=tol, restart=restart)
+    out["levels"] = n_refine + 1
+    out["L"] = L
+    out["config"] = cfg
+    out["per_level_ops"] = [kc.tracker(l)["total"] for l in range(n_refine + 1)]
+    out["per_level_iters"] = [kc.tracker(l)["iters"] for l in range(n_refine + 1)]
+    out["precond_apply_s"] = kc.time_precond(1, 2)
+    out["wall_s_incl_setup"] = time.perf_counter() - t0
+    kc.free()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -96,12 +125,16 @@ def run_reference(args):
     sec = sum(times) / len(times)
     val = BYTES_PER_SITE * L * L / sec / 1e9
     sample = "Wilson apply on %dx%d (of the %dx%d workload), %d applies per step, g++ -O2 single thread" % (L, L, args.L, args.L, args.cpu_reps)
+    kc = None
+    if args.cpu_kcycle_L > 0:
+        kc = kcycle_run("ref", args.cpu_kcycle_L)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3 * args.cpu_reps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "wilson_stencil_apply_%dx%d_u1" % (args.L, args.L), "sample_L": L},
         "cpu_baseline": {"value": val, "unit": "GB/s", "cores": 1, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "kcycle": kc,
     }))
 
 
@@ -216,6 +249,15 @@ def run_gpu(args):
     lib.qmg_free_host(hout)
     clocks = sampler.summary() if rank == 0 else None
 
+    # second half of the metric: 3-level Wilson K-cycle solve time (single GPU leg; the sharded solve is reported by --kcycle-sharded)
+    kcycle = kcycle_same = None
+    if world == 1 and args.kcycle_L > 0:
+        del clover, hopping, rhs, lhs, desc
+        torch.cuda.empty_cache()
+        kcycle = kcycle_run("gpu", args.kcycle_L)
+        if args.cpu_kcycle_L > 0 and not args.no_cpu:
+            kcycle_same = kcycle_run("gpu", args.cpu_kcycle_L)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = BYTES_PER_SITE * V / (kern_ms * 1e-3) / 1e9
@@ -226,6 +268,9 @@ def run_gpu(args):
                 cpu = {"value": gbs, "unit": "GB/s", "cores": 1, "kind": "reference",
                        "sample": "Wilson apply on %dx%d, %d applies, oracle/_ref (unmodified reference headers, g++ -O2, 1 thread; the reference is single-threaded)" % (args.cpu_L, args.cpu_L, args.cpu_reps),
                        "ms_per_apply": sec * 1e3, "host_cores_available": os.cpu_count()}
+                if args.cpu_kcycle_L > 0:
+                    cpu["kcycle"] = kcycle_run("ref", args.cpu_kcycle_L)
+                    cpu["kcycle_gpu_same_config"] = kcycle_same
             except Exception as e:  # the baseline is a report, never the product path
                 cpu = {"value": None, "unit": "GB/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
         print(json.dumps({
@@ -240,6 +285,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps},
             "gpu_launches": launches,
             "clocks": clocks,
+            "kcycle": kcycle,
         }))
     if world > 1:
         import torch.distributed as dist
@@ -256,6 +302,8 @@ def main():
     ap.add_argument("--cpu-L", type=int, default=2048, dest="cpu_L")
     ap.add_argument("--cpu-reps", type=int, default=5, dest="cpu_reps")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
+    ap.add_argument("--kcycle-L", type=int, default=4096, dest="kcycle_L", help="3-level K-cycle solve on L x L after the stencil run (0 = skip)")
+    ap.add_argument("--cpu-kcycle-L", type=int, default=256, dest="cpu_kcycle_L", help="K-cycle size for the CPU reference leg (n13's 256x256 config; 0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,106 @@
+"""CPU suite, part 2: the drop-in boundary.  The C-ABI library loads without a GPU, exports every symbol that
+include/qmg_b200.h declares, refuses to compute without a device (no CPU fallback), and the host-class library exports
+the same flat driver API as the oracle with identical host-side (Lattice2D) answers."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import capi
+import latutil
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_libqmg_b200_exports_header_symbols():
+    import qmg
+    lib = qmg.lib()
+    syms = qmg.exported_symbols()
+    assert len(syms) > 60
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_header_cites_reference_for_every_entry():
+    text = open(os.path.join(ROOT, "include", "qmg_b200.h")).read()
+    assert text.count("stencil_2d.h") >= 8 and "transfer.h" in text and "coarse.h" in text and "extern \"C\"" in text
+    assert "torch" not in text.lower().replace("torch's current stream", "")
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import qmg
+    lib = qmg.lib()
+    assert lib.qmg_device_count() == 0
+    x = np.zeros(8, np.complex128)
+    out = C.c_double()
+    rc = lib.qmg_norm2sq(x.ctypes.data_as(C.c_void_p), C.c_long(8), C.byref(out))
+    assert rc != 0
+    assert b"no CPU fallback" in lib.qmg_last_error()
+    with pytest.raises(qmg.QmgError):
+        qmg.init(0)
+
+
+def test_product_does_not_touch_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may execute oracle/."""
+    for base in ("quantum-mg_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if not f.endswith((".py", ".h", ".cuh", ".cu", ".cpp")):
+                    continue
+                for line in open(os.path.join(dirpath, f), errors="ignore"):
+                    code = line.split("//")[0]
+                    if "#include" in code or "import " in code or "CDLL" in code or "dlopen" in code:
+                        assert "oracle" not in code and "qlinalg_shim" not in code and "libqmg_ref" not in code, (f, line)
+    out = subprocess.run(["ldd", os.path.join(ROOT, "quantum-mg_b200", "libqmg_host.so")], stdout=subprocess.PIPE, text=True).stdout
+    assert "libqmg_ref" not in out and "libqmg_b200" in out
+
+
+def _exports(path, prefix):
+    out = subprocess.run(["nm", "-D", "--defined-only", path], stdout=subprocess.PIPE, text=True).stdout
+    return sorted(set(m.group(1) for m in re.finditer(r" T " + prefix + r"(\w+)", out)))
+
+
+@pytest.mark.skipif(not capi.have_ref(), reason="oracle/_ref not built")
+def test_host_library_mirrors_oracle_driver_api():
+    ref = _exports(capi.REF_LIB, "ref_")
+    gpu = _exports(capi.GPU_LIB, "qmgh_")
+    assert ref == gpu and len(gpu) > 45
+
+
+@pytest.mark.skipif(not capi.have_ref(), reason="oracle/_ref not built")
+def test_lattice2d_parity_without_gpu():
+    """Lattice2D is host-only integer geometry: the product class must agree with the reference's for every index map."""
+    ref, gpu = capi.Backend("ref"), capi.Backend("gpu")
+    for X, Y, nc in ((6, 4, 2), (8, 8, 8), (2, 2, 1), (1, 1, 4)):
+        a, b = ref.lattice(X, Y, nc), gpu.lattice(X, Y, nc)
+        assert (a.volume, a.size_cv, a.size_cm, a.size_gauge, a.size_hopping, a.size_corner) == (b.volume, b.size_cv, b.size_cm, b.size_gauge, b.size_hopping, b.size_corner)
+        xyc = (C.c_int * 3)()
+        for i in range(X * Y):
+            assert a.index_to_coord(i) == b.index_to_coord(i)
+        for x in range(X):
+            for y in range(Y):
+                assert a.coord_to_index(x, y) == b.coord_to_index(x, y)
+                for fn, args in (("lattice_cm_index", (x, y, nc - 1, 0)), ("lattice_hopping_index", (x, y, 0, nc - 1, 3)), ("lattice_gauge_index", (x, y, 0, 0, 1))):
+                    assert ref.fn(fn)(a.h, *args) == gpu.fn(fn)(b.h, *args)
+        for i in range(0, a.size_cv, 3):
+            ref.fn("lattice_cv_index_to_coord")(a.h, i, xyc); ra = tuple(xyc)
+            gpu.fn("lattice_cv_index_to_coord")(b.h, i, xyc)
+            assert ra == tuple(xyc)
+
+
+def test_bench_reference_arm_runs():
+    """bench.py --impl reference times the reference's own CPU apply and prints one JSON line with the contract keys."""
+    if not capi.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import json
+    out = subprocess.run(["python", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-L", "256", "--cpu-reps", "2", "--kcycle-L", "0", "--cpu-kcycle-L", "0"],
+                         stdout=subprocess.PIPE, text=True, timeout=600).stdout.strip().splitlines()[-1]
+    line = json.loads(out)
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "GB/s"
