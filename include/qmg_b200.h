@@ -41,6 +41,11 @@ int qmg_device_count(void);
 int qmg_sm_count(void);
 long qmg_kernel_launches(void);           /* kernels launched by this library so far */
 
+/* Per-entry-point timing (also QMG_PROFILE=1): each call is bracketed by stream synchronisations and accumulated by name. */
+int qmg_profile_enable(int on);
+int qmg_profile_reset(void);
+double qmg_profile_report(void);          /* prints the table, returns total seconds */
+
 /* allocate_vector / deallocate_vector (qlinalg; stencil/stencil_2d.h:220,299) */
 int qmg_malloc(void** dptr, size_t bytes);
 int qmg_free(void* dptr);                 /* parks the block in a size-keyed cache; qmg_trim returns parked blocks to the driver */

@@ -16,6 +16,7 @@ struct Runtime
   int sm_count = 148;
   cudaStream_t stream = 0;
   long launches = 0;
+  int profile = 0;                  // per-entry-point timing enabled
   int managed = 0;                  // qmg_malloc hands out managed memory (reference drivers index vectors on the host)
   // reduction scratch: per-block partials + a completion counter, and a pinned result slot
   double* d_partials = nullptr;     // at least kMaxRedBlocks * kMaxRedWidth doubles (grown on demand)
@@ -37,7 +38,16 @@ int fail(const char* what, cudaError_t e, const char* file, int line);
 int fail_msg(const char* msg);
 
 #define QMG_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return qmg::fail(#call, e__, __FILE__, __LINE__); } while (0)
-#define QMG_REQUIRE_INIT() do { if (!qmg::rt().ready) { int r__ = qmg_init(-1); if (r__) return r__; } } while (0)
+// Optional per-entry-point timing (QMG_PROFILE=1 or qmg_profile_enable(1)): every C-ABI call is bracketed by stream
+// synchronisations and its wall time is accumulated under the function's name; qmg_profile_report() prints the table.
+// Off by default: the scope object is then a single predictable branch.
+struct ProfScope
+{
+  const char* name; double t0; bool on;
+  explicit ProfScope(const char* n);
+  ~ProfScope();
+};
+#define QMG_REQUIRE_INIT() if (!qmg::rt().ready) { int r__ = qmg_init(-1); if (r__) return r__; } qmg::ProfScope prof_scope__(__func__)
 #define QMG_LAUNCH_CHECK() do { qmg::rt().launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return qmg::fail("kernel launch", e__, __FILE__, __LINE__); } while (0)
 
 // ---- complex<double> as double2 -------------------------------------------------

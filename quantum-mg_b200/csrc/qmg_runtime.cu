@@ -2,6 +2,8 @@
 #include "qmg_common.cuh"
 #include <string.h>
 #include <stdlib.h>
+#include <time.h>
+#include <algorithm>
 #include <map>
 #include <unordered_map>
 #include <vector>
@@ -9,6 +11,27 @@
 namespace qmg {
 
 Runtime& rt() { static Runtime r; return r; }
+
+struct ProfEntry { double seconds = 0.0; long calls = 0; };
+static std::map<std::string, ProfEntry>& prof_table() { static std::map<std::string, ProfEntry> t; return t; }
+static thread_local int prof_depth = 0;
+static double now_seconds() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+ProfScope::ProfScope(const char* n) : name(n), t0(0.0), on(false)
+{
+  if (!rt().profile || !rt().ready) return;
+  on = (prof_depth++ == 0);          // nested entries (one C-ABI call using another) are charged to the outer one
+  if (on) { cudaStreamSynchronize(rt().stream); t0 = now_seconds(); }
+}
+ProfScope::~ProfScope()
+{
+  if (!rt().profile || !rt().ready) return;
+  prof_depth--;
+  if (!on) return;
+  cudaStreamSynchronize(rt().stream);
+  ProfEntry& e = prof_table()[name];
+  e.seconds += now_seconds() - t0; e.calls++;
+}
 
 // Size-keyed cache of device blocks.  The Krylov solvers allocate and release their work vectors on every call
 // (like the reference's allocate_vector / deallocate_vector); cudaMalloc / cudaFree would serialise the device each
@@ -115,6 +138,8 @@ int qmg_init(int device)
   QMG_CUDA(cudaDeviceSynchronize());
   const char* env = getenv("QMG_MANAGED");
   if (env != nullptr && env[0] == '1') r.managed = 1;
+  env = getenv("QMG_PROFILE");
+  if (env != nullptr && env[0] == '1') r.profile = 1;
   r.ready = true;
   return 0;
 }
@@ -201,6 +226,22 @@ int qmg_memcpy_d2d(void* dst, const void* src, size_t bytes)
   QMG_REQUIRE_INIT();
   QMG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, rt().stream));
   return 0;
+}
+int qmg_profile_enable(int on) { rt().profile = on ? 1 : 0; return 0; }
+int qmg_profile_reset(void) { prof_table().clear(); return 0; }
+// prints "name calls seconds" rows sorted by time to stdout and returns the total seconds
+double qmg_profile_report(void)
+{
+  std::vector<std::pair<double, std::string> > rows;
+  double total = 0.0;
+  for (auto& kv : prof_table()) { rows.push_back(std::make_pair(kv.second.seconds, kv.first)); total += kv.second.seconds; }
+  std::sort(rows.begin(), rows.end());
+  printf("[QMG-PROFILE] %-28s %10s %12s %7s\n", "entry point", "calls", "seconds", "share");
+  for (size_t i = rows.size(); i-- > 0;)
+    printf("[QMG-PROFILE] %-28s %10ld %12.6f %6.1f%%\n", rows[i].second.c_str(), prof_table()[rows[i].second].calls, rows[i].first, 100.0 * rows[i].first / (total > 0 ? total : 1.0));
+  printf("[QMG-PROFILE] %-28s %10s %12.6f\n", "total", "", total);
+  fflush(stdout);
+  return total;
 }
 int qmg_set_alloc_mode(int managed) { QMG_REQUIRE_INIT(); rt().managed = managed ? 1 : 0; return 0; }
 int qmg_get_alloc_mode(void) { return rt().managed; }

@@ -55,46 +55,61 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
   const int c1 = c / NC, c2 = c % NC;
   const bool active = (k < a.g.xh) && (y < a.g.Y);
 
-  cd acc = cmake(0.0, 0.0);
-  size_t site = 0;
-  if (active)
-  {
-    const unsigned h = (unsigned)y * a.g.xh + k;
-    site = (size_t)p * a.g.half + h;
-    const int q = 1 - p;
+  // Straight-line body: every address is formed first, then all (up to 11) 16-byte loads are issued back to back as
+  // predicated loads with no branch in between, so one thread keeps ~176 B in flight and a full SM ~350 KB -- the
+  // latency-bandwidth product of HBM3e needs ~45 KB per SM.  (A branch per direction serialises the round trips.)
+  const cd zero = cmake(0.0, 0.0);
+  const unsigned h = active ? (unsigned)y * a.g.xh + k : 0u;
+  const size_t site = (size_t)p * a.g.half + h;
+  const int q = 1 - p;
+  const bool hop = active && (a.hop != nullptr) && (a.hop_to[p] != 0);
+  const bool m0 = hop && (a.dir_mask & 1), m1 = hop && (a.dir_mask & 2), m2 = hop && (a.dir_mask & 4), m3 = hop && (a.dir_mask & 8);
+  const bool has_cl = active && (a.clover != nullptr);
+  const bool has_dg = active && a.use_diag && (c1 == c2);
+  const bool writer = active && (c2 == 0);
+  const size_t idx = site * NC + c1;
 
-    if (a.clover != nullptr || (a.use_diag && c1 == c2))
-    {
-      const cd v0 = ld_keep(a.in + site * NC + c2);
-      if (a.clover != nullptr) cfma(acc, ld_stream(a.clover + site * LPS + c), v0);
-      if (a.use_diag && c1 == c2) cfma(acc, a.diag[p][(2 * c2 >= NC && NC > 1) ? 1 : 0], v0);
-    }
+  const int sft = (y + p) & 1;
+  int kxp = k + sft; kxp = (kxp == a.g.xh) ? 0 : kxp;
+  int kxm = k - 1 + sft; kxm = (kxm < 0) ? a.g.xh - 1 : kxm;
+  const int yp1 = (y + 1 == a.g.Y) ? 0 : y + 1;
+  const int ym1 = (y == 0) ? a.g.Y - 1 : y - 1;
+  const cd* in_q = a.in + (size_t)q * a.g.half * NC + c2;
+  const cd* s0 = in_q + ((size_t)y * a.g.xh + kxp) * NC;
+  const cd* s2 = in_q + ((size_t)y * a.g.xh + kxm) * NC;
+  const cd* s1 = (a.halo_yp != nullptr && y == a.g.Y - 1) ? a.halo_yp + ((size_t)q * a.g.xh + k) * NC + c2 : in_q + ((size_t)yp1 * a.g.xh + k) * NC;
+  const cd* s3 = (a.halo_ym != nullptr && y == 0) ? a.halo_ym + ((size_t)q * a.g.xh + k) * NC + c2 : in_q + ((size_t)ym1 * a.g.xh + k) * NC;
+  const cd* hp = a.hop + site * LPS + c;
 
-    if (a.hop != nullptr && a.hop_to[p])
-    {
-      const cd* in_q = a.in + (size_t)q * a.g.half * NC;
-#pragma unroll
-      for (int mu = 0; mu < 4; mu++)
-      {
-        if (!((a.dir_mask >> mu) & 1)) continue;
-        const cd* src;
-        if (mu == 1 && a.halo_yp != nullptr && y == a.g.Y - 1) src = a.halo_yp + ((size_t)q * a.g.xh + k) * NC + c2;
-        else if (mu == 3 && a.halo_ym != nullptr && y == 0) src = a.halo_ym + ((size_t)q * a.g.xh + k) * NC + c2;
-        else src = in_q + (size_t)nbr_h(a.g, p, y, k, mu) * NC + c2;
-        cfma(acc, ld_stream(a.hop + (size_t)mu * a.size_cm + site * LPS + c), ld_keep(src));
-      }
-    }
-  }
+  const cd H0 = m0 ? ld_stream(hp) : zero;
+  const cd H1 = m1 ? ld_stream(hp + a.size_cm) : zero;
+  const cd H2 = m2 ? ld_stream(hp + 2 * a.size_cm) : zero;
+  const cd H3 = m3 ? ld_stream(hp + 3 * a.size_cm) : zero;
+  const cd CL = has_cl ? ld_stream(a.clover + site * LPS + c) : zero;
+  const cd V0 = m0 ? ld_keep(s0) : zero;
+  const cd V1 = m1 ? ld_keep(s1) : zero;
+  const cd V2 = m2 ? ld_keep(s2) : zero;
+  const cd V3 = m3 ? ld_keep(s3) : zero;
+  const cd VC = (has_cl || has_dg) ? ld_keep(a.in + site * NC + c2) : zero;
+  const cd OLD = (writer && a.accumulate) ? a.out[idx] : zero;
+  const cd DG = has_dg ? a.diag[p][(2 * c2 >= NC && NC > 1) ? 1 : 0] : zero;
+
+  cd acc = zero;
+  cfma(acc, CL, VC);
+  cfma(acc, DG, VC);
+  cfma(acc, H0, V0);
+  cfma(acc, H1, V1);
+  cfma(acc, H2, V2);
+  cfma(acc, H3, V3);
 
   // sum the nc partial products of each matrix row (lanes c2 = 0..NC-1 are consecutive)
 #pragma unroll
   for (int o = NC / 2; o > 0; o >>= 1) { cd t = shfl_xor_c(acc, o); acc = cadd(acc, t); }
 
   double red[3] = {0.0, 0.0, 0.0};
-  if (active && c2 == 0)
+  if (writer)
   {
-    const size_t idx = site * NC + c1;
-    if (a.accumulate) acc = cadd(acc, a.out[idx]);
+    acc = cadd(acc, OLD);
     a.out[idx] = acc;
     if (REDUCE)
     {

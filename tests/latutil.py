@@ -45,10 +45,34 @@ def load_gauge(L, beta=60):
     return phases_to_gauge(ph, L, L)
 
 
-def synthetic_gauge(X, Y, beta=6.0, seed=1337):
-    """Gaussian non-compact phases of width 1/sqrt(beta): the large-lattice stand-in for a heatbath config."""
+def synthetic_phases(X, Y, beta=6.0, seed=1337):
+    """Link phases with the plaquette statistics of the 2D non-compact U(1) theory at coupling beta -- the large-lattice
+    stand-in for the reference's serial heatbath (u1/u1_utils.h:607-667), which needs hours beyond 1024^2.
+    In 2D the plaquette angles are independent gaussians of variance 1/beta (up to the torus constraints): draw
+    F(x,y) ~ N(0, 1/beta) with zero total flux per column, integrate it into theta_x in the gauge theta_y = 0, then apply a
+    random gauge transformation.  <cos plaquette> = exp(-1/(2 beta)) = 0.920 at beta = 6, as in tests/common_cfgs_u1.
+    Returns phases in the reference's file order (x outer, y, mu inner)."""
     rng = np.random.default_rng(seed)
-    return phases_to_gauge(rng.normal(0.0, 1.0 / np.sqrt(beta), size=X * Y * 2), X, Y)
+    F = rng.normal(0.0, 1.0 / np.sqrt(beta), size=(X, Y))
+    F -= F.mean(axis=1, keepdims=True)
+    thx = -(np.cumsum(F, axis=1) - F)
+    del F
+    a = rng.uniform(-np.pi, np.pi, size=(X, Y))
+    thx += np.roll(a, -1, axis=0) - a
+    thy = np.roll(a, -1, axis=1) - a
+    return np.stack([thx, thy], axis=2).ravel()
+
+
+def synthetic_gauge(X, Y, beta=6.0, seed=1337):
+    return phases_to_gauge(synthetic_phases(X, Y, beta, seed), X, Y)
+
+
+def average_plaquette(gauge, X, Y):
+    """<Re U_x(x) U_y(x+x^) U_x*(x+y^) U_y*(x)> (u1/u1_utils.h:424-460)."""
+    xs, ys = np.meshgrid(np.arange(X), np.arange(Y), indexing="ij")
+    idx = site_index(xs, ys, X, Y)
+    ux, uy = gauge[idx], gauge[X * Y + idx]
+    return float(np.mean((ux * np.roll(uy, -1, axis=0) * np.conj(np.roll(ux, -1, axis=1)) * np.conj(uy)).real))
 
 
 def gaussian_cv(n, seed):

@@ -149,3 +149,11 @@ def test_n13_kcycle_converges(ref):
     assert t0["presmooth"] == 5 * out["iter"] and t0["postsmooth"] == 4 * out["iter"]   # MR(2): 4 ops + residual
     assert t1["iters"] > 0 and t1["krylov"] >= t1["iters"]
     kc.free()
+
+
+def test_synthetic_gauge_matches_heatbath_plaquette():
+    """The large-lattice synthetic field has the plaquette of the reference's thermalised beta = 6 configs."""
+    L = 64
+    want = np.exp(-1.0 / 12.0)
+    assert abs(latutil.average_plaquette(latutil.load_gauge(L), L, L) - want) < 0.01
+    assert abs(latutil.average_plaquette(latutil.synthetic_gauge(L, L, 6.0, 5), L, L) - want) < 0.01
