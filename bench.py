@@ -8,8 +8,10 @@ A "step" is one out-of-place apply lhs = M rhs over the whole (per-rank) lattice
 whole-job algorithmic GB/s (384 B/site for the stored-block Wilson operator) with all
 operands resident in HBM; `e2e` is the same apply through the C ABI with HOST source/result vectors
 (pinned host -> device copy of rhs and device -> host copy of lhs inside the timed region).
-N > 1: y-slab weak scaling, every rank owns an L x L slab of an L x (N L) lattice and exchanges
-one boundary row with its two ring neighbours per apply.
+N > 1: y-slab weak scaling, every rank owns an L x L slab of an L x (N L) lattice; the library
+(qmg_comm_init) exchanges one boundary row with the two ring neighbours per apply, overlapped with
+the interior rows.  The second half of the metric, the 3-level Wilson K-cycle solve, runs on the
+same slabs (`kcycle` in the JSON line).
 
 --impl reference: the reference's own CPU implementation (oracle/_ref: the unmodified reference
 headers, single thread -- the reference has no threading) on a bounded sample of the same workload.
@@ -83,9 +85,11 @@ def cpu_reference_apply(L, reps, warm=1):
     return BYTES_PER_SITE * L * L / sec / 1e9, sec
 
 
-def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=None):
+def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=None, world=1, rank=0):
     """3-level (n_refine=2) Wilson K-cycle as tests/n13_wilson_kcycle sets it up (4x4 blocks, 8 coarse dof, BiCGstab-6 null
-    vectors, MR(2,2) smoothing, inner tol 0.2), mass -0.075, gaussian right-hand side; returns the solve record."""
+    vectors, MR(2,2) smoothing, inner tol 0.2), gaussian right-hand side; returns the solve record.
+    world > 1 (after qmg.comm_init): this rank owns an L x L y-slab of the L x (world L) lattice (weak scaling); the
+    hierarchy, the solvers and the K-cycle are the same host code, the library exchanges halo rows and all-reduces dots."""
     import capi
     import latutil
     be = capi.Backend(backend)
@@ -96,19 +100,28 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
     mass = -0.05
     if gauge is None:
         try:
+            if world > 1:
+                raise ValueError
             gauge = latutil.load_gauge(L)          # the reference's own thermalised config where one exists (32, 64, 128, 256)
             cfg = "tests/common_cfgs_u1 l%dt%db60" % (L, L)
         except Exception:
-            gauge = latutil.synthetic_gauge(L, L, beta=6.0, seed=seed)
-            cfg = "synthetic non-compact U(1), beta 6.0, seed %d (tests/latutil.py synthetic_phases)" % seed
+            gauge = latutil.synthetic_gauge(L, L, beta=6.0, seed=seed + rank, slab=True)
+            cfg = "synthetic non-compact U(1), beta 6.0, seed %d + rank, one stackable slab per rank (tests/latutil.py synthetic_phases)" % seed
     else:
         cfg = "caller-supplied"
     t0 = time.perf_counter()
     kc = capi.KCycle(be, L, mass, gauge, n_refine=n_refine, seed=seed, inner_iters=100, coarsest_iters=400)
+    del gauge
     out = kc.solve(tol=tol, restart=restart, max_iter=100)
     out["mass"] = mass
     out["levels"] = n_refine + 1
     out["L"] = L
+    out["lattice"] = [L, L * world]
+    out["outer_restart"] = restart
+    if backend == "gpu":
+        import torch
+        free, total = torch.cuda.mem_get_info()
+        out["hbm_in_use_gb"] = (total - free) / 1e9
     out["config"] = cfg
     out["per_level_ops"] = [kc.tracker(l)["total"] for l in range(n_refine + 1)]
     out["per_level_iters"] = [kc.tracker(l)["iters"] for l in range(n_refine + 1)]
@@ -157,6 +170,8 @@ def run_gpu(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     qmg.init(local)
+    if world > 1:
+        qmg.comm_init()          # from here on every lattice handed to the library is this rank's y-slab
     lib = qmg.lib()
     L = args.L
     X, Y = L, L
@@ -173,31 +188,11 @@ def run_gpu(args):
     rhs = qmg.cvec(n)
     qmg.check(lib.qmg_gaussian(qmg.ptr(rhs), C.c_long(n), C.c_uint64(7), C.c_uint64(rank), C.c_double(1.0)))
     lhs = qmg.cvec(n)
-    halo_ym = halo_yp = None
-    row = X * 2  # complex elements in one boundary row (both parities)
-    if world > 1:
-        halo_ym, halo_yp = qmg.cvec(row), qmg.cvec(row)
-        send_lo, send_hi = qmg.cvec(row), qmg.cvec(row)
-    desc = qmg.stencil_desc(X, Y, 2, clover, hopping, shift=-0.075, halo_ym=halo_ym, halo_yp=halo_yp)
-    xh = X // 2
-    half = xh * Y * 2
-
-    def exchange():
-        # boundary rows y=0 and y=Y-1 of rhs (parity-major) to the ring neighbours
-        import torch.distributed as dist
-        send_lo[:xh * 2] = rhs[0:xh * 2]
-        send_lo[xh * 2:] = rhs[half:half + xh * 2]
-        send_hi[:xh * 2] = rhs[(Y - 1) * xh * 2:Y * xh * 2]
-        send_hi[xh * 2:] = rhs[half + (Y - 1) * xh * 2:half + Y * xh * 2]
-        up, down = (rank + 1) % world, (rank - 1) % world
-        ops = [dist.P2POp(dist.isend, send_hi, up), dist.P2POp(dist.irecv, halo_ym, down),
-               dist.P2POp(dist.isend, send_lo, down), dist.P2POp(dist.irecv, halo_yp, up)]
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
+    desc = qmg.stencil_desc(X, Y, 2, clover, hopping, shift=-0.075)
 
     def step():
-        if world > 1:
-            exchange()
+        # N > 1: the library sends the two boundary rows of rhs round the ring on its exchange stream while the interior
+        # rows are computed, then finishes rows 0 and Y-1 (qmg_stencil_apply, csrc/qmg_stencil.cu apply_sharded)
         qmg.stencil_apply(desc, lhs, rhs)
 
     def barrier():
@@ -257,11 +252,17 @@ def run_gpu(args):
 
     # second half of the metric: 3-level Wilson K-cycle solve time (single GPU leg; the sharded solve is reported by --kcycle-sharded)
     kcycle = kcycle_same = None
-    if world == 1 and args.kcycle_L > 0:
+    if args.kcycle_L > 0:
         del clover, hopping, rhs, lhs, desc
         torch.cuda.empty_cache()
-        kcycle = kcycle_run("gpu", args.kcycle_L)
-        if args.cpu_kcycle_L > 0 and not args.no_cpu:
+        kcycle = kcycle_run("gpu", args.kcycle_L, restart=args.kcycle_restart, world=world, rank=rank)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([kcycle["seconds"], kcycle["setup_seconds"], kcycle["precond_apply_s"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)     # wall time between device synchronisations, max over ranks
+            kcycle["seconds"], kcycle["setup_seconds"], kcycle["precond_apply_s"] = (float(v) for v in t.tolist())
+            kcycle["comm"] = qmg.comm_counters()
+        if world == 1 and args.cpu_kcycle_L > 0 and not args.no_cpu:
             kcycle_same = kcycle_run("gpu", args.cpu_kcycle_L)
 
     if rank == 0:
@@ -295,6 +296,7 @@ def run_gpu(args):
         }))
     if world > 1:
         import torch.distributed as dist
+        qmg.comm_finalize()
         dist.destroy_process_group()
 
 
@@ -308,7 +310,9 @@ def main():
     ap.add_argument("--cpu-L", type=int, default=2048, dest="cpu_L")
     ap.add_argument("--cpu-reps", type=int, default=5, dest="cpu_reps")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")
-    ap.add_argument("--kcycle-L", type=int, default=4096, dest="kcycle_L", help="3-level K-cycle solve on L x L after the stencil run (0 = skip)")
+    ap.add_argument("--kcycle-L", type=int, default=8192, dest="kcycle_L", help="3-level K-cycle solve on L x L per GPU after the stencil run (0 = skip)")
+    ap.add_argument("--kcycle-restart", type=int, default=16, dest="kcycle_restart",
+                    help="restart length of the outer flexible GCR (n13 uses 32; at 8192^2 per GPU 2 x 32 stored 2.1 GB vectors do not fit beside the hierarchy)")
     ap.add_argument("--cpu-kcycle-L", type=int, default=128, dest="cpu_kcycle_L", help="K-cycle size for the CPU reference leg (a bounded sample: the reference needs ~10 s at 128x128; 0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -145,8 +145,26 @@ inline void orthogonal(qmg_cd* v, const qmg_cd* against, long n) { const qmg_cd 
 // -------------------------------------------------------------------- RNG --
 // Host draws in the quantum-linalg order (re, im per element from one std::mt19937 stream),
 // staged to the device: a driver seeded like the reference's produces the same vectors on both.
+// Exception: when the lattice is sharded over several GPUs, for vectors beyond 2^22 elements, or with QMG_DEVICE_RNG=1,
+// the fill is the counter-based device generator keyed by two words drawn from `gen` -- a slab cannot reproduce its part
+// of one serial mt19937 stream without drawing the whole lattice, and host draws of 10^8 normals take seconds.  The
+// device stream is indexed by the GLOBAL element, so 1 GPU and N GPUs draw the same vector.
+namespace qmg_host {
+inline bool device_rng(long n)
+{
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("QMG_DEVICE_RNG"); forced = (e != 0 && e[0] == '1') ? 1 : 0; }
+  return forced == 1 || qmg_comm_size() > 1 || n > (1L << 22);
+}
+}
 inline void gaussian(qmg_cd* v, long n, std::mt19937& gen, double dev = 1.0)
 {
+  if (qmg_host::device_rng(n))
+  {
+    const unsigned long long hi = gen(), lo = gen();
+    QMG_CHK(qmg_gaussian(qmg_host::P(v), n, (hi << 32) | lo, 0ULL, dev));
+    return;
+  }
   std::vector<qmg_cd> h((size_t)n);
   std::normal_distribution<double> dist(0.0, dev);
   for (long i = 0; i < n; i++) { const double re = dist(gen); const double im = dist(gen); h[i] = qmg_cd(re, im); }

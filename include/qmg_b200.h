@@ -63,6 +63,29 @@ int qmg_get_alloc_mode(void);
 int qmg_malloc_host(void** hptr, size_t bytes);   /* pinned host staging */
 int qmg_free_host(void* hptr);
 
+/* --------------------------------------------------------------- sharding -- */
+/* y-slab sharding over the GPUs of one node, one process per GPU (the "Becomes MPI" periodic-boundary loops of
+ * cshift/cshift_2d.h:72-205).  After qmg_comm_init with nranks > 1 every lattice handed to this library is the LOCAL slab
+ * (X, Y/nranks) of rank `rank`, and
+ *   - qmg_stencil_apply exchanges one boundary row of rhs with the two ring neighbours over NCCL, overlapped with the
+ *     interior rows (when the descriptor's halo pointers are NULL);
+ *   - the link fills, variant builders and the coarse build exchange the boundary rows of their inputs once;
+ *   - every reduction is all-reduced over the ranks before it is returned;
+ *   - prolong / restrict / block-orthonormalise stay local (slab heights must be multiples of the block size).
+ * unique_id128: the 128-byte NCCL id from qmg_comm_unique_id on rank 0, handed to every rank by the caller (any out-of-band channel). */
+int qmg_comm_unique_id(void* out128);
+int qmg_comm_init(int nranks, int rank, const void* unique_id128);
+int qmg_comm_finalize(void);
+int qmg_comm_size(void);
+int qmg_comm_rank(void);
+int qmg_comm_active(void);
+/* Single-rank loopback: the slab is the whole periodic lattice, but every access across y = 0 / Y-1 goes through the
+ * pack / exchange / halo-row path of the sharded build (device copies instead of NCCL).  For single-GPU testing. */
+int qmg_comm_set_loopback(int on);
+long qmg_comm_halo_exchanges(void);
+long qmg_comm_allreduces(void);
+int qmg_halo_exchange(const qmg_cplx* field, int X, int Y, int dof, qmg_cplx* out_ym, qmg_cplx* out_yp);
+
 /* ------------------------------------------------------------ stencil ---- */
 /* One stored stencil = one pointer set of Stencil2D (stencil/stencil_2d.h:148-210). */
 typedef struct qmg_stencil_desc
@@ -169,7 +192,8 @@ int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p, const qmg_cplx* 
 int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y, long n);
 /* y = x0 + sum_j a_j xs[j]   (GCR: p_k = r + sum beta_i p_i without a separate copy); x0 == y allowed */
 int qmg_multi_axpyz(const double* a_host, const qmg_cplx* const* xs_host, int k, const qmg_cplx* x0, qmg_cplx* y, long n);
-/* gaussian fill, counter-based (Philox) so results do not depend on the launch shape */
+/* gaussian fill, counter-based (Philox) so results do not depend on the launch shape; when sharded the counter is the
+ * GLOBAL element index of an even-odd field (the ranks together draw what one GPU draws for the whole lattice) */
 int qmg_gaussian(qmg_cplx* x, long n, uint64_t seed, uint64_t stream_id, double dev);
 
 /* ------------------------------------------------------------ transfer ---- */

@@ -57,7 +57,7 @@ def build_kernels(force=False, verbose=False):
                 print(out)
     lib = os.path.join(HERE, "libqmg_b200.so")
     if force or _newer(lib, objs):
-        _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs)
+        _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-ldl"])
     return lib
 
 

@@ -323,7 +323,7 @@ int qmg_norminf(const qmg_cplx* x_, long n, double* result)
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
   norminf_kernel<<<grid, kEwBlock, 0, r.stream>>>(CCD(x_), n, r.d_partials, r.d_counter, r.d_result);
   QMG_LAUNCH_CHECK();
-  return fetch_result(result, 1);
+  return fetch_result(result, 1, 1);
 }
 
 } // extern "C"
@@ -457,8 +457,15 @@ extern "C" int qmg_gaussian(qmg_cplx* x_, long n, uint64_t seed, uint64_t stream
 {
   QMG_REQUIRE_INIT();
   cd* x = CD(x_);
+  // y-slab sharding: element i of the local even-odd field is element  p * (N half) + rank * half + i'  of the global one
+  // (i = p * half + i'), so the ranks together draw exactly the vector a single GPU would draw for the whole lattice.
+  const long half = n / 2;
+  const long nranks = qmg_comm_size(), rank = qmg_comm_rank();
+  const bool split = nranks > 1 && (n % 2 == 0);
   return launch_ew(n, [=] __device__(long i) {
-    uint32_t c[4] = { (uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32) };
+    long gi = i;
+    if (split) { const long p = i >= half ? 1 : 0; gi = p * nranks * half + rank * half + (i - p * half); }
+    uint32_t c[4] = { (uint32_t)gi, (uint32_t)((uint64_t)gi >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32) };
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     // two 53-bit-ish uniforms in (0,1): 32 random bits each, centred
     const double u1 = ((double)c[0] + 0.5) * (1.0 / 4294967296.0);

@@ -72,9 +72,13 @@ int fail_msg(const char* msg)
   return 2;
 }
 
-int fetch_result(double* host_out, int count)
+int allreduce_result(double* d_buf, int count, int op_max);   // qmg_comm.cu
+
+int fetch_result(double* host_out, int count, int op_max)
 {
   Runtime& r = rt();
+  int rc = allreduce_result(r.d_result, count, op_max);
+  if (rc) return rc;
   QMG_CUDA(cudaMemcpyAsync(r.h_result, r.d_result, sizeof(double) * count, cudaMemcpyDeviceToHost, r.stream));
   QMG_CUDA(cudaStreamSynchronize(r.stream));
   for (int i = 0; i < count; i++) host_out[i] = r.h_result[i];
@@ -141,6 +145,8 @@ int qmg_init(int device)
   env = getenv("QMG_PROFILE");
   if (env != nullptr && env[0] == '1') r.profile = 1;
   r.ready = true;
+  env = getenv("QMG_LOOPBACK");   // single-GPU exercise of the sharded code path (see qmg_comm_set_loopback)
+  if (env != nullptr && env[0] == '1') return qmg_comm_set_loopback(1);
   return 0;
 }
 
@@ -148,6 +154,7 @@ int qmg_finalize(void)
 {
   Runtime& r = rt();
   if (!r.ready) return 0;
+  qmg_comm_finalize();
   cache_trim();
   cudaFree(r.d_partials); cudaFree(r.d_counter); cudaFree(r.d_result); cudaFree(r.d_ptrs); cudaFree(r.d_scalars);
   cudaFreeHost(r.h_result);

@@ -2,7 +2,7 @@
 // builders (K9), cshift, and the batched nc x nc site-matrix routines (K3).
 // None of these is on the per-iteration path; they are written to be
 // coalesced (one thread per OUTPUT element) and correct, not tuned.
-#include "qmg_lattice.cuh"
+#include "qmg_comm.cuh"
 
 namespace qmg {
 
@@ -39,6 +39,14 @@ __device__ __forceinline__ long site_nbr(const Geom& g, long site, int mu)
   return (long)(1 - p) * g.half + nbr_h(g, p, y, k, mu);
 }
 
+// first dof of `field` (dof complex per site) at the neighbour of `site` in direction mu; across the slab edges the
+// value comes from the rows received from the ring neighbours (y-slab sharding) when they are present
+__device__ __forceinline__ const cd* field_nbr(const Geom& g, const cd* field, const HaloRows& h, long site, int mu, int dof)
+{
+  int p, y, k; site_decode(g, site, p, y, k);
+  return nbr_site_ptr(field, h, g, p, y, k, mu, dof);
+}
+
 static inline int check_dims(int X, int Y, const char* who)
 {
   if (X < 2 || Y < 2 || (X & 1) || (Y & 1)) { fail_msg(who); return 1; }
@@ -48,11 +56,22 @@ static inline int check_dims(int X, int Y, const char* who)
 // Link that multiplies the neighbour in direction mu, as seen from `site`:
 // U_mu(x) for forward hops, conj(U_mu(x - mu)) for backward hops
 // (wilson.h:178-209: cshift FROM_XM1/YM1 then conj_vector).
-__device__ __forceinline__ cd link_for(const Geom& g, const cd* gauge, long V, long site, int mu)
+// hy: rows -1 / Y of the U_y field when the lattice is a slab of a sharded one.
+__device__ __forceinline__ cd link_for(const Geom& g, const cd* gauge, const HaloRows& hy, long V, long site, int mu)
 {
   if (mu < 2) return gauge[(long)mu * V + site];
+  if (mu == 3) return cconj(*field_nbr(g, gauge + V, hy, site, 3, 1));
   const long back = site_nbr(g, site, mu);
   return cconj(gauge[(long)(mu - 2) * V + back]);
+}
+
+// rows -1 / Y of U_y for the link fills
+static int gauge_halo(HaloTemp& t, const cd* gauge, int X, int Y, HaloRows& hy)
+{
+  int rc = t.fetch(gauge + (long)X * Y, 0, 1, X, Y, 1);
+  if (rc) return rc;
+  hy = t.rows(0, X, 1);
+  return 0;
 }
 
 } // namespace qmg
@@ -73,6 +92,8 @@ int qmg_fill_wilson(int X, int Y, double w, const qmg_cplx* gauge_, qmg_cplx* cl
   const cd* gauge = CCD(gauge_); cd* clover = CD(clover_); cd* hop = CD(hopping_);
   Geom g; g.xh = X / 2; g.Y = Y; g.half = (unsigned)(X / 2) * Y;
   const long V = (long)X * Y;
+  HaloTemp halo; HaloRows hy;
+  { int hrc = gauge_halo(halo, gauge, X, Y, hy); if (hrc) return hrc; }
   return launch_n(V * 4 * 5, [=] __device__(long e) {
     const long per = V * 4;
     const int which = (int)(e / per);        // 0 clover, 1..4 hopping mu = which-1
@@ -81,7 +102,7 @@ int qmg_fill_wilson(int X, int Y, double w, const qmg_cplx* gauge_, qmg_cplx* cl
     const bool diagel = (c == 0 || c == 3);
     if (which == 0) { clover[r] = diagel ? cmake(2.0 * w, 0.0) : cmake(0.0, 0.0); return; }
     const int mu = which - 1;
-    const cd u = link_for(g, gauge, V, site, mu);
+    const cd u = link_for(g, gauge, hy, V, site, mu);
     cd coef;
     if (diagel) coef = cmake(-0.5 * w, 0.0);
     else if (mu == 0) coef = cmake(0.5, 0.0);
@@ -100,6 +121,8 @@ int qmg_fill_staggered(int X, int Y, const qmg_cplx* gauge_, qmg_cplx* hopping_)
   const cd* gauge = CCD(gauge_); cd* hop = CD(hopping_);
   Geom g; g.xh = X / 2; g.Y = Y; g.half = (unsigned)(X / 2) * Y;
   const long V = (long)X * Y;
+  HaloTemp halo; HaloRows hy;
+  { int hrc = gauge_halo(halo, gauge, X, Y, hy); if (hrc) return hrc; }
   return launch_n(V * 4, [=] __device__(long e) {
     const int mu = (int)(e / V);
     const long site = e - (long)mu * V;
@@ -107,7 +130,7 @@ int qmg_fill_staggered(int X, int Y, const qmg_cplx* gauge_, qmg_cplx* hopping_)
     const double eta = ((y + p) & 1) ? -1.0 : 1.0;      // x mod 2 = (y+p)&1
     double s = (mu < 2) ? -0.5 : 0.5;
     if (mu & 1) s *= eta;
-    const cd u = link_for(g, gauge, V, site, mu);
+    const cd u = link_for(g, gauge, hy, V, site, mu);
     hop[e] = cmake(s * u.x, s * u.y);
   });
 }
@@ -120,12 +143,14 @@ int qmg_fill_laplace(int X, int Y, const qmg_cplx* gauge_, qmg_cplx* clover_, qm
   const cd* gauge = CCD(gauge_); cd* clover = CD(clover_); cd* hop = CD(hopping_);
   Geom g; g.xh = X / 2; g.Y = Y; g.half = (unsigned)(X / 2) * Y;
   const long V = (long)X * Y;
+  HaloTemp halo; HaloRows hy;
+  { int hrc = gauge_halo(halo, gauge, X, Y, hy); if (hrc) return hrc; }
   return launch_n(V * 5, [=] __device__(long e) {
     const int which = (int)(e / V);
     const long site = e - (long)which * V;
     if (which == 0) { clover[site] = cmake(4.0, 0.0); return; }
     const int mu = which - 1;
-    const cd u = link_for(g, gauge, V, site, mu);
+    const cd u = link_for(g, gauge, hy, V, site, mu);
     hop[(long)mu * V + site] = cmake(-u.x, -u.y);
   });
 }
@@ -142,6 +167,8 @@ int qmg_fill_dwf(int X, int Y, int Ls, double w, double mass_re, double mass_im,
   const long V = (long)X * Y;
   const int nc = 2 * Ls; const long nc2 = (long)nc * nc;
   const cd mass = cmake(mass_re, mass_im);
+  HaloTemp halo; HaloRows hy;
+  { int hrc = gauge_halo(halo, gauge, X, Y, hy); if (hrc) return hrc; }
   return launch_n(V * nc2 * 5, [=] __device__(long e) {
     const long per = V * nc2;
     const int which = (int)(e / per);
@@ -171,7 +198,7 @@ int qmg_fill_dwf(int X, int Y, int Ls, double w, double mass_re, double mass_im,
       else if (mu == 2) coef = cmake(-0.5, 0.0);
       else if (mu == 1) coef = (cc == 1) ? cmake(0.0, -0.5) : cmake(0.0, 0.5);
       else coef = (cc == 1) ? cmake(0.0, 0.5) : cmake(0.0, -0.5);
-      out = cmul(coef, link_for(g, gauge, V, site, mu));
+      out = cmul(coef, link_for(g, gauge, hy, V, site, mu));
     }
     hop[(long)mu * per + r] = out;
   });
@@ -195,14 +222,23 @@ int qmg_build_dagger(int X, int Y, int nc, const qmg_cplx* clover_, const qmg_cp
     });
   if (rc) return rc;
   if (hop != nullptr && dhop != nullptr)
+  {
+    // sharded: row Y of hopping_{-y} (for mu = +y) and row -1 of hopping_{+y} (for mu = -y) come from the ring neighbours
+    HaloTemp halo;
+    rc = halo.fetch(hop, per, 4, X, Y, (int)nc2); if (rc) return rc;
+    const cd* hym = halo.ym; const cd* hyp = halo.yp;
+    const long hrow = (long)X * nc2;
     rc = launch_n(per * 4, [=] __device__(long e) {
       const int mu = (int)(e / per);
       const long r = e - (long)mu * per;
       const long site = r / nc2; const int c = (int)(r - site * nc2);
       const int row = c / nc, col = c % nc;
-      const long nb = site_nbr(g, site, mu);
-      dhop[e] = cconj(hop[(long)opposite_dir(mu) * per + nb * nc2 + (long)col * nc + row]);
+      const int om = opposite_dir(mu);
+      HaloRows h; if (hym != nullptr) { h.ym = hym + om * hrow; h.yp = hyp + om * hrow; }
+      const cd* nb = field_nbr(g, hop + (long)om * per, h, site, mu, (int)nc2);
+      dhop[e] = cconj(nb[(long)col * nc + row]);
     });
+  }
   return rc;
 }
 
@@ -216,13 +252,21 @@ int qmg_cshift(qmg_cplx* lhs_, const qmg_cplx* rhs_, int cdir, int eo, int dof, 
   Geom g; g.xh = X / 2; g.Y = Y; g.half = (unsigned)(X / 2) * Y;
   const int mu = cdir - 2;    // QMG_CSHIFT_FROM_XP1=2 .. YM1=5  ->  +x,+y,-x,-y
   const long V = (long)X * Y;
+  HaloTemp halo; HaloRows h;
+  if (comm().active && (mu & 1))
+  {
+    // the periodic-boundary loops the reference marks "Becomes MPI" (cshift_2d.h:101,114)
+    if (halo.alloc_rows(X, dof)) return 1;
+    int rc = halo_exchange_sync(rhs, X, Y, dof, halo.ym, halo.yp, eo & 3); if (rc) return rc;
+    h = halo.rows(0, X, dof);
+  }
   return launch_n(V * dof, [=] __device__(long e) {
     const long site = e / dof; const int d = (int)(e - site * dof);
     const int p = site >= (long)g.half ? 1 : 0;
     // destination parity p receives from source parity 1-p: FROM_EVEN(1) writes odd, FROM_ODD(2) writes even
     const int need = p ? 1 : 2;
     if (!(eo & need)) return;
-    lhs[e] = rhs[site_nbr(g, site, mu) * dof + d];
+    lhs[e] = field_nbr(g, rhs, h, site, mu, dof)[d];
   });
 }
 
@@ -424,18 +468,23 @@ int qmg_build_rbjacobi(const qmg_stencil_desc* st, qmg_cplx* cinv_, qmg_cplx* rb
   });
   if (rc) return rc;
   if (hop != nullptr && rhop != nullptr)
+  {
+    // sharded: B^-1 on rows -1 / Y comes from the ring neighbours
+    HaloTemp halo;
+    rc = halo.fetch(cinv, 0, 1, st->X, st->Y, (int)nc2); if (rc) return rc;
+    const HaloRows hr = halo.rows(0, st->X, (int)nc2);
     rc = launch_n(per * 4, [=] __device__(long e) {
       const int mu = (int)(e / per);
       const long r = e - (long)mu * per;
       const long site = r / nc2; const int c = (int)(r - site * nc2);
       const int row = c / nc, col = c % nc;
-      const long nb = site_nbr(g, site, mu);
       const cd* h = hop + (long)mu * per + site * nc2 + (long)row * nc;
-      const cd* b = cinv + nb * nc2 + col;
+      const cd* b = field_nbr(g, cinv, hr, site, mu, (int)nc2) + col;
       cd acc = cmake(0.0, 0.0);
       for (int k = 0; k < nc; k++) cfma(acc, h[k], b[(long)k * nc]);
       rhop[e] = acc;
     });
+  }
   return rc;
 }
 

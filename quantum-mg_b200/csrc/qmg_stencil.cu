@@ -17,7 +17,7 @@
 //
 // HBM-bound: 16*(nc^2*(n_clover+4) + 2nc) algorithmic bytes per site
 // (Wilson 384 B, coarse nc=8 5376 B) for 8*nc^2*(n_clover+4) flops.
-#include "qmg_lattice.cuh"
+#include "qmg_comm.cuh"
 
 namespace qmg {
 
@@ -40,6 +40,8 @@ struct StencilKArgs
   int p_begin;          // first parity written
   int n_par;            // parities written; the parity is the FASTEST block index so that the even and the odd
                         // output rows y are in flight together and each input row is fetched from HBM once
+  int y_off, y_stride, y_cnt;   // rows of this launch: y = y_off + i * y_stride, i < y_cnt (all rows: 0, 1, Y; the two
+                                // slab-boundary rows of a sharded apply: 0, Y-1, 2; its interior: 1, 1, Y-2)
 };
 
 template <int NC, bool REDUCE>
@@ -48,12 +50,13 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
   constexpr int LPS = NC * NC;   // lanes per site
   const int bxi = (a.n_par == 2) ? (blockIdx.x >> 1) : blockIdx.x;
   const int col = bxi * blockDim.x + threadIdx.x;   // element inside the row
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int yi = blockIdx.y * blockDim.y + threadIdx.y;
+  const int y = a.y_off + yi * a.y_stride;
   const int p = a.p_begin + ((a.n_par == 2) ? (blockIdx.x & 1) : 0);
   const int k = col / LPS;
   const int c = col % LPS;
   const int c1 = c / NC, c2 = c % NC;
-  const bool active = (k < a.g.xh) && (y < a.g.Y);
+  const bool active = (k < a.g.xh) && (yi < a.y_cnt);
 
   // Straight-line body: every address is formed first, then all (up to 11) 16-byte loads are issued back to back as
   // predicated loads with no branch in between, so one thread keeps ~176 B in flight and a full SM ~350 KB -- the
@@ -177,14 +180,16 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
 // (site, row), looping over the columns.  Slow path, same arithmetic.
 __global__ void __launch_bounds__(256) stencil_kernel_generic(const StencilKArgs a, int nc, int n_par)
 {
-  const long rows = (long)n_par * a.g.half * nc;
+  const long sub_half = (long)a.y_cnt * a.g.xh;     // sites per parity in this launch's row set
+  const long rows = (long)n_par * sub_half * nc;
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < rows; t += (long)gridDim.x * blockDim.x)
   {
     const int c1 = (int)(t % nc);
     const long s = t / nc;
-    const int p = a.p_begin + (int)(s / a.g.half);
-    const unsigned h = (unsigned)(s % a.g.half);
-    const int y = h / a.g.xh, k = h % a.g.xh;
+    const int p = a.p_begin + (int)(s / sub_half);
+    const long hs = s % sub_half;
+    const int y = a.y_off + (int)(hs / a.g.xh) * a.y_stride, k = (int)(hs % a.g.xh);
+    const unsigned h = (unsigned)y * a.g.xh + k;
     const size_t site = (size_t)p * a.g.half + h;
     const int q = 1 - p;
     const size_t lps = (size_t)nc * nc;
@@ -253,6 +258,7 @@ static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   if (pieces & QMG_APPLY_ODD_ROWS_ONLY) { a.p_begin = 1; n_par = 1; }
   if (single_site) { a.p_begin = 0; n_par = 1; }
   a.n_par = n_par;
+  a.y_off = 0; a.y_stride = 1; a.y_cnt = a.g.Y;
   return 0;
 }
 
@@ -264,9 +270,9 @@ static int launch_stencil(const StencilKArgs& a, int n_par, bool reduce)
   int bx = 256;
   while (bx > 32 && bx / 2 >= row_elems) bx /= 2;
   int by = 256 / bx;
-  if (by > a.g.Y) by = a.g.Y;
+  if (by > a.y_cnt) by = a.y_cnt;
   dim3 block(bx, by, 1);
-  dim3 grid(((row_elems + bx - 1) / bx) * n_par, (a.g.Y + by - 1) / by, 1);
+  dim3 grid(((row_elems + bx - 1) / bx) * n_par, (a.y_cnt + by - 1) / by, 1);
   if (grid.y > 65535) return fail_msg("qmg_stencil_apply: Y too large for the launch grid");
   if (reduce)
   {
@@ -294,11 +300,44 @@ static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduc
   }
   if (reduce) return fail_msg("qmg_stencil_apply_dot: fused reduction needs nc in {1,2,4,8,16,32}");
   Runtime& r = rt();
-  const long rows = (long)n_par * a.g.half * nc;
+  const long rows = (long)n_par * a.y_cnt * a.g.xh * nc;
   long blocks = (rows + 255) / 256, cap = (long)r.sm_count * 8;
   stencil_kernel_generic<<<(int)(blocks < cap ? blocks : cap), 256, 0, r.stream>>>(a, nc, n_par);
   QMG_LAUNCH_CHECK();
   return 0;
+}
+
+// Does this apply read rows of rhs that live on the ring neighbours?  (sharded, a hop in +-y, no caller-supplied rows)
+static bool needs_exchange(const StencilKArgs& a)
+{
+  return comm().active && a.hop != nullptr && (a.dir_mask & 10) != 0 && a.halo_ym == nullptr && a.halo_yp == nullptr &&
+         (a.hop_to[0] || a.hop_to[1]) && a.g.half > 1;
+}
+// parities of rhs whose boundary rows are read: writing parity p hops from parity 1 - p
+static int exchange_parities(const StencilKArgs& a, int n_par)
+{
+  int m = 0;
+  for (int i = 0; i < n_par; i++) { const int p = a.p_begin + i; if (a.hop_to[p]) m |= 1 << (1 - p); }
+  return m;
+}
+
+// Sharded apply: the two boundary rows of rhs travel on the exchange stream while the interior rows are computed;
+// rows 0 and Y-1 follow once the neighbours' rows have arrived.
+static int apply_sharded(StencilKArgs& a, int nc, int n_par)
+{
+  HaloRows rows;
+  int rc = halo_exchange_begin(a.in, 2 * a.g.xh, a.g.Y, nc, exchange_parities(a, n_par), &rows);
+  if (rc) return rc;
+  if (a.g.Y > 2)
+  {
+    a.y_off = 1; a.y_stride = 1; a.y_cnt = a.g.Y - 2;
+    rc = dispatch_stencil(a, nc, n_par, false);
+    if (rc) return rc;
+  }
+  rc = halo_exchange_end(); if (rc) return rc;
+  a.halo_ym = rows.ym; a.halo_yp = rows.yp;
+  a.y_off = 0; a.y_stride = a.g.Y - 1; a.y_cnt = 2;
+  return dispatch_stencil(a, nc, n_par, false);
 }
 
 } // namespace qmg
@@ -313,6 +352,7 @@ int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   StencilKArgs a; int n_par;
   int rc = build_args(st, pieces, dir_mask, lhs, rhs, a, n_par);
   if (rc) return rc;
+  if (needs_exchange(a)) return apply_sharded(a, st->nc, n_par);
   return dispatch_stencil(a, st->nc, n_par, false);
 }
 
@@ -323,6 +363,14 @@ int qmg_stencil_apply_dot(const qmg_stencil_desc* st, int pieces, qmg_cplx* lhs,
   int rc = build_args(st, pieces, 15, lhs, rhs, a, n_par);
   if (rc) return rc;
   a.dotw = reinterpret_cast<const cd*>(dot_with);
+  if (needs_exchange(a))
+  {
+    // the fused reduction finishes in ONE launch (last-block tail), so the rows are fetched first, without overlap
+    HaloRows rows;
+    rc = halo_exchange_begin(a.in, st->X, st->Y, st->nc, exchange_parities(a, n_par), &rows); if (rc) return rc;
+    rc = halo_exchange_end(); if (rc) return rc;
+    a.halo_ym = rows.ym; a.halo_yp = rows.yp;
+  }
   rc = dispatch_stencil(a, st->nc, n_par, true);
   if (rc) return rc;
   return fetch_result(result3, 3);

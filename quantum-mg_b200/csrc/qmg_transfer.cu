@@ -10,7 +10,7 @@
 //
 // All four kernels are HBM-bound streaming passes over the null vectors
 // (16 (N_f (nvec + 1) + N_c) algorithmic bytes per prolong / restrict).
-#include "qmg_lattice.cuh"
+#include "qmg_comm.cuh"
 
 namespace qmg {
 
@@ -258,6 +258,10 @@ struct CoarseBuildArgs
   cd* const* R;          // device table of ncc restrict vectors
   cd* clover_c;
   cd* hopping_c;
+  // y-slab sharding: rows -1 / Y of the ncc prolong vectors from the ring neighbours (vector b at + b * prow), or nullptr
+  const cd* Pym;
+  const cd* Pyp;
+  long prow;             // Xf ncf
 };
 
 __global__ void __launch_bounds__(256) coarse_build_kernel(const CoarseBuildArgs a, const int nchunk)
@@ -296,16 +300,18 @@ __global__ void __launch_bounds__(256) coarse_build_kernel(const CoarseBuildArgs
         {
           if (tgt != 0 && mu != tgt - 1) continue;
           int xn = x, yn = y;
+          const cd* hrows = nullptr;     // set when the neighbour lives on the next slab
           if (mu == 0) xn = (x + 1 == g.Xf) ? 0 : x + 1;
           else if (mu == 2) xn = (x == 0) ? g.Xf - 1 : x - 1;
-          else if (mu == 1) yn = (y + 1 == g.Yf) ? 0 : y + 1;
-          else yn = (y == 0) ? g.Yf - 1 : y - 1;
-          const bool inside = (xn / g.bx == xc) && (yn / g.by == yc);
+          else if (mu == 1) { if (y + 1 == g.Yf) { yn = 0; hrows = a.Pyp; } else yn = y + 1; }
+          else { if (y == 0) { yn = g.Yf - 1; hrows = a.Pym; } else yn = y - 1; }
+          const bool inside = (hrows == nullptr) && (xn / g.bx == xc) && (yn / g.by == yc);
           if ((tgt == 0) != inside) continue;
-          const int pn = (xn + yn) & 1;
-          const long sn = (long)(yn + pn * g.Yf) * g.xhf + (xn >> 1);
+          const int pn = (xn + yn) & 1;   // Yf is even: row Y has the parity pattern of row 0, row -1 that of row Yf-1
+          const cd* src = (hrows != nullptr) ? hrows + (long)b * a.prow + ((long)pn * g.xhf + (xn >> 1)) * g.ncf
+                                            : Pb + ((long)(yn + pn * g.Yf) * g.xhf + (xn >> 1)) * g.ncf;
           const cd* row = a.hop + (long)mu * a.size_cm_f + s * ncf2 + (long)c1 * g.ncf;
-          for (int c2 = 0; c2 < g.ncf; c2++) cfma(val, row[c2], Pb[sn * g.ncf + c2]);
+          for (int c2 = 0; c2 < g.ncf; c2++) cfma(val, row[c2], src[c2]);
         }
       T[item] = val;
     }
@@ -441,6 +447,20 @@ int qmg_coarse_build(const qmg_transfer_desc* t, const qmg_stencil_desc* fine, c
   a.P = dP; a.R = dR;
   a.clover_c = reinterpret_cast<cd*>(clover_c);
   a.hopping_c = reinterpret_cast<cd*>(hopping_c);
+  a.Pym = nullptr; a.Pyp = nullptr; a.prow = (long)g.Xf * g.ncf;
+  HaloTemp halo;
+  if (comm().nranks > 1 && g.Yc < 2) return fail_msg("qmg_coarse_build: a slab must keep at least two coarse rows");
+  if (comm().active && fine->hopping != nullptr && g.Yc > 1)   // (one coarse row: +-y hops fold into the clover, coarse.h:226-229)
+  {
+    // the coarse +-y links of the aggregates on the slab edges see the neighbouring slab's prolong vectors
+    rc = halo.alloc_rows(g.Xf, g.ncf, g.ncc); if (rc) return rc;
+    for (int b = 0; b < g.ncc; b++)
+    {
+      rc = halo_exchange_sync(reinterpret_cast<const cd*>(prolong_vecs_host[b]), g.Xf, g.Yf, g.ncf, halo.ym + b * a.prow, halo.yp + b * a.prow, 3);
+      if (rc) return rc;
+    }
+    a.Pym = halo.ym; a.Pyp = halo.yp;
+  }
   const int ncc2 = g.ncc * g.ncc;
   int nchunk = 256 / ncc2; if (nchunk < 1) nchunk = 1; if (nchunk > g.fspc) nchunk = g.fspc;
   const size_t smem = sizeof(cd) * ((size_t)g.fspc * g.ncc + (size_t)nchunk * ncc2);

@@ -197,3 +197,37 @@ def norm2sq(x):
 
 def kernel_launches():
     return int(lib().qmg_kernel_launches())
+
+
+# ---- y-slab sharding (include/qmg_b200.h "sharding"): one process per GPU, torch.distributed for the rendezvous ----
+def comm_init(group=None):
+    """Join the ring of slabs: rank 0 creates the NCCL id, torch.distributed (any backend) hands it round, and every
+    rank calls qmg_comm_init.  After this every lattice given to the library is this rank's (X, Y / world_size) slab."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise QmgError("comm_init needs an initialised torch.distributed process group")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        check(lib().qmg_comm_unique_id(buf))
+    ids = [bytes(buf.raw)]
+    dist.broadcast_object_list(ids, src=0, group=group)
+    check(lib().qmg_comm_init(world, rank, C.c_char_p(ids[0])))
+    return world, rank
+
+
+def comm_finalize():
+    check(lib().qmg_comm_finalize())
+
+
+def comm_set_loopback(on):
+    check(lib().qmg_comm_set_loopback(1 if on else 0))
+
+
+def comm_counters():
+    l = lib()
+    l.qmg_comm_halo_exchanges.restype = C.c_long
+    l.qmg_comm_allreduces.restype = C.c_long
+    return dict(halo_exchanges=int(l.qmg_comm_halo_exchanges()), allreduces=int(l.qmg_comm_allreduces()),
+                size=int(l.qmg_comm_size()), rank=int(l.qmg_comm_rank()), active=bool(l.qmg_comm_active()))

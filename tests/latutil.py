@@ -45,12 +45,15 @@ def load_gauge(L, beta=60):
     return phases_to_gauge(ph, L, L)
 
 
-def synthetic_phases(X, Y, beta=6.0, seed=1337):
+def synthetic_phases(X, Y, beta=6.0, seed=1337, slab=False):
     """Link phases with the plaquette statistics of the 2D non-compact U(1) theory at coupling beta -- the large-lattice
     stand-in for the reference's serial heatbath (u1/u1_utils.h:607-667), which needs hours beyond 1024^2.
     In 2D the plaquette angles are independent gaussians of variance 1/beta (up to the torus constraints): draw
     F(x,y) ~ N(0, 1/beta) with zero total flux per column, integrate it into theta_x in the gauge theta_y = 0, then apply a
     random gauge transformation.  <cos plaquette> = exp(-1/(2 beta)) = 0.920 at beta = 6, as in tests/common_cfgs_u1.
+    slab=True: the gauge transformation is trivial on row y = 0.  Such fields can be stacked in y into one valid
+    periodic configuration (theta_x vanishes on row 0 of every slab because the flux per column is zero slab by slab), so N
+    ranks can each draw their own (X, Y) slab of an (X, N Y) lattice without seeing the others.
     Returns phases in the reference's file order (x outer, y, mu inner)."""
     rng = np.random.default_rng(seed)
     F = rng.normal(0.0, 1.0 / np.sqrt(beta), size=(X, Y))
@@ -58,13 +61,15 @@ def synthetic_phases(X, Y, beta=6.0, seed=1337):
     thx = -(np.cumsum(F, axis=1) - F)
     del F
     a = rng.uniform(-np.pi, np.pi, size=(X, Y))
+    if slab:
+        a[:, 0] = 0.0
     thx += np.roll(a, -1, axis=0) - a
     thy = np.roll(a, -1, axis=1) - a
     return np.stack([thx, thy], axis=2).ravel()
 
 
-def synthetic_gauge(X, Y, beta=6.0, seed=1337):
-    return phases_to_gauge(synthetic_phases(X, Y, beta, seed), X, Y)
+def synthetic_gauge(X, Y, beta=6.0, seed=1337, slab=False):
+    return phases_to_gauge(synthetic_phases(X, Y, beta, seed, slab), X, Y)
 
 
 def average_plaquette(gauge, X, Y):
