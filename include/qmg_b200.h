@@ -118,6 +118,15 @@ enum { QMG_APPLY_CLOVER = 1, QMG_APPLY_HOP_TO_EVEN = 2 /* apply_M_eo */, QMG_APP
  * zero_vector + apply of the apply_stencil_2D_* wrappers (:2571-2716). */
 int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs);
 
+/* The same apply for vectors in HOST memory (pinned for full overlap; pageable works, slower): rhs is uploaded in row
+ * chunks on one copy stream, every chunk of output rows is computed once the rows it reads have arrived and is
+ * downloaded on a second copy stream, so both PCIe directions and the SMs are busy together.  Returns when lhs_host is
+ * complete.  dev_lhs / dev_rhs: device staging vectors of size_cv elements, or NULL (taken from the block cache);
+ * rows_per_chunk <= 0 picks ~64 MB chunks.  This is the entry a driver that keeps the reference's host-resident vectors
+ * (tests/n11_wilson_test/wilson_test.cpp:96-104) calls in place of apply_stencil_2D_M. */
+int qmg_stencil_apply_host(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs_host, const qmg_cplx* rhs_host,
+                           qmg_cplx* dev_lhs, qmg_cplx* dev_rhs, int rows_per_chunk);
+
 /* Fused apply + reductions for the Krylov updates: out3 = { <lhs|rhs_dot>, |lhs|^2 } after lhs = A rhs.
  * (MR step: alpha = <Ar|r>/<Ar|Ar>, stateful_multigrid.h:860 via qlinalg minres.)
  * dot_with may be NULL (then only the norm is produced).  result: 3 doubles (re, im, norm2). */

@@ -340,11 +340,133 @@ static int apply_sharded(StencilKArgs& a, int nc, int n_par)
   return dispatch_stencil(a, nc, n_par, false);
 }
 
+// ---- host-vector apply: upload, compute and download pipelined over row chunks -------------------------------------------
+// The reference-facing call for callers whose vectors live in HOST memory (the reference's own drivers): rhs goes up
+// chunk by chunk on one copy stream, each chunk of output rows is computed as soon as the rows it reads have landed, and
+// comes down on a second copy stream, so PCIe carries traffic in both directions while the SMs work.
+struct HostPipe
+{
+  cudaStream_t up = nullptr, down = nullptr;
+  static const int kMaxChunks = 64;
+  cudaEvent_t uploaded[kMaxChunks + 1], computed[kMaxChunks], start = nullptr;
+  bool ready = false;
+};
+static HostPipe& host_pipe() { static HostPipe h; return h; }
+
+static int host_pipe_init()
+{
+  HostPipe& h = host_pipe();
+  if (h.ready) return 0;
+  QMG_CUDA(cudaStreamCreateWithFlags(&h.up, cudaStreamNonBlocking));
+  QMG_CUDA(cudaStreamCreateWithFlags(&h.down, cudaStreamNonBlocking));
+  for (int i = 0; i <= HostPipe::kMaxChunks; i++) QMG_CUDA(cudaEventCreateWithFlags(&h.uploaded[i], cudaEventDisableTiming));
+  for (int i = 0; i < HostPipe::kMaxChunks; i++) QMG_CUDA(cudaEventCreateWithFlags(&h.computed[i], cudaEventDisableTiming));
+  QMG_CUDA(cudaEventCreateWithFlags(&h.start, cudaEventDisableTiming));
+  h.ready = true;
+  return 0;
+}
+
+// rows [y0, y0 + cnt) of both parity halves of an (parity, y, x/2, nc) vector
+static int copy_rows(cd* dst, const cd* src, const Geom& g, int nc, int y0, int cnt, int parity_mask, cudaMemcpyKind kind, cudaStream_t s)
+{
+  const size_t rowlen = (size_t)g.xh * nc;
+  for (int p = 0; p < 2; p++)
+  {
+    if (!((parity_mask >> p) & 1)) continue;
+    const size_t off = ((size_t)p * g.Y + y0) * rowlen;
+    QMG_CUDA(cudaMemcpyAsync(dst + off, src + off, sizeof(cd) * rowlen * cnt, kind, s));
+  }
+  return 0;
+}
+
+static int apply_host_pipelined(StencilKArgs& a, int nc, int n_par, cd* lhs_host, const cd* rhs_host, int rows_per_chunk)
+{
+  int rc = host_pipe_init(); if (rc) return rc;
+  HostPipe& h = host_pipe();
+  Runtime& r = rt();
+  const int Y = a.g.Y;
+  if (rows_per_chunk < 2) rows_per_chunk = 2;
+  int nch = (Y + rows_per_chunk - 1) / rows_per_chunk;
+  if (nch > HostPipe::kMaxChunks) { nch = HostPipe::kMaxChunks; rows_per_chunk = (Y + nch - 1) / nch; nch = (Y + rows_per_chunk - 1) / rows_per_chunk; }
+  const int out_mask = (n_par == 2) ? 3 : (1 << a.p_begin);
+  cd* d_in = const_cast<cd*>(a.in);
+  // both streams start after whatever the caller queued before
+  QMG_CUDA(cudaEventRecord(h.start, r.stream));
+  QMG_CUDA(cudaStreamWaitEvent(h.up, h.start, 0));
+  QMG_CUDA(cudaStreamWaitEvent(h.down, h.start, 0));
+  // the periodic wrap: row Y-1 is read by row 0
+  rc = copy_rows(d_in, rhs_host, a.g, nc, Y - 1, 1, 3, cudaMemcpyHostToDevice, h.up); if (rc) return rc;
+  if (a.accumulate) { rc = copy_rows(a.out, lhs_host, a.g, nc, 0, Y, out_mask, cudaMemcpyHostToDevice, h.up); if (rc) return rc; }
+  for (int c = 0; c < nch; c++)
+  {
+    const int y0 = c * rows_per_chunk, cnt = (y0 + rows_per_chunk <= Y) ? rows_per_chunk : Y - y0;
+    const int up_cnt = (c == nch - 1 && nch > 1) ? cnt - 1 : cnt;     // row Y-1 went first; never rewrite a row a kernel may be reading
+    if (up_cnt > 0) { rc = copy_rows(d_in, rhs_host, a.g, nc, y0, up_cnt, 3, cudaMemcpyHostToDevice, h.up); if (rc) return rc; }
+    QMG_CUDA(cudaEventRecord(h.uploaded[c], h.up));
+  }
+  for (int c = 0; c < nch; c++)
+  {
+    const int y0 = c * rows_per_chunk, cnt = (y0 + rows_per_chunk <= Y) ? rows_per_chunk : Y - y0;
+    // chunk c reads rows y0-1 .. y0+cnt: everything up to chunk c+1 (the last chunk wraps to row 0, long since there)
+    QMG_CUDA(cudaStreamWaitEvent(r.stream, h.uploaded[c + 1 < nch ? c + 1 : c], 0));
+    a.y_off = y0; a.y_stride = 1; a.y_cnt = cnt;
+    rc = dispatch_stencil(a, nc, n_par, false); if (rc) return rc;
+    QMG_CUDA(cudaEventRecord(h.computed[c], r.stream));
+    QMG_CUDA(cudaStreamWaitEvent(h.down, h.computed[c], 0));
+    rc = copy_rows(lhs_host, a.out, a.g, nc, y0, cnt, out_mask, cudaMemcpyDeviceToHost, h.down); if (rc) return rc;
+  }
+  QMG_CUDA(cudaEventRecord(h.uploaded[HostPipe::kMaxChunks], h.down));
+  QMG_CUDA(cudaStreamWaitEvent(r.stream, h.uploaded[HostPipe::kMaxChunks], 0));
+  QMG_CUDA(cudaStreamSynchronize(r.stream));
+  return 0;
+}
+
 } // namespace qmg
 
 using namespace qmg;
 
 extern "C" {
+
+int qmg_stencil_apply_host(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs_host, const qmg_cplx* rhs_host,
+                           qmg_cplx* dev_lhs, qmg_cplx* dev_rhs, int rows_per_chunk)
+{
+  QMG_REQUIRE_INIT();
+  if (st == nullptr) return fail_msg("qmg_stencil_apply_host: null stencil");
+  if (lhs_host == nullptr || rhs_host == nullptr) return fail_msg("qmg_stencil_apply_host: null host vector");
+  const size_t bytes = sizeof(cd) * (size_t)st->X * st->Y * st->nc;
+  void* own_l = nullptr; void* own_r = nullptr;
+  int rc = 0;
+  if (dev_lhs == nullptr) { rc = qmg_malloc(&own_l, bytes); if (rc) return rc; dev_lhs = (qmg_cplx*)own_l; }
+  if (dev_rhs == nullptr) { rc = qmg_malloc(&own_r, bytes); if (rc) { qmg_free(own_l); return rc; } dev_rhs = (qmg_cplx*)own_r; }
+  StencilKArgs a; int n_par;
+  rc = build_args(st, pieces, dir_mask, dev_lhs, dev_rhs, a, n_par);
+  if (!rc)
+  {
+    const bool half_vectors = (pieces & (QMG_APPLY_EVEN_ROWS_ONLY | QMG_APPLY_ODD_ROWS_ONLY)) != 0;
+    if (comm().active || half_vectors || a.g.Y < 4 || st->halo_ym != nullptr || st->halo_yp != nullptr)
+    {
+      // sharded slabs and partial applies take the plain route: whole vector up, apply, whole vector down
+      rc = qmg_memcpy_h2d(dev_rhs, rhs_host, bytes);
+      if (!rc && (pieces & QMG_APPLY_ACCUMULATE)) rc = qmg_memcpy_h2d(dev_lhs, lhs_host, bytes);
+      if (!rc) rc = qmg_stencil_apply(st, pieces, dir_mask, dev_lhs, dev_rhs);
+      if (!rc) rc = qmg_memcpy_d2h(lhs_host, dev_lhs, bytes);
+    }
+    else
+    {
+      if (rows_per_chunk <= 0)
+      {
+        // ~64 MB of rhs per chunk: long enough for PCIe to run at full rate, short enough that the exposed head and tail
+        // (first upload, last download) stay a few per cent of the transfer
+        const size_t row_bytes = sizeof(cd) * (size_t)st->X * st->nc;
+        rows_per_chunk = (int)((64u << 20) / row_bytes);
+        if (rows_per_chunk < 2) rows_per_chunk = 2;
+      }
+      rc = apply_host_pipelined(a, st->nc, n_par, reinterpret_cast<cd*>(lhs_host), reinterpret_cast<const cd*>(rhs_host), rows_per_chunk);
+    }
+  }
+  qmg_free(own_l); qmg_free(own_r);
+  return rc;
+}
 
 int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs)
 {

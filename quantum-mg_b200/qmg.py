@@ -116,6 +116,14 @@ def stencil_apply(desc, lhs, rhs, pieces=APPLY_ALL, dir_mask=15):
     check(lib().qmg_stencil_apply(C.byref(desc), C.c_int(pieces), C.c_int(dir_mask), ptr(lhs), ptr(rhs)))
 
 
+def stencil_apply_host(desc, lhs_host, rhs_host, pieces=APPLY_ALL, dir_mask=15, dev_lhs=None, dev_rhs=None, rows_per_chunk=0):
+    """lhs_host = M rhs_host for HOST vectors (numpy complex128 arrays or raw pointers), pipelined over row chunks."""
+    def hp(a):
+        return a if isinstance(a, C.c_void_p) else C.c_void_p(a.ctypes.data)
+    check(lib().qmg_stencil_apply_host(C.byref(desc), C.c_int(pieces), C.c_int(dir_mask), hp(lhs_host), hp(rhs_host),
+                                       ptr(dev_lhs), ptr(dev_rhs), C.c_int(rows_per_chunk)))
+
+
 def stencil_apply_dot(desc, lhs, rhs, dot_with=None, pieces=APPLY_ALL):
     out = (C.c_double * 3)()
     check(lib().qmg_stencil_apply_dot(C.byref(desc), C.c_int(pieces), ptr(lhs), ptr(rhs), ptr(dot_with), out))

@@ -221,6 +221,26 @@ def test_halo_slabs_equal_periodic(qmg_gpu):
     assert np.array_equal(got, full)
 
 
+@pytest.mark.parametrize("nc,chunk", [(2, 0), (2, 2), (2, 6), (2, 5), (8, 4), (1, 64)])
+def test_host_vector_apply_pipelined(qmg_gpu, nc, chunk):
+    """qmg_stencil_apply_host (upload / compute / download pipelined over row chunks) == the device-resident apply, bit for
+    bit, for chunk sizes that do and do not divide Y, with and without accumulation."""
+    qmg = qmg_gpu
+    X, Y = 16, 24
+    V = X * Y
+    cl = latutil.gaussian_cv(V * nc * nc, 1)
+    hp = latutil.gaussian_cv(4 * V * nc * nc, 2)
+    d = qmg.stencil_desc(X, Y, nc, dev(qmg, cl), dev(qmg, hp), shift=0.2)
+    rhs = latutil.gaussian_cv(V * nc, 3)
+    old = latutil.gaussian_cv(V * nc, 4)
+    for pieces in (qmg.APPLY_ALL, qmg.APPLY_ALL | qmg.APPLY_ACCUMULATE):
+        want = dev(qmg, old)
+        qmg.stencil_apply(d, want, dev(qmg, rhs), pieces)
+        got = old.copy()
+        qmg.stencil_apply_host(d, got, rhs, pieces, rows_per_chunk=chunk)
+        assert np.array_equal(got, host(want)), (nc, chunk, pieces)
+
+
 def test_blas(qmg_gpu):
     import ctypes as C
     qmg = qmg_gpu

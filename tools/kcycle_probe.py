@@ -23,6 +23,8 @@ ap.add_argument("--coarsest-iters", type=int, default=200)
 ap.add_argument("--max-iter", type=int, default=60)
 ap.add_argument("--null-iters", type=int, default=500)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--restart", type=int, default=32)
+ap.add_argument("--seed", type=int, default=1337)
 args = ap.parse_args()
 if args.backend == "gpu":
     import qmg
@@ -30,17 +32,17 @@ if args.backend == "gpu":
 be = capi.Backend(args.backend)
 for L in args.sizes:
     t0 = time.perf_counter()
-    g = latutil.synthetic_gauge(L, L, 6.0, 1337)
+    g = latutil.synthetic_gauge(L, L, 6.0, args.seed, slab=True)
     t1 = time.perf_counter()
     kc = capi.KCycle(be, L, args.mass, g, n_refine=args.n_refine, inner_iters=args.inner_iters, coarsest_iters=args.coarsest_iters,
                      null_max_iter=args.null_iters, verbosity=args.verbosity)
     t2 = time.perf_counter()
-    out = kc.solve(max_iter=args.max_iter, verbosity=args.verbosity)
+    out = kc.solve(max_iter=args.max_iter, verbosity=args.verbosity, restart=args.restart)
     t3 = time.perf_counter()
     if args.profile and args.backend == "gpu":
         qmg.lib().qmg_profile_reset(); qmg.lib().qmg_profile_enable(1)
     t4 = time.perf_counter()
-    out2 = kc.solve(max_iter=args.max_iter, verbosity=0)
+    out2 = kc.solve(max_iter=args.max_iter, verbosity=0, restart=args.restart)
     if args.profile and args.backend == "gpu":
         qmg.lib().qmg_profile_enable(0)
         qmg.lib().qmg_profile_report.restype = __import__("ctypes").c_double
