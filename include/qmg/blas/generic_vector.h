@@ -117,6 +117,13 @@ template <typename U, typename W> inline void caxpbypz(U a_, const qmg_cd* x, W 
 // stencil/stencil_2d.h:1526 (pattern lives on the host)
 inline void capx_pattern(const qmg_cd* pattern, int len, qmg_cd* v, long nrepeat)
 { QMG_CHK(qmg_cmat_add_pattern(reinterpret_cast<const double*>(pattern), len, qmg_host::P(v), nrepeat)); }
+// real pattern (operators/coarse.h:702-721 passes a double array)
+inline void capx_pattern(const double* pattern, int len, qmg_cd* v, long nrepeat)
+{
+  std::vector<qmg_cd> c((size_t)len);
+  for (int i = 0; i < len; i++) c[i] = qmg_cd(pattern[i], 0.0);
+  capx_pattern(c.data(), len, v, nrepeat);
+}
 // operators/wilson.h:132 (scale / shuffle live on the host); in == out is allowed for the identity shuffle
 inline void caxy_shuffle_pattern(const double* scale, const int* shuffle, int n, const qmg_cd* in, qmg_cd* out, long nsites)
 { QMG_CHK(qmg_shuffle_pattern(scale, shuffle, n, qmg_host::P(in), qmg_host::P(out), nsites)); }

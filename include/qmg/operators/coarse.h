@@ -10,6 +10,16 @@
 #include "../stencil/stencil_2d.h"
 #include "../transfer/transfer.h"
 
+// apply_sigma flavours that only exist on a coarse operator whose transfer kept its block factorisations
+// (/root/reference/operators/coarse.h:19-25); numbering continues QMGSigmaType
+enum QMGSigmaTypeCoarse
+{
+  QMG_SIGMA_1_L = 6,      // left-apply  L^dag sigma_1 U^-1
+  QMG_SIGMA_1_R = 7,      // right-apply U sigma_1 L^-dag
+  QMG_SIGMA_1_L_RBJ = 8,  // B^-dag sigma_1^L   (coarsened rbjacobi system)
+  QMG_SIGMA_1_R_RBJ = 9,  // B sigma_1^R
+};
+
 struct CoarseOperator2D : public Stencil2D
 {
 protected:
@@ -21,6 +31,37 @@ protected:
   bool use_rbjacobi;
   TransferMG* in_transfer;
   QMGDefaultChirality default_chirality;
+  complex<double>* sigma_1_L;   // V nc nc, built on first use by apply_sigma
+  complex<double>* sigma_1_R;
+
+  // sigma_1^L = L^dag sigma_1 U^-1 and sigma_1^R = U sigma_1 L^-dag per coarse site, from the factors the transfer saved
+  // while (bi-)orthonormalising its blocks: P_raw = P_ortho U, R_raw = R_ortho L^dag (coarse.h:673-731, 771-846).
+  // With R = P^dag both factors are the Cholesky factor Sigma and the two matrices coincide.
+  void build_sigma_matrices()
+  {
+    const long cm = lat->get_size_cm(); const long V = lat->get_volume(); const int nc = lat->get_nc();
+    complex<double>* U = allocate_vector<complex<double> >(cm);
+    complex<double>* Ldag = allocate_vector<complex<double> >(cm);
+    if (in_transfer->is_symmetric()) { in_transfer->copy_cholesky(U); copy_vector(Ldag, U, cm); }
+    else { in_transfer->copy_LU(Ldag, U); cMATconjtrans_square(Ldag, V, nc); }
+    // the sigma_1 block (swap of the two dof halves), repeated over the sites
+    std::vector<complex<double> > one_site(nc * nc, 0.0);
+    for (int i = 0; i < nc; i++) one_site[i * nc + (i < nc / 2 ? i + nc / 2 : i - nc / 2)] = 1.0;
+    complex<double>* s1 = allocate_vector<complex<double> >(cm);
+    zero_vector(s1, cm);
+    capx_pattern(one_site.data(), nc * nc, s1, V);
+    complex<double>* inv = allocate_vector<complex<double> >(cm);
+    complex<double>* tmp = allocate_vector<complex<double> >(cm);
+    sigma_1_L = allocate_vector<complex<double> >(cm);
+    sigma_1_R = allocate_vector<complex<double> >(cm);
+    cMATinverse_square(U, inv, V, nc);
+    cMATxtMATyMATz_square(Ldag, s1, tmp, V, nc);
+    cMATxtMATyMATz_square(tmp, inv, sigma_1_L, V, nc);
+    cMATinverse_square(Ldag, inv, V, nc);
+    cMATxtMATyMATz_square(U, s1, tmp, V, nc);
+    cMATxtMATyMATz_square(tmp, inv, sigma_1_R, V, nc);
+    deallocate_vector(&tmp); deallocate_vector(&inv); deallocate_vector(&s1); deallocate_vector(&Ldag); deallocate_vector(&U);
+  }
 
   // per-site dof map out[s][i] = scale[i] in[s][pick[i]]; top half of the dof is "up", bottom half "down"
   void half_map(double s_top, double s_bot, bool swap_halves, complex<double>* in, complex<double>* out)
@@ -51,14 +92,14 @@ public:
   CoarseOperator2D(Lattice2D* in_lat, int pieces, bool is_chiral, QMGDefaultChirality def_chiral = QMG_CHIRALITY_NONE,
                    complex<double> in_shift = 0.0, complex<double> in_eo_shift = 0.0, complex<double> in_dof_shift = 0.0)
     : Stencil2D(in_lat, pieces, in_shift, in_eo_shift, in_dof_shift), fine_lat(0), is_chiral(is_chiral), use_rbjacobi(false),
-      in_transfer(0), default_chirality(def_chiral)
+      in_transfer(0), default_chirality(def_chiral), sigma_1_L(0), sigma_1_R(0)
   { }
 
   // Galerkin build (coarse.h:90-471)
   CoarseOperator2D(Lattice2D* in_lat, Stencil2D* fine_stencil, Lattice2D* fine_lattice, TransferMG* transfer, bool is_chiral = false,
                    bool use_rbjacobi = false, QMGCoarseBuildStencil build_extra = QMG_COARSE_BUILD_ORIGINAL)
     : Stencil2D(in_lat, QMG_PIECE_CLOVER_HOPPING, 0.0, 0.0, 0.0), fine_lat(fine_lattice), is_chiral(is_chiral), use_rbjacobi(use_rbjacobi),
-      in_transfer(transfer)
+      in_transfer(transfer), sigma_1_L(0), sigma_1_R(0)
   {
     switch (transfer->get_doubling())
     {
@@ -86,7 +127,11 @@ public:
     if (build_extra == QMG_COARSE_BUILD_RBJDAGGER || build_extra == QMG_COARSE_BUILD_ALL)
       build_rbj_dagger_stencil();
   }
-  ~CoarseOperator2D() { }
+  ~CoarseOperator2D()
+  {
+    if (sigma_1_L != 0) deallocate_vector(&sigma_1_L);
+    if (sigma_1_R != 0) deallocate_vector(&sigma_1_R);
+  }
 
   static int get_dof(int i = 0) { (void)i; return -1; }
   static chirality_state has_chirality() { return QMG_CHIRAL_UNKNOWN; }
@@ -144,6 +189,50 @@ public:
   }
   virtual QMGDefaultChirality get_default_chirality() { return default_chirality; }
   using Stencil2D::apply_sigma;
+
+  // sigma_1 as seen through the block factorisations of the transfer (coarse.h:661-894)
+  void apply_sigma(complex<double>* output, complex<double>* input, QMGSigmaTypeCoarse type)
+  {
+    if (in_transfer == 0 || !in_transfer->has_decompositions())
+    {
+      std::cout << "[QMG-ERROR]: In CoarseOperator2D, cannot apply apply_sigma() if the transfer op does not have factorizations.\n";
+      return;
+    }
+    if (sigma_1_L == 0 || sigma_1_R == 0) build_sigma_matrices();
+    const long V = lat->get_volume(); const int nc = lat->get_nc();
+    switch (type)
+    {
+      case QMG_SIGMA_1_L: cMATxy(sigma_1_L, input, output, V, nc, nc); break;
+      case QMG_SIGMA_1_R: cMATxy(sigma_1_R, input, output, V, nc, nc); break;
+      case QMG_SIGMA_1_L_RBJ:
+        if (!built_rbj_dagger)
+        {
+          std::cout << "[QMG-ERROR]: In apply_sigma, cannot apply QMG_SIGMA_1_L_RBJ without rbjacobi dagger stencil.\n";
+          copy_vector(output, input, lat->get_size_cv());
+        }
+        else
+        {
+          complex<double>* tmp = scratch_extra();
+          cMATxy(sigma_1_L, input, tmp, V, nc, nc);
+          cMATxy(rbj_dagger_cinv, tmp, output, V, nc, nc);
+        }
+        break;
+      case QMG_SIGMA_1_R_RBJ:
+        if (!built_rbjacobi)
+        {
+          std::cout << "[QMG-ERROR]: In apply_sigma, cannot apply QMG_SIGMA_1_R_RBJ without rbjacobi stencil.\n";
+          copy_vector(output, input, lat->get_size_cv());
+        }
+        else
+        {
+          complex<double>* tmp = scratch_extra();
+          cMATxy(sigma_1_R, input, tmp, V, nc, nc);
+          cMATxy(clover, tmp, output, V, nc, nc);
+          caxpy(shift, tmp, output, lat->get_size_cv());
+        }
+        break;
+    }
+  }
 };
 
 #endif

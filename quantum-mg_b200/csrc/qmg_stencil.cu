@@ -390,19 +390,33 @@ static int apply_host_pipelined(StencilKArgs& a, int nc, int n_par, cd* lhs_host
   if (nch > HostPipe::kMaxChunks) { nch = HostPipe::kMaxChunks; rows_per_chunk = (Y + nch - 1) / nch; nch = (Y + rows_per_chunk - 1) / rows_per_chunk; }
   const int out_mask = (n_par == 2) ? 3 : (1 << a.p_begin);
   cd* d_in = const_cast<cd*>(a.in);
-  // both streams start after whatever the caller queued before
+  const bool sharded = needs_exchange(a);
+  // both copy streams start after whatever the caller queued before
   QMG_CUDA(cudaEventRecord(h.start, r.stream));
   QMG_CUDA(cudaStreamWaitEvent(h.up, h.start, 0));
   QMG_CUDA(cudaStreamWaitEvent(h.down, h.start, 0));
-  // the periodic wrap: row Y-1 is read by row 0
+  // the two edge rows go first: row Y-1 is what row 0 reads across the periodic wrap, and on a y-slab both are what the
+  // ring neighbours need, so the halo exchange runs while the bulk of rhs is still uploading
+  rc = copy_rows(d_in, rhs_host, a.g, nc, 0, 1, 3, cudaMemcpyHostToDevice, h.up); if (rc) return rc;
   rc = copy_rows(d_in, rhs_host, a.g, nc, Y - 1, 1, 3, cudaMemcpyHostToDevice, h.up); if (rc) return rc;
+  QMG_CUDA(cudaEventRecord(h.uploaded[HostPipe::kMaxChunks], h.up));
   if (a.accumulate) { rc = copy_rows(a.out, lhs_host, a.g, nc, 0, Y, out_mask, cudaMemcpyHostToDevice, h.up); if (rc) return rc; }
   for (int c = 0; c < nch; c++)
   {
-    const int y0 = c * rows_per_chunk, cnt = (y0 + rows_per_chunk <= Y) ? rows_per_chunk : Y - y0;
-    const int up_cnt = (c == nch - 1 && nch > 1) ? cnt - 1 : cnt;     // row Y-1 went first; never rewrite a row a kernel may be reading
-    if (up_cnt > 0) { rc = copy_rows(d_in, rhs_host, a.g, nc, y0, up_cnt, 3, cudaMemcpyHostToDevice, h.up); if (rc) return rc; }
+    // rows 0 and Y-1 are already there; never rewrite a row a kernel may be reading
+    int y0 = c * rows_per_chunk, y1 = (y0 + rows_per_chunk <= Y) ? y0 + rows_per_chunk : Y;
+    if (c == 0) y0 = 1;
+    if (y1 == Y) y1 = Y - 1;
+    if (y1 > y0) { rc = copy_rows(d_in, rhs_host, a.g, nc, y0, y1 - y0, 3, cudaMemcpyHostToDevice, h.up); if (rc) return rc; }
     QMG_CUDA(cudaEventRecord(h.uploaded[c], h.up));
+  }
+  if (sharded)
+  {
+    HaloRows rows;
+    QMG_CUDA(cudaStreamWaitEvent(r.stream, h.uploaded[HostPipe::kMaxChunks], 0));
+    rc = halo_exchange_begin(a.in, 2 * a.g.xh, Y, nc, exchange_parities(a, n_par), &rows); if (rc) return rc;
+    rc = halo_exchange_end(); if (rc) return rc;
+    a.halo_ym = rows.ym; a.halo_yp = rows.yp;
   }
   for (int c = 0; c < nch; c++)
   {
@@ -415,8 +429,8 @@ static int apply_host_pipelined(StencilKArgs& a, int nc, int n_par, cd* lhs_host
     QMG_CUDA(cudaStreamWaitEvent(h.down, h.computed[c], 0));
     rc = copy_rows(lhs_host, a.out, a.g, nc, y0, cnt, out_mask, cudaMemcpyDeviceToHost, h.down); if (rc) return rc;
   }
-  QMG_CUDA(cudaEventRecord(h.uploaded[HostPipe::kMaxChunks], h.down));
-  QMG_CUDA(cudaStreamWaitEvent(r.stream, h.uploaded[HostPipe::kMaxChunks], 0));
+  QMG_CUDA(cudaEventRecord(h.start, h.down));
+  QMG_CUDA(cudaStreamWaitEvent(r.stream, h.start, 0));
   QMG_CUDA(cudaStreamSynchronize(r.stream));
   return 0;
 }
@@ -443,9 +457,9 @@ int qmg_stencil_apply_host(const qmg_stencil_desc* st, int pieces, int dir_mask,
   if (!rc)
   {
     const bool half_vectors = (pieces & (QMG_APPLY_EVEN_ROWS_ONLY | QMG_APPLY_ODD_ROWS_ONLY)) != 0;
-    if (comm().active || half_vectors || a.g.Y < 4 || st->halo_ym != nullptr || st->halo_yp != nullptr)
+    if (half_vectors || a.g.Y < 4 || st->halo_ym != nullptr || st->halo_yp != nullptr)
     {
-      // sharded slabs and partial applies take the plain route: whole vector up, apply, whole vector down
+      // partial applies take the plain route: whole vector up, apply, whole vector down
       rc = qmg_memcpy_h2d(dev_rhs, rhs_host, bytes);
       if (!rc && (pieces & QMG_APPLY_ACCUMULATE)) rc = qmg_memcpy_h2d(dev_lhs, lhs_host, bytes);
       if (!rc) rc = qmg_stencil_apply(st, pieces, dir_mask, dev_lhs, dev_rhs);

@@ -394,6 +394,18 @@ void* CAPI(coarse_new)(void* coarse_lat_, void* fine_stencil_, void* fine_lat_, 
   return h;
 }
 
+// CoarseOperator2D::apply_sigma(out, in, QMGSigmaTypeCoarse) (operators/coarse.h:661); type 6..9.  Returns 0 when the handle
+// is not a coarse operator.
+int CAPI(coarse_apply_sigma)(void* h_, int type, capi_cd* out, const capi_cd* in)
+{
+  CoarseOperator2D* op = dynamic_cast<CoarseOperator2D*>(((capi::StencilH*)h_)->op);
+  if (op == 0) return 0;
+  const long n = op->lat->get_size_cv();
+  capi::Stage dout(out, n, true, true), din(in, n, true, false);
+  op->apply_sigma((capi_cd*)dout, (capi_cd*)din, (QMGSigmaTypeCoarse)type);
+  return 1;
+}
+
 // ----------------------------------------------------------------- multigrid --
 void* CAPI(mg_new)(void* lat0_, void* stencil0_, int coarsest_type, double coarsest_tol, int coarsest_iters, int coarsest_restart)
 {

@@ -168,6 +168,13 @@ class Stencil:
         self.be.fn("stencil_chiral")(self.h, op, _c(a), _c(bb))
         return a, bb
 
+    def coarse_sigma(self, type, v):
+        """CoarseOperator2D::apply_sigma(out, v, QMGSigmaTypeCoarse type in 6..9); out starts as zeros."""
+        out = np.zeros(self.lat.size_cv, CD)
+        vv = carr(v)
+        assert self.lat.be.fn("coarse_apply_sigma")(self.h, type, _c(out), _c(vv)) == 1
+        return out
+
     def time_apply(self, rhs, type=0, warm=1, reps=5):
         rhs = carr(rhs)
         return self.be.fn("stencil_time_apply")(self.h, type, warm, reps, _c(rhs))

@@ -246,6 +246,35 @@ def test_coarse_operator_class(ref, gpu, use_rbj, extra):
         assert np.allclose(a_, b_, atol=1e-14)
 
 
+@pytest.mark.parametrize("asym", [False, True])
+def test_coarse_apply_sigma(ref, gpu, asym):
+    """CoarseOperator2D::apply_sigma with the four QMGSigmaTypeCoarse flavours (coarse.h:19-25, 661-894): sigma_1 seen
+    through the Cholesky factor (R = P^dag) or the L, U factors (R != P^dag) the transfer saved; the RBJ flavours also use
+    B and B^-dag of the coarse operator.  Without saved factors the call is an error that leaves the output alone."""
+    L, Lc, ncc = 16, 4, 8
+    g = latutil.phases_to_gauge(np.random.default_rng(8).normal(0, 0.4, size=L * L * 2), L, L)
+    pv = np.stack([latutil.gaussian_cv(L * L * 2, 30 + v) for v in range(ncc)])
+    rv = pv + 0.3 * np.stack([latutil.gaussian_cv(L * L * 2, 60 + v) for v in range(ncc)]) if asym else None
+    x = latutil.gaussian_cv(Lc * Lc * ncc, 3)
+    out = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        fl, cl = be.lattice(L, L, 2), be.lattice(Lc, Lc, ncc)
+        op = fl.wilson(0.02, g)
+        tr = capi.Transfer(fl, cl, pv, block_ortho=True, save_decomp=True, doubling=2, restrict_vecs=rv)
+        co = tr.coarse_operator(op, is_chiral=True, use_rbjacobi=False, build_extra=5)
+        res = [co.coarse_sigma(t, x) for t in (6, 7, 8, 9)]
+        tr0 = capi.Transfer(fl, cl, pv, block_ortho=True, save_decomp=False, doubling=2)
+        co0 = tr0.coarse_operator(op, is_chiral=True)
+        res.append(co0.coarse_sigma(6, x))
+        out[name] = res
+        co.free(); co0.free(); tr.free(); tr0.free(); op.free()
+    for i, (a_, b_) in enumerate(zip(out["ref"], out["gpu"])):
+        assert latutil.rel_l2(b_, a_) < 1e-10, i
+    assert not np.any(out["gpu"][4])
+    if not asym:
+        assert np.array_equal(out["gpu"][0], out["gpu"][1])      # sigma_1^L == sigma_1^R when R = P^dag
+
+
 def _n13_nullvecs(be, lat, op, coarse_dof, seed):
     """Null vectors as tests/n13_wilson_kcycle/wilson_kcycle.cpp:338-385 generates them (through backend `be`)."""
     rng = np.random.default_rng(seed)

@@ -119,3 +119,20 @@ def test_two_rank_gloo_halo_exchange():
     for rank, err, nrm, want in res:
         assert err < 1e-14
         assert abs(nrm - want) < 1e-10 * want
+
+
+def test_stackable_synthetic_slabs_form_one_configuration():
+    """bench.py's sharded runs let every rank draw its own slab (latutil.synthetic_phases(slab=True)); stacked in y the slabs
+    must be ONE smooth periodic configuration: the plaquette across the seams is as gaussian as inside a slab."""
+    import latutil
+    X, Yl, N, beta = 32, 16, 4, 6.0
+    parts = [latutil.synthetic_phases(X, Yl, beta, 100 + r, slab=True).reshape(X, Yl, 2) for r in range(N)]
+    ph = np.concatenate(parts, axis=1)
+    thx, thy = ph[:, :, 0], ph[:, :, 1]
+    plaq = thx + np.roll(thy, -1, axis=0) - np.roll(thx, -1, axis=1) - thy
+    plaq = (plaq + np.pi) % (2 * np.pi) - np.pi
+    seams = plaq[:, Yl - 1::Yl]
+    assert abs(plaq.std() - 1 / np.sqrt(beta)) < 0.03
+    assert abs(seams.std() - 1 / np.sqrt(beta)) < 0.08
+    g = latutil.phases_to_gauge(ph.ravel(), X, Yl * N)
+    assert abs(latutil.average_plaquette(g, X, Yl * N) - np.exp(-0.5 / beta)) < 0.01

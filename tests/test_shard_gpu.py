@@ -70,6 +70,9 @@ def test_loopback_fill_apply(qmg_gpu, loop, kind):
             lhs += 1.0
             qmg.stencil_apply(d, lhs, rhs, pieces, dm)
             out.append(host(lhs))
+        hout = np.zeros(X * Y * nc, np.complex128)
+        qmg.stencil_apply_host(d, hout, host(rhs), rows_per_chunk=5)      # pipelined host-vector entry, halo exchanged mid-upload
+        out.append(hout)
         dot, nrm = qmg.stencil_apply_dot(d, qmg.cvec(X * Y * nc), rhs, rhs)
         out.append(np.array([dot.real, dot.imag, nrm]))
         return out
