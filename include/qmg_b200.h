@@ -205,6 +205,21 @@ int qmg_multi_axpyz(const double* a_host, const qmg_cplx* const* xs_host, int k,
  * GLOBAL element index of an even-odd field (the ranks together draw what one GPU draws for the whole lattice) */
 int qmg_gaussian(qmg_cplx* x, long n, uint64_t seed, uint64_t stream_id, double dev);
 
+/* ------------------------------------------------------- U(1) gauge fields -- */
+/* u1/u1_utils.h on the nc = 1 lattice: gauge = 2 V complex links, phases = 2 V real angles, both [mu * V + site]. */
+int qmg_zero_bytes(void* dptr, size_t bytes);                                               /* zero_vector on a double field (tests/n13_wilson_kcycle/wilson_kcycle.cpp:203) */
+int qmg_polar_vector(const double* phases, qmg_cplx* gauge, long n);                       /* qlinalg polar_vector (n13 :212) */
+/* result4 = { Re <plaq>, Im <plaq>, topological charge, 0 } in one pass (get_plaquette_u1 / get_topo_u1, u1_utils.h:424-508) */
+int qmg_u1_plaquette(const qmg_cplx* gauge, int X, int Y, double* result4);
+int qmg_u1_noncompact_action(const double* phases, int X, int Y, double beta, double* result);    /* u1_utils.h:386-421 */
+int qmg_u1_gauge_transform(qmg_cplx* gauge, const qmg_cplx* trans, int X, int Y);          /* apply_gauge_trans_u1, u1_utils.h:241-272 */
+/* apply_ape_smear_u1, u1_utils.h:276-383.  textbook = 0: bit-for-bit what the reference computes (its y staples land on the
+ * x links, :352,:372); textbook = 1: each link smeared with its own two staples */
+int qmg_u1_ape_smear(qmg_cplx* smeared, const qmg_cplx* gauge, int X, int Y, double alpha, int n_iter, int textbook);
+/* heatbath_noncompact_update (u1_utils.h:607-667) as four independent subsets per update (the reference sweeps serially
+ * and notes "We would need subsets"); counter-based RNG keyed by (seed, global link, update0 + update) */
+int qmg_u1_heatbath(double* phases, int X, int Y, double beta, int n_update, uint64_t seed, uint64_t update0);
+
 /* ------------------------------------------------------------ transfer ---- */
 /* Regular non-overlapping blocking of a fine (Xf,Yf,ncf) lattice onto a coarse
  * (Xc,Yc) lattice with ncc dof per coarse site (transfer/transfer.h:118-140).

@@ -32,12 +32,15 @@
 #include "operators/coarse.h"
 #include "transfer/transfer.h"
 #include "multigrid/stateful_multigrid.h"
+#include "u1/u1_utils.h"
 
 #define CAPI(name) ref_##name
 static inline std::complex<double>* capi_alloc(long n) { return allocate_vector<std::complex<double> >((int)n); }
 static inline void capi_free(std::complex<double>* p) { deallocate_vector(&p); }
 static inline void capi_put(std::complex<double>* dst, const std::complex<double>* src, long n) { std::memcpy(dst, src, sizeof(std::complex<double>) * n); }
 static inline void capi_get(std::complex<double>* dst, const std::complex<double>* src, long n) { std::memcpy(dst, src, sizeof(std::complex<double>) * n); }
+static inline void capi_put_real(double* dst, const double* src, long n) { std::memcpy(dst, src, sizeof(double) * n); }
+static inline void capi_get_real(double* dst, const double* src, long n) { std::memcpy(dst, src, sizeof(double) * n); }
 static inline void capi_barrier() { }
 
 #include "../quantum-mg_b200/host/qmg_capi_body.h"

@@ -3,58 +3,7 @@
 // Krylov updates.  All kernels are HBM-bound streaming kernels: 16-byte
 // (double2) coalesced accesses, grid-stride loops sized to fill every SM,
 // warp-shuffle tree reductions finished deterministically by the last block.
-#include "qmg_common.cuh"
-
-namespace qmg {
-
-constexpr int kEwBlock = 256;
-
-template <class F>
-__global__ void __launch_bounds__(kEwBlock) ew_kernel(long n, F f)
-{
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
-}
-
-template <int W, class F>
-__global__ void __launch_bounds__(kEwBlock) reduce_kernel(long n, F f, double* partials, unsigned int* counter, double* result)
-{
-  __shared__ double smem[(kEwBlock / 32) * W];
-  double acc[W];
-#pragma unroll
-  for (int w = 0; w < W; w++) acc[w] = 0.0;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, acc);
-  grid_reduce_finish<W>(acc, smem, partials, counter, result);
-}
-
-static inline int ew_grid(long n)
-{
-  long want = (n + kEwBlock - 1) / kEwBlock;
-  long cap = (long)rt().sm_count * 8;
-  if (want < 1) want = 1;
-  return (int)(want < cap ? want : cap);
-}
-
-template <class F> static int launch_ew(long n, F f)
-{
-  if (n <= 0) return 0;
-  ew_kernel<<<ew_grid(n), kEwBlock, 0, rt().stream>>>(n, f);
-  QMG_LAUNCH_CHECK();
-  return 0;
-}
-
-template <int W, class F> static int launch_reduce(long n, F f, double* host_out)
-{
-  Runtime& r = rt();
-  int grid = ew_grid(n > 0 ? n : 1);
-  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
-  reduce_kernel<W><<<grid, kEwBlock, 0, r.stream>>>(n, f, r.d_partials, r.d_counter, r.d_result);
-  QMG_LAUNCH_CHECK();
-  return host_out ? fetch_result(host_out, W) : 0;
-}
-
-} // namespace qmg
+#include "qmg_launch.cuh"
 
 using namespace qmg;
 
@@ -436,23 +385,6 @@ int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p_, const qmg_cplx*
 } // extern "C"
 
 // ------------------------------------------------------------------ gaussian --
-namespace qmg {
-
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
-{
-#pragma unroll
-  for (int round = 0; round < 10; round++)
-  {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-}
-
-} // namespace qmg
-
 extern "C" int qmg_gaussian(qmg_cplx* x_, long n, uint64_t seed, uint64_t stream_id, double dev)
 {
   QMG_REQUIRE_INIT();
@@ -465,14 +397,8 @@ extern "C" int qmg_gaussian(qmg_cplx* x_, long n, uint64_t seed, uint64_t stream
   return launch_ew(n, [=] __device__(long i) {
     long gi = i;
     if (split) { const long p = i >= half ? 1 : 0; gi = p * nranks * half + rank * half + (i - p * half); }
-    uint32_t c[4] = { (uint32_t)gi, (uint32_t)((uint64_t)gi >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32) };
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    // two 53-bit-ish uniforms in (0,1): 32 random bits each, centred
-    const double u1 = ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
-    const double u2 = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
-    const double rad = dev * sqrt(-2.0 * log(u1));
-    double s, co;
-    sincospi(2.0 * u2, &s, &co);
-    x[i] = cmake(rad * co, rad * s);
+    double n0, n1;
+    philox_normal2(seed, (uint64_t)gi, stream_id, n0, n1);
+    x[i] = cmake(dev * n0, dev * n1);
   });
 }

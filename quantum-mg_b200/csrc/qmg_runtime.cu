@@ -234,6 +234,13 @@ int qmg_memcpy_d2d(void* dst, const void* src, size_t bytes)
   QMG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, rt().stream));
   return 0;
 }
+int qmg_zero_bytes(void* dptr, size_t bytes)
+{
+  QMG_REQUIRE_INIT();
+  if (bytes == 0) return 0;
+  QMG_CUDA(cudaMemsetAsync(dptr, 0, bytes, rt().stream));
+  return 0;
+}
 int qmg_profile_enable(int on) { rt().profile = on ? 1 : 0; return 0; }
 int qmg_profile_reset(void) { prof_table().clear(); return 0; }
 // prints "name calls seconds" rows sorted by time to stdout and returns the total seconds

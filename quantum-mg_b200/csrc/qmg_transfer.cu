@@ -172,8 +172,14 @@ static int launch_restrict(const TGeom& g, const qmg_cplx* const* vecs, int coun
 {
   VecPack<NV> pk;
   for (int v = 0; v < NV; v++) pk.p[v] = reinterpret_cast<const cd*>(vecs[v < count ? v : 0]);
+  // Lanes per aggregate.  With an even block width the aggregate's elements of one (row, parity) are `seg` contiguous
+  // complex numbers and neighbouring aggregates continue the same memory row, so G = seg makes every warp-level load one
+  // contiguous 512-byte span (32 / G aggregates side by side) and each lane walks down the 2 by (row, parity) segments of
+  // its aggregate.  (G = 32 lanes on ONE aggregate reads eight 64-byte pieces of eight different DRAM pages per load:
+  // 3.3 TB/s at 4096^2 -> 1024^2.)  Other shapes keep the element-strided assignment.
   int G = 1, logG = 0;
-  while (G < 32 && G < g.fspc) { G <<= 1; logG++; }
+  if (g.even_bx && g.seg <= 32 && (g.seg & (g.seg - 1)) == 0) { while (G < g.seg) { G <<= 1; logG++; } }
+  else { while (G < 32 && G < g.fspc) { G <<= 1; logG++; } }
   const long threads = g.Vc * G;
   const long blocks = (threads + 255) / 256;
   if (blocks > 0x7fffffffL) return fail_msg("restrict: lattice too large for the launch grid");

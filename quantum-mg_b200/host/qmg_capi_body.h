@@ -406,6 +406,97 @@ int CAPI(coarse_apply_sigma)(void* h_, int type, capi_cd* out, const capi_cd* in
   return 1;
 }
 
+// ------------------------------------------------------------ U(1) gauge side --
+// u1/u1_utils.h through the class-API storage; gauge: host 2 V complex, phases: host 2 V doubles (nc = 1 lattice).
+namespace capi {
+struct StageReal
+{
+  double* p; double* host; long n; bool write_back;
+  StageReal(const double* h, long n_, bool in, bool out) : p(0), host((double*)h), n(n_), write_back(out)
+  { p = allocate_vector<double>(n); if (in && h != 0) capi_put_real(p, h, n); }
+  ~StageReal() { if (write_back && host != 0) capi_get_real(host, p, n); deallocate_vector(&p); }
+  operator double*() { return p; }
+private:
+  StageReal(const StageReal&); StageReal& operator=(const StageReal&);
+};
+}
+// out: Re plaq, Im plaq, topological charge
+void CAPI(u1_observables)(void* lat_, const capi_cd* gauge, double* out)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage g(gauge, lat->get_size_gauge(), true, false);
+  const capi_cd pl = get_plaquette_u1((capi_cd*)g, lat);
+  out[0] = real(pl); out[1] = imag(pl);
+  out[2] = get_topo_u1((capi_cd*)g, lat);
+}
+double CAPI(u1_action)(void* lat_, const double* phases, double beta)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::StageReal p(phases, lat->get_size_gauge(), true, false);
+  return get_noncompact_action_u1((double*)p, beta, lat);
+}
+void CAPI(u1_polar)(void* lat_, const double* phases, capi_cd* gauge)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::StageReal p(phases, lat->get_size_gauge(), true, false);
+  capi::Stage g(gauge, lat->get_size_gauge(), false, true);
+  polar_vector((double*)p, (capi_cd*)g, lat->get_size_gauge());
+}
+void CAPI(u1_gauge_trans)(void* lat_, capi_cd* gauge, const capi_cd* trans)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage g(gauge, lat->get_size_gauge(), true, true), t(trans, lat->get_size_cm(), true, false);
+  apply_gauge_trans_u1((capi_cd*)g, (capi_cd*)t, lat);
+}
+void CAPI(u1_ape_smear)(void* lat_, capi_cd* smeared, const capi_cd* gauge, double alpha, int n_iter)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage s(smeared, lat->get_size_gauge(), false, true), g(gauge, lat->get_size_gauge(), true, false);
+  apply_ape_smear_u1((capi_cd*)s, (capi_cd*)g, lat, alpha, n_iter);
+}
+void CAPI(u1_instanton)(void* lat_, capi_cd* gauge, double Q, int x0, int y0)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage g(gauge, lat->get_size_gauge(), true, true);
+  create_instanton_u1((capi_cd*)g, lat, Q, x0, y0);
+}
+void CAPI(u1_noncompact_instanton)(void* lat_, double* phases, double Q)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::StageReal p(phases, lat->get_size_gauge(), true, true);
+  create_noncompact_instanton_u1((double*)p, lat, Q);
+}
+// n_update heatbath updates from std::mt19937(seed); phases in/out
+void CAPI(u1_heatbath)(void* lat_, double* phases, double beta, int n_update, unsigned seed)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::StageReal p(phases, lat->get_size_gauge(), true, true);
+  std::mt19937 gen(seed);
+  heatbath_noncompact_update((double*)p, lat, beta, n_update, gen);
+}
+// kind: 0 read_gauge_u1 -> gauge, 1 write_gauge_u1(gauge), 2 read_phase_u1 -> phases, 3 write_gauge_u1(phases)
+void CAPI(u1_file)(void* lat_, int kind, const char* path, capi_cd* gauge, double* phases)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  const long n = lat->get_size_gauge();
+  if (kind == 0) { capi::Stage g(gauge, n, false, true); read_gauge_u1((capi_cd*)g, lat, path); }
+  else if (kind == 1) { capi::Stage g(gauge, n, true, false); write_gauge_u1((capi_cd*)g, lat, path); }
+  else if (kind == 2) { capi::StageReal p(phases, n, false, true); read_phase_u1((double*)p, lat, path); }
+  else if (kind == 3) { capi::StageReal p(phases, n, true, false); write_gauge_u1((double*)p, lat, path); }
+}
+// kind: 0 unit, 1 rand, 2 gauss(beta); 3 rand_trans (V elements).  Host draws from std::mt19937(seed) on both back ends.
+void CAPI(u1_create)(void* lat_, int kind, double beta, unsigned seed, capi_cd* out)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  std::mt19937 gen(seed);
+  const long n = kind == 3 ? lat->get_size_cm() : lat->get_size_gauge();
+  capi::Stage g(out, n, false, true);
+  if (kind == 0) unit_gauge_u1((capi_cd*)g, lat);
+  else if (kind == 1) rand_gauge_u1((capi_cd*)g, lat, gen);
+  else if (kind == 2) gauss_gauge_u1((capi_cd*)g, lat, gen, beta);
+  else rand_trans_u1((capi_cd*)g, lat, gen);
+}
+
 // ----------------------------------------------------------------- multigrid --
 void* CAPI(mg_new)(void* lat0_, void* stencil0_, int coarsest_type, double coarsest_tol, int coarsest_iters, int coarsest_restart)
 {

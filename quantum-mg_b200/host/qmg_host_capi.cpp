@@ -23,12 +23,15 @@
 #include "operators/coarse.h"
 #include "transfer/transfer.h"
 #include "multigrid/stateful_multigrid.h"
+#include "u1/u1_utils.h"
 
 #define CAPI(name) qmgh_##name
 static inline std::complex<double>* capi_alloc(long n) { return allocate_vector<std::complex<double> >(n); }
 static inline void capi_free(std::complex<double>* p) { deallocate_vector(&p); }
 static inline void capi_put(std::complex<double>* dst, const std::complex<double>* src, long n) { qmg_host::upload(dst, src, n); }
 static inline void capi_get(std::complex<double>* dst, const std::complex<double>* src, long n) { qmg_host::download(dst, src, n); }
+static inline void capi_put_real(double* dst, const double* src, long n) { qmg_host::upload_real(dst, src, n); }
+static inline void capi_get_real(double* dst, const double* src, long n) { qmg_host::download_real(dst, src, n); }
 static inline void capi_barrier() { QMG_CHK(qmg_sync()); }
 
 #include "qmg_capi_body.h"

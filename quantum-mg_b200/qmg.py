@@ -239,3 +239,9 @@ def comm_counters():
     l.qmg_comm_allreduces.restype = C.c_long
     return dict(halo_exchanges=int(l.qmg_comm_halo_exchanges()), allreduces=int(l.qmg_comm_allreduces()),
                 size=int(l.qmg_comm_size()), rank=int(l.qmg_comm_rank()), active=bool(l.qmg_comm_active()))
+
+
+def u1_ape_smear(gauge, X, Y, alpha, n_iter, textbook=False):
+    out = cvec(2 * X * Y)
+    check(lib().qmg_u1_ape_smear(ptr(out), ptr(gauge), C.c_int(X), C.c_int(Y), C.c_double(alpha), C.c_int(n_iter), C.c_int(1 if textbook else 0)))
+    return out

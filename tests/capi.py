@@ -75,6 +75,68 @@ class Lattice:
         return lhs
 
     # ---- operators
+    # ---- U(1) gauge side (u1/u1_utils.h); nc = 1 lattices
+    def u1_observables(self, gauge):
+        g = carr(gauge)
+        out = (C.c_double * 3)()
+        self.be.fn("u1_observables")(self.h, _c(g), out)
+        return complex(out[0], out[1]), out[2]
+
+    def u1_action(self, phases, beta):
+        p = np.ascontiguousarray(phases, dtype=np.float64)
+        f = self.be.fn("u1_action")
+        f.restype = C.c_double
+        return f(self.h, _c(p), C.c_double(beta))
+
+    def u1_polar(self, phases):
+        p = np.ascontiguousarray(phases, dtype=np.float64)
+        out = np.zeros(p.size, CD)
+        self.be.fn("u1_polar")(self.h, _c(p), _c(out))
+        return out
+
+    def u1_gauge_trans(self, gauge, trans):
+        g, t = carr(gauge).copy(), carr(trans)
+        self.be.fn("u1_gauge_trans")(self.h, _c(g), _c(t))
+        return g
+
+    def u1_ape_smear(self, gauge, alpha, n_iter):
+        g = carr(gauge)
+        out = np.zeros(g.size, CD)
+        self.be.fn("u1_ape_smear")(self.h, _c(out), _c(g), C.c_double(alpha), n_iter)
+        return out
+
+    def u1_instanton(self, gauge, Q, x0, y0):
+        g = carr(gauge).copy()
+        self.be.fn("u1_instanton")(self.h, _c(g), C.c_double(Q), x0, y0)
+        return g
+
+    def u1_noncompact_instanton(self, phases, Q):
+        p = np.ascontiguousarray(phases, dtype=np.float64).copy()
+        self.be.fn("u1_noncompact_instanton")(self.h, _c(p), C.c_double(Q))
+        return p
+
+    def u1_heatbath(self, phases, beta, n_update, seed):
+        p = np.ascontiguousarray(phases, dtype=np.float64).copy()
+        self.be.fn("u1_heatbath")(self.h, _c(p), C.c_double(beta), n_update, C.c_uint(seed))
+        return p
+
+    def u1_file(self, kind, path, gauge=None, phases=None):
+        n = 2 * self.X * self.Y
+        if kind == 0:
+            gauge = np.zeros(n, CD)
+        if kind == 2:
+            phases = np.zeros(n, np.float64)
+        g = None if gauge is None else carr(gauge)
+        p = None if phases is None else np.ascontiguousarray(phases, dtype=np.float64)
+        self.be.fn("u1_file")(self.h, kind, path.encode(), _c(g), _c(p))
+        return g if kind == 0 else (p if kind == 2 else None)
+
+    def u1_create(self, kind, beta=1.0, seed=1):
+        n = self.X * self.Y * (1 if kind == 3 else 2)
+        out = np.zeros(n, CD)
+        self.be.fn("u1_create")(self.h, kind, C.c_double(beta), C.c_uint(seed), _c(out))
+        return out
+
     def wilson(self, mass, gauge, wilson_coeff=1.0):
         m = complex(mass)
         g = carr(gauge)

@@ -157,3 +157,38 @@ def test_synthetic_gauge_matches_heatbath_plaquette():
     want = np.exp(-1.0 / 12.0)
     assert abs(latutil.average_plaquette(latutil.load_gauge(L), L, L) - want) < 0.01
     assert abs(latutil.average_plaquette(latutil.synthetic_gauge(L, L, 6.0, 5), L, L) - want) < 0.01
+
+
+def test_u1_known_answers(ref, tmp_path):
+    """tests/n01_u1_test: a unit field has plaquette 1 and topology 0; the plaquette is gauge invariant; a written
+    field reads back; the shipped thermalised beta = 6 configuration sits at <plaq> = exp(-1/12); a charge-1 instanton
+    on a smooth field shifts the topology by one; the non-compact action of a pure gauge field vanishes."""
+    L = 16
+    lat = ref.lattice(L, L, 1)
+    unit = lat.u1_create(0)
+    pl, q = lat.u1_observables(unit)
+    assert abs(pl - 1.0) < 1e-15 and abs(q) < 1e-15
+    hot = lat.u1_create(1, seed=3)
+    tr = lat.u1_create(3, seed=4)
+    pl0, q0 = lat.u1_observables(hot)
+    pl1, q1 = lat.u1_observables(lat.u1_gauge_trans(hot, tr))
+    assert abs(pl0 - pl1) < 1e-13 and abs(q0 - q1) < 1e-9
+    path = str(tmp_path / "cfg16_hot.dat")
+    lat.u1_file(1, path, gauge=hot)
+    back = lat.u1_file(0, path)
+    assert np.max(np.abs(back - hot)) < 1e-14
+    smooth = lat.u1_create(2, beta=60.0, seed=5)
+    q_before = lat.u1_observables(smooth)[1]
+    q_after = lat.u1_observables(lat.u1_instanton(smooth, 1.0, L // 2, L // 2))[1]
+    assert abs((q_after - q_before) - 1.0) < 0.05 or abs((q_after - q_before) + 1.0) < 0.05
+    g64 = latutil.load_gauge(64)
+    pl64, _ = ref.lattice(64, 64, 1).u1_observables(g64)
+    assert abs(pl64.real - np.exp(-1.0 / 12.0)) < 0.01
+    # pure gauge phases A_mu(x) = a(x + mu) - a(x): every plaquette angle is zero
+    a = np.random.default_rng(2).normal(size=(L, L))
+    xs, ys = np.meshgrid(np.arange(L), np.arange(L), indexing="ij")
+    idx = latutil.site_index(xs, ys, L, L)
+    ph = np.zeros(2 * L * L)
+    ph[idx.ravel()] = (np.roll(a, -1, axis=0) - a).ravel()
+    ph[L * L + idx.ravel()] = (np.roll(a, -1, axis=1) - a).ravel()
+    assert lat.u1_action(ph, 6.0) < 1e-24
