@@ -205,6 +205,10 @@ int qmg_multi_axpyz(const double* a_host, const qmg_cplx* const* xs_host, int k,
  * GLOBAL element index of an even-odd field (the ranks together draw what one GPU draws for the whole lattice) */
 int qmg_gaussian(qmg_cplx* x, long n, uint64_t seed, uint64_t stream_id, double dev);
 
+/* per-row (time-slice) reductions of colour vectors: op 0 norm2sq_cv_timeslice(a), 1 redot_cv_timeslice(a, b),
+ * 2 dot_cv_timeslice(a, b) (reductions/reductions.h:24-92); host_out: Y doubles (op 2: 2 Y, interleaved re, im) */
+int qmg_timeslice_reduce(int op, const qmg_cplx* a, const qmg_cplx* b, int X, int Y, int nc, double* host_out);
+
 /* ------------------------------------------------------- U(1) gauge fields -- */
 /* u1/u1_utils.h on the nc = 1 lattice: gauge = 2 V complex links, phases = 2 V real angles, both [mu * V + site]. */
 int qmg_zero_bytes(void* dptr, size_t bytes);                                               /* zero_vector on a double field (tests/n13_wilson_kcycle/wilson_kcycle.cpp:203) */

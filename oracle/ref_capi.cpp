@@ -33,6 +33,7 @@
 #include "transfer/transfer.h"
 #include "multigrid/stateful_multigrid.h"
 #include "u1/u1_utils.h"
+#include "reductions/reductions.h"
 
 #define CAPI(name) ref_##name
 static inline std::complex<double>* capi_alloc(long n) { return allocate_vector<std::complex<double> >((int)n); }

@@ -384,6 +384,63 @@ int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p_, const qmg_cplx*
 
 } // extern "C"
 
+// ------------------------------------------------------- time-slice reductions --
+// sum over x and colour for every row y (reductions/reductions.h:24-92: norm2sq / re_dot / dot per time slice, the
+// correlator measurement of tests/n16_wilson_kcycle_heatbath).  In the even-odd layout row y is two contiguous spans of
+// (X/2) nc elements, one per parity: one CTA per row streams both and writes out[y] (deterministic tree sum).
+namespace qmg {
+template <int OP>   // 0 |a|^2, 1 Re conj(a) b, 2 conj(a) b
+__global__ void __launch_bounds__(256) timeslice_kernel(const cd* __restrict__ a, const cd* __restrict__ b, int rowlen, long half, double* __restrict__ out)
+{
+  __shared__ double smem[8 * 2];
+  const int y = blockIdx.x;
+  double acc[2] = {0.0, 0.0};
+  for (int p = 0; p < 2; p++)
+  {
+    const cd* ra = a + (size_t)p * half + (size_t)y * rowlen;
+    const cd* rb = (OP == 0) ? ra : b + (size_t)p * half + (size_t)y * rowlen;
+    for (int i = threadIdx.x; i < rowlen; i += blockDim.x)
+    {
+      const cd u = ra[i];
+      if (OP == 0) acc[0] += u.x * u.x + u.y * u.y;
+      else
+      {
+        const cd v = rb[i];
+        acc[0] += u.x * v.x + u.y * v.y;
+        if (OP == 2) acc[1] += u.x * v.y - u.y * v.x;
+      }
+    }
+  }
+  block_sum<2>(acc, smem);
+  if (threadIdx.x == 0)
+  {
+    if (OP == 2) { out[2 * y] = acc[0]; out[2 * y + 1] = acc[1]; }
+    else out[y] = acc[0];
+  }
+}
+} // namespace qmg
+
+// op: 0 norm2sq_cv_timeslice(a), 1 redot_cv_timeslice(a, b), 2 dot_cv_timeslice(a, b); host_out: Y doubles (op 2: 2 Y).
+// On a y-slab the rows are this rank's rows (no exchange: every row lives on one rank).
+extern "C" int qmg_timeslice_reduce(int op, const qmg_cplx* a_, const qmg_cplx* b_, int X, int Y, int nc, double* host_out)
+{
+  QMG_REQUIRE_INIT();
+  if (X < 2 || Y < 1 || (X & 1) || nc < 1) return fail_msg("qmg_timeslice_reduce: bad lattice");
+  if (op < 0 || op > 2 || (op > 0 && b_ == nullptr)) return fail_msg("qmg_timeslice_reduce: bad op / missing second vector");
+  Runtime& r = rt();
+  const int rowlen = (X / 2) * nc; const long half = (long)rowlen * Y;
+  const size_t nout = (size_t)Y * (op == 2 ? 2 : 1);
+  double* d_out = ensure_partials(nout > (size_t)kMaxRedBlocks * kMaxRedWidth ? nout : (size_t)kMaxRedBlocks * kMaxRedWidth);
+  if (d_out == nullptr) return 1;
+  if (op == 0) timeslice_kernel<0><<<Y, 256, 0, r.stream>>>(CCD(a_), nullptr, rowlen, half, d_out);
+  else if (op == 1) timeslice_kernel<1><<<Y, 256, 0, r.stream>>>(CCD(a_), CCD(b_), rowlen, half, d_out);
+  else timeslice_kernel<2><<<Y, 256, 0, r.stream>>>(CCD(a_), CCD(b_), rowlen, half, d_out);
+  QMG_LAUNCH_CHECK();
+  QMG_CUDA(cudaMemcpyAsync(host_out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, r.stream));
+  QMG_CUDA(cudaStreamSynchronize(r.stream));
+  return 0;
+}
+
 // ------------------------------------------------------------------ gaussian --
 extern "C" int qmg_gaussian(qmg_cplx* x_, long n, uint64_t seed, uint64_t stream_id, double dev)
 {

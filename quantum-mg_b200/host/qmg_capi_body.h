@@ -406,6 +406,25 @@ int CAPI(coarse_apply_sigma)(void* h_, int type, capi_cd* out, const capi_cd* in
   return 1;
 }
 
+// ----------------------------------------------------- time-slice reductions --
+// op: 0 norm2sq_cv_timeslice, 1 redot_cv_timeslice, 2 dot_cv_timeslice (reductions/reductions.h); out: Y doubles (op 2: 2 Y)
+void CAPI(timeslice)(void* lat_, int op, const capi_cd* a, const capi_cd* b, double* out)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  const long n = lat->get_size_cv();
+  capi::Stage da(a, n, true, false), db(b, n, b != 0, false);
+  if (op == 0) norm2sq_cv_timeslice(out, (capi_cd*)da, lat);
+  else if (op == 1) redot_cv_timeslice(out, (capi_cd*)da, (capi_cd*)db, lat);
+  else dot_cv_timeslice((capi_cd*)out, (capi_cd*)da, (capi_cd*)db, lat);
+}
+void CAPI(wall_source)(void* lat_, int timeslice, int color, unsigned seed, double deviation, double mean, capi_cd* out)
+{
+  Lattice2D* lat = ((capi::LatticeH*)lat_)->lat;
+  capi::Stage d(out, lat->get_size_cv(), true, true);
+  std::mt19937 gen(seed);
+  gaussian_wall_source((capi_cd*)d, timeslice, color, lat, gen, deviation, mean);
+}
+
 // ------------------------------------------------------------ U(1) gauge side --
 // u1/u1_utils.h through the class-API storage; gauge: host 2 V complex, phases: host 2 V doubles (nc = 1 lattice).
 namespace capi {
@@ -645,33 +664,20 @@ struct KCycleH
   std::mt19937 generator;
   double setup_seconds;
   int null_ops;
+  int ip[14]; double dp[5]; int verbosity;
 };
-}
 
-void* CAPI(kcycle_new)(int X, int Y, double mass, const capi_cd* gauge, const int* ip, const double* dp, unsigned seed, int verbosity)
+// null vectors -> TransferMG -> Galerkin coarse operator, level by level, on top of h->op (n13 :250-416, n16 :318-440)
+inline void kcycle_build_hierarchy(KCycleH* h)
 {
-  capi_barrier();
-  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  capi::KCycleH* h = new capi::KCycleH;
-  h->generator.seed(seed);
-  h->null_ops = 0;
+  const int* ip = h->ip; const double* dp = h->dp;
   const int n_refine = ip[0], xb = ip[1], yb = ip[2], coarse_dof = ip[3];
   const QMGStencilType level_app = (QMGStencilType)ip[12];
-  h->lats.push_back(new Lattice2D(X, Y, 2));
-  {
-    capi::Stage g(gauge, 2L * X * Y, true, false);
-    h->op = new Wilson2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
-  }
   const bool need_rbj = (level_app != QMG_MATVEC_ORIGINAL) || ((QMGStencilType)ip[13] != QMG_MATVEC_ORIGINAL);
   if (need_rbj) h->op->build_rbjacobi_stencil();
-  h->coarsest = new StatefulMultigridMG::CoarsestSolveMG;
-  h->coarsest->coarsest_stencil_app = (QMGStencilType)ip[13];
-  h->coarsest->coarsest_tol = dp[1];
-  h->coarsest->coarsest_iters = ip[8];
-  h->coarsest->coarsest_restart_freq = ip[9];
   h->mg = new StatefulMultigridMG(h->lats[0], h->op, h->coarsest);
-  inversion_verbose_struct verb((inversion_verbose_level)verbosity, "[CAPI-NULLVEC]: ");
-  int cx = X, cy = Y;
+  inversion_verbose_struct verb((inversion_verbose_level)h->verbosity, "[CAPI-NULLVEC]: ");
+  int cx = h->lats[0]->get_dim_mu(0), cy = h->lats[0]->get_dim_mu(1);
   for (int i = 1; i <= n_refine; i++)
   {
     cx /= xb; cy /= yb;
@@ -715,9 +721,96 @@ void* CAPI(kcycle_new)(int X, int Y, double mass, const capi_cd* gauge, const in
                       need_rbj ? CoarseOperator2D::QMG_COARSE_BUILD_RBJACOBI : CoarseOperator2D::QMG_COARSE_BUILD_ORIGINAL, (capi_cd**)0);
     for (int j = 0; j < coarse_dof; j++) capi_free(nv[j]);
   }
+}
+// everything above level 0 (the fine operator and its lattice stay)
+inline void kcycle_drop_hierarchy(KCycleH* h)
+{
+  delete h->mg; h->mg = 0;
+  for (size_t i = 0; i < h->transfers.size(); i++) delete h->transfers[i];
+  for (size_t i = 0; i < h->level_solves.size(); i++) delete h->level_solves[i];
+  for (size_t i = 1; i < h->lats.size(); i++) delete h->lats[i];
+  h->transfers.clear(); h->level_solves.clear(); h->lats.resize(1);
+}
+}
+
+void* CAPI(kcycle_new)(int X, int Y, double mass, const capi_cd* gauge, const int* ip, const double* dp, unsigned seed, int verbosity)
+{
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  capi::KCycleH* h = new capi::KCycleH;
+  h->generator.seed(seed);
+  h->null_ops = 0;
+  for (int i = 0; i < 14; i++) h->ip[i] = ip[i];
+  for (int i = 0; i < 5; i++) h->dp[i] = dp[i];
+  h->verbosity = verbosity;
+  h->lats.push_back(new Lattice2D(X, Y, 2));
+  {
+    capi::Stage g(gauge, 2L * X * Y, true, false);
+    h->op = new Wilson2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
+  }
+  h->coarsest = new StatefulMultigridMG::CoarsestSolveMG;
+  h->coarsest->coarsest_stencil_app = (QMGStencilType)ip[13];
+  h->coarsest->coarsest_tol = dp[1];
+  h->coarsest->coarsest_iters = ip[8];
+  h->coarsest->coarsest_restart_freq = ip[9];
+  capi::kcycle_build_hierarchy(h);
   capi_barrier();
   h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return h;
+}
+// The measurement-loop step of tests/n16_wilson_kcycle_heatbath/wilson_kcycle_heatbath.cpp:300-440: new links into the
+// SAME Wilson operator (Wilson2D::update_links drops its derived link sets, wilson.h:211-225), then a fresh hierarchy.
+void CAPI(kcycle_update_links)(void* h_, const capi_cd* gauge)
+{
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  capi::kcycle_drop_hierarchy(h);
+  {
+    capi::Stage g(gauge, 2L * h->lats[0]->get_volume(), true, false);
+    static_cast<Wilson2D*>(h->op)->update_links((capi_cd*)g);
+  }
+  capi::kcycle_build_hierarchy(h);
+  capi_barrier();
+  h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// The would-be pion correlator from a point source at (x0, y0): one K-cycle-preconditioned solve per spin component,
+// |prop|^2 summed over each time slice and folded about the source (n16 :452-506).  pion: Y doubles.
+// info: total outer iterations, all converged (1/0), seconds
+void CAPI(kcycle_pion)(void* h_, int x0, int y0, int max_iter, double tol, int restart, int verbosity, double* pion, double* info)
+{
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  Lattice2D* l0 = h->lats[0];
+  const long n = l0->get_size_cv();
+  const int Y = l0->get_dim_mu(1);
+  capi_cd* src = h->mg->check_out(0); capi_cd* prop = h->mg->check_out(0);
+  std::vector<capi_cd> hsrc((size_t)n);
+  std::vector<double> part((size_t)Y);
+  inversion_verbose_struct verb((inversion_verbose_level)verbosity, "[CAPI-PION]: ");
+  for (int t = 0; t < Y; t++) pion[t] = 0.0;
+  info[0] = 0.0; info[1] = 1.0;
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  for (int spin = 0; spin < 2; spin++)
+  {
+    std::fill(hsrc.begin(), hsrc.end(), capi_cd(0.0, 0.0));
+    hsrc[l0->cv_coord_to_index(x0, y0, spin)] = 1.0;
+    capi_put(src, &hsrc[0], n);
+    zero_vector(prop, n);
+    h->mg->set_multigrid_level(0);
+    inversion_info inv = minv_vector_gcr_var_precond_restart(prop, src, (int)n, max_iter, tol, restart, apply_stencil_2D_M, (void*)h->op,
+                                                             StatefulMultigridMG::mg_preconditioner, (void*)h->mg, &verb);
+    info[0] += inv.iter; if (!inv.success) info[1] = 0.0;
+    norm2sq_cv_timeslice(&part[0], prop, l0);
+    for (int t = 0; t < Y; t++)
+    {
+      const int mirror = (2 * y0 - t + 2 * Y) % Y;     // the slice at the same distance on the other side of the source
+      pion[t] += 0.5 * (part[t] + part[mirror]);
+    }
+  }
+  capi_barrier();
+  info[2] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  h->mg->check_in(src, 0); h->mg->check_in(prop, 0);
 }
 void CAPI(kcycle_free)(void* h_)
 {

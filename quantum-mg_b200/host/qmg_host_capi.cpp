@@ -24,6 +24,7 @@
 #include "transfer/transfer.h"
 #include "multigrid/stateful_multigrid.h"
 #include "u1/u1_utils.h"
+#include "reductions/reductions.h"
 
 #define CAPI(name) qmgh_##name
 static inline std::complex<double>* capi_alloc(long n) { return allocate_vector<std::complex<double> >(n); }

@@ -75,6 +75,19 @@ class Lattice:
         return lhs
 
     # ---- operators
+    # ---- time-slice reductions / wall sources (reductions/reductions.h)
+    def timeslice(self, op, a, b=None):
+        aa = carr(a)
+        bb = None if b is None else carr(b)
+        out = np.zeros(self.Y * (2 if op == 2 else 1), np.float64)
+        self.be.fn("timeslice")(self.h, op, _c(aa), _c(bb), _c(out))
+        return out.view(CD) if op == 2 else out
+
+    def wall_source(self, timeslice, color, seed, deviation=1.0, mean=0.0):
+        out = np.full(self.size_cv, 7.0 + 0j, CD)
+        self.be.fn("wall_source")(self.h, timeslice, color, C.c_uint(seed), C.c_double(deviation), C.c_double(mean), _c(out))
+        return out
+
     # ---- U(1) gauge side (u1/u1_utils.h); nc = 1 lattices
     def u1_observables(self, gauge):
         g = carr(gauge)
@@ -394,6 +407,19 @@ class KCycle:
         out = (C.c_int * 6)()
         self.be.fn("mg_tracker")(self._mg, level, out)
         return dict(nullvec=out[0], krylov=out[1], presmooth=out[2], postsmooth=out[3], total=out[4], iters=out[5])
+
+    def update_links(self, gauge):
+        """New gauge links into the same Wilson operator and a fresh hierarchy (the n16 measurement-loop step)."""
+        g = carr(gauge)
+        self.be.fn("kcycle_update_links")(self.h, _c(g))
+        self._mg = C.c_void_p(self.be.fn("kcycle_mg")(self.h))
+
+    def pion(self, x0=0, y0=0, max_iter=1000, tol=1e-10, restart=32, verbosity=0):
+        """Folded would-be pion correlator from a point source (n16 :452-506): (Y values, info dict)."""
+        out = np.zeros(self.Y, np.float64)
+        info = (C.c_double * 3)()
+        self.be.fn("kcycle_pion")(self.h, x0, y0, max_iter, C.c_double(tol), restart, verbosity, _c(out), info)
+        return out, dict(iters=int(info[0]), success=bool(info[1]), seconds=info[2])
 
     def time_precond(self, warm=1, reps=3):
         return self.be.fn("kcycle_time_precond")(self.h, warm, reps) / reps

@@ -133,3 +133,21 @@ def test_gauge_side_on_slabs_loopback(qmg_gpu, gpu):
     assert a[0] == b[0] and a[1] == b[1]
     for u, v in zip(a[2:], b[2:]):
         assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("X,Y,nc", [(16, 8, 2), (32, 32, 8), (6, 4, 1)])
+def test_timeslice_reductions_and_wall_source(ref, gpu, X, Y, nc):
+    """reductions/reductions.h: per-row norm2sq / re_dot / dot and the gaussian wall source (the correlator measurement of
+    tests/n16_wilson_kcycle_heatbath), against the oracle and against a direct numpy sum."""
+    lr, lg = ref.lattice(X, Y, nc), gpu.lattice(X, Y, nc)
+    a, b = latutil.gaussian_cv(X * Y * nc, 1), latutil.gaussian_cv(X * Y * nc, 2)
+    for op in (0, 1, 2):
+        ra, rb = lr.timeslice(op, a, b), lg.timeslice(op, a, b)
+        assert np.allclose(rb, ra, rtol=1e-13, atol=1e-13), op
+    xs, ys = latutil.site_coords(X, Y)
+    want = np.zeros(Y)
+    np.add.at(want, np.repeat(ys, nc), np.abs(a) ** 2)
+    assert np.allclose(lg.timeslice(0, a), want, rtol=1e-13)
+    wa, wb = lr.wall_source(Y // 2, nc - 1, 5, 0.7, 0.1), lg.wall_source(Y // 2, nc - 1, 5, 0.7, 0.1)
+    assert np.array_equal(wa, wb)
+    assert np.count_nonzero(wb) == X

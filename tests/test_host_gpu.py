@@ -392,3 +392,30 @@ def test_native_kcycle_driver(ref, gpu):
     assert res["gpu"]["success"] and res["ref"]["success"]
     assert abs(res["gpu"]["iter"] - res["ref"]["iter"]) <= 2, res
     assert res["gpu"]["check_relres"] < 2e-10
+
+
+def test_n16_measurement_loop(ref, gpu):
+    """tests/n16_wilson_kcycle_heatbath: heatbath updates -> compact links -> Wilson2D::update_links on the SAME operator ->
+    fresh 3-level hierarchy -> two point-source solves -> |prop|^2 per time slice, folded.  The gauge chain is produced
+    once (by the GPU heatbath) and fed to both back ends; correlators must agree to the solver tolerance."""
+    L, beta, mass = 32, 6.0, -0.01
+    lg1 = gpu.lattice(L, L, 1)
+    phases = lg1.u1_heatbath(np.zeros(2 * L * L), beta, 300, 1)
+    kcs = {name: capi.KCycle(be, L, mass, lg1.u1_polar(phases), n_refine=2, block=4, coarse_dof=8, seed=3) for name, be in (("ref", ref), ("gpu", gpu))}
+    for step in range(2):
+        phases = lg1.u1_heatbath(phases, beta, 20, 10 + step)
+        g = lg1.u1_polar(phases)
+        plaq = lg1.u1_observables(g)[0].real
+        assert 0.85 < plaq < 0.97
+        res = {}
+        for name, kc in kcs.items():
+            kc.update_links(g)
+            res[name] = kc.pion(0, 0, tol=1e-10)
+        (pr, ir), (pg, ig) = res["ref"], res["gpu"]
+        assert ir["success"] and ig["success"]
+        assert abs(ir["iters"] - ig["iters"]) <= 2          # two solves, +-1 each
+        assert np.allclose(pg, pr, rtol=1e-6, atol=0)
+        assert np.allclose(pg[1:L // 2], pg[:L // 2:-1], rtol=1e-12)     # folded
+        assert pg[0] > pg[L // 4] > pg[L // 2] > 0                        # decays away from the source
+    for kc in kcs.values():
+        kc.free()
