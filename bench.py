@@ -95,7 +95,7 @@ def cpu_reference_apply(L, reps, warm=1):
     return BYTES_PER_SITE * L * L / sec / 1e9, sec
 
 
-def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=None, world=1, rank=0):
+def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=None, world=1, rank=0, Yl=None):
     """3-level (n_refine=2) Wilson K-cycle as tests/n13_wilson_kcycle sets it up (4x4 blocks, 8 coarse dof, BiCGstab-6 null
     vectors, MR(2,2) smoothing, inner tol 0.2), gaussian right-hand side; returns the solve record.
     world > 1 (after qmg.comm_init): this rank owns an L x L y-slab of the L x (world L) lattice (weak scaling); the
@@ -115,12 +115,12 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
             gauge = latutil.load_gauge(L)          # the reference's own thermalised config where one exists (32, 64, 128, 256)
             cfg = "tests/common_cfgs_u1 l%dt%db60" % (L, L)
         except Exception:
-            gauge = latutil.synthetic_gauge(L, L, beta=6.0, seed=seed + rank, slab=True)
+            gauge = latutil.synthetic_gauge(L, Yl or L, beta=6.0, seed=seed + rank, slab=True)
             cfg = "synthetic non-compact U(1), beta 6.0, seed %d + rank, one stackable slab per rank (tests/latutil.py synthetic_phases)" % seed
     else:
         cfg = "caller-supplied"
     t0 = time.perf_counter()
-    kc = capi.KCycle(be, L, mass, gauge, n_refine=n_refine, seed=seed, inner_iters=100, coarsest_iters=400)
+    kc = capi.KCycle(be, L, mass, gauge, n_refine=n_refine, seed=seed, inner_iters=100, coarsest_iters=400, Y=Yl)
     del gauge
     out = kc.solve(tol=tol, restart=restart, max_iter=100)
     if backend == "gpu":
@@ -132,7 +132,7 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
     out["mass"] = mass
     out["levels"] = n_refine + 1
     out["L"] = L
-    out["lattice"] = [L, L * world]
+    out["lattice"] = [L, (Yl or L) * world]
     out["outer_restart"] = restart
     if backend == "gpu":
         import torch
@@ -163,7 +163,7 @@ def run_reference(args):
     kc = None
     if args.cpu_kcycle_L > 0:
         kc = kcycle_run("ref", args.cpu_kcycle_L)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3 * args.cpu_reps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "wilson_stencil_apply_%dx%d_u1" % (args.L, args.L), "sample_L": L},
@@ -190,7 +190,10 @@ def run_gpu(args):
         qmg.comm_init()          # from here on every lattice handed to the library is this rank's y-slab
     lib = qmg.lib()
     L = args.L
-    X, Y = L, L
+    strong = args.scaling == "strong"
+    if strong and (L % (32 * world) != 0):
+        raise SystemExit("--scaling strong needs L divisible by 32 x the number of GPUs (4x4 blocks twice, even slabs)")
+    X, Y = L, (L // world if strong else L)
     V = X * Y
     n = 2 * V
     beta = 6.0
@@ -271,7 +274,8 @@ def run_gpu(args):
     if args.kcycle_L > 0:
         del clover, hopping, rhs, lhs, desc
         torch.cuda.empty_cache()
-        kcycle = kcycle_run("gpu", args.kcycle_L, restart=args.kcycle_restart, world=world, rank=rank)
+        kcycle = kcycle_run("gpu", args.kcycle_L, restart=args.kcycle_restart, world=world, rank=rank,
+                            Yl=(args.kcycle_L // world if strong else None))
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([kcycle["seconds"], kcycle["setup_seconds"], kcycle["precond_apply_s"]], device="cuda", dtype=torch.float64)
@@ -296,9 +300,9 @@ def run_gpu(args):
                     cpu["kcycle_gpu_same_config"] = kcycle_same
             except Exception as e:  # the baseline is a report, never the product path
                 cpu = {"value": None, "unit": "GB/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
-        print(json.dumps({
+        emit(json.dumps({
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "wilson_stencil_apply_%dx%d_u1" % (X, Y * world), "per_gpu_lattice": [X, Y], "beta": beta, "mass": -0.075,
                        "bytes_per_site": BYTES_PER_SITE, "l2": "operands (%.1f GB per apply) far larger than the 126 MB L2; no flush needed" % (BYTES_PER_SITE * V / 1e9),
                        "parallelism": "y-slabs x%d, 1-row halo ring" % world},
@@ -316,13 +320,29 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    # Libraries print banners on stdout (NCCL: "NCCL version ..."); stdout must carry exactly one JSON line, so everything
+    # else is sent to stderr and the line goes to a saved copy of the original descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--L", type=int, default=8192, help="per-GPU lattice is L x L")
+    ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
+                    help="weak: L x L per GPU (an L x N L lattice); strong: the L x L lattice cut into N slabs of L / N rows")
     ap.add_argument("--cpu-L", type=int, default=2048, dest="cpu_L")
     ap.add_argument("--cpu-reps", type=int, default=5, dest="cpu_reps")
     ap.add_argument("--no-cpu", action="store_true", dest="no_cpu")

@@ -83,7 +83,11 @@ int qmg_comm_active(void);
  * pack / exchange / halo-row path of the sharded build (device copies instead of NCCL).  For single-GPU testing. */
 int qmg_comm_set_loopback(int on);
 long qmg_comm_halo_exchanges(void);
-long qmg_comm_allreduces(void);
+long qmg_comm_allreduces(void);     /* ncclAllReduce calls so far (0 when the reductions all-reduce in-kernel, see qmg_comm_p2p) */
+/* 1 when every reducing kernel all-reduces its result itself through NVLink peer memory (IPC-mapped mailboxes, set up by
+ * qmg_comm_init unless QMG_P2P=0 or a peer cannot be mapped), so that no collective is launched per dot / norm */
+int qmg_comm_p2p(void);
+long qmg_comm_p2p_halo_exchanges(void);   /* halo exchanges done by peer stores into the neighbours' mailboxes (the rest went through ncclSend/Recv) */
 int qmg_halo_exchange(const qmg_cplx* field, int X, int Y, int dof, qmg_cplx* out_ym, qmg_cplx* out_yp);
 
 /* ------------------------------------------------------------ stencil ---- */

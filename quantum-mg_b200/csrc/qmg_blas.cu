@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(kEwBlock) norminf_kernel(const cd* x, long n, 
     double v = 0.0;
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) v = fmax(v, __ldcg(&partials[b]));
     v = block_max(v);
-    if (threadIdx.x == 0) { result[0] = v; *counter = 0u; }
+    if (threadIdx.x == 0) result[0] = v;
+    __syncthreads();
+    publish_result(counter, result, 1, 1, threadIdx.x, blockDim.x);
   }
 }
 } // namespace qmg

@@ -21,7 +21,15 @@ struct Comm
   size_t row_cap = 0;              // capacity of each buffer in complex elements
   long halo_exchanges = 0;
   long allreduces = 0;
+  // peer mailboxes of the in-kernel all-reduce (RedState, qmg_common.cuh): own block + the peers' blocks, IPC-mapped
+  bool p2p = false;
+  unsigned long long halo_seq = 0;      // p2p halo exchanges so far (same on every rank: exchanges are collective)
+  unsigned int* d_halo_counter = nullptr;
+  long p2p_halo_exchanges = 0;
+  double* mail_local = nullptr;
+  double* mail[kMaxRanks] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 };
+int upload_red_state(int nranks, int rank, int p2p, double* const* mail);   // qmg_runtime.cu
 Comm& comm();
 
 // rows -1 and Y of a field as received from the ring neighbours, layout (parity, x/2, dof)

@@ -21,9 +21,13 @@ struct Runtime
   // reduction scratch: per-block partials + a completion counter, and a pinned result slot
   double* d_partials = nullptr;     // at least kMaxRedBlocks * kMaxRedWidth doubles (grown on demand)
   size_t partials_cap = 0;          // capacity of d_partials in doubles
-  unsigned int* d_counter = nullptr;
+  unsigned int* d_counter = nullptr; // first word of the RedState block (see below)
   double* d_result = nullptr;       // kMaxRedWidth doubles
-  double* h_result = nullptr;       // pinned
+  double* h_result = nullptr;       // pinned, mapped: the last block of every reduction writes its result here
+  unsigned long long* h_flag = nullptr;   // pinned, mapped: number of reductions published so far
+  unsigned long long red_seq = 0;   // host mirror of that number (reductions launched)
+  int publish = 1;                  // 1: results arrive through h_result / h_flag; 0 (QMG_PUBLISH=0): copy + stream synchronise
+  int publish_now = 1;              // publish, and the kernels hold the final (all-reduced) values themselves
   void** d_ptrs = nullptr;          // small device table for pointer arrays (multi-dot etc.)
   double* d_scalars = nullptr;      // small device table for coefficient arrays
   std::string error;
@@ -33,6 +37,37 @@ Runtime& rt();
 constexpr int kMaxRedBlocks = 1184;   // 148 SMs * 8
 constexpr int kMaxRedWidth = 130;     // doubles per block partial (64 complex + 2)
 constexpr int kMaxPtrs = 256;
+constexpr int kMaxRanks = 8;          // GPUs of one NVSwitch node
+constexpr int kMailWidth = 2 * kMaxPtrs;   // doubles one rank can publish per reduction
+
+// Device-resident state of the reduction tail, shared by every reducing kernel through its `counter` argument (the block
+// starts with the completion counter).  The LAST block of a reduction, after summing the per-block partials:
+//   1. sharded with peer mailboxes (p2p): stores its values into slot [seq & 1][rank] of EVERY rank's mailbox with plain
+//      NVLink peer stores, raises its flag there, waits until all nranks flags of its own mailbox show this sequence
+//      number and sums the nranks contributions in rank order -- the all-reduce happens inside the reducing kernel, every
+//      rank obtains bit-identical values, and no collective kernel is launched;
+//   2. writes the final values and the sequence number into mapped pinned host memory, where the host thread is
+//      polling: no device-to-host copy, no stream synchronisation.
+// Two slots are enough: a rank can only start reduction n+2 after every rank has raised its flag for n+1, i.e. after
+// every rank has finished reading slot n.
+struct RedState
+{
+  unsigned int counter; unsigned int pad;
+  unsigned long long seq;
+  int nranks, rank, p2p, publish;
+  double* mail[kMaxRanks];          // mail[r]: rank r's mailbox (own: local pointer; others: IPC-mapped peer memory)
+  double* host_out;
+  unsigned long long* host_flag;
+};
+// mailbox layout: data[2][kMaxRanks][kMailWidth] doubles, then flags[2][kMaxRanks] (unsigned long long)
+constexpr size_t kMailDataDoubles = (size_t)2 * kMaxRanks * kMailWidth;
+constexpr size_t kMailBytes = sizeof(double) * kMailDataDoubles + sizeof(unsigned long long) * 2 * kMaxRanks;
+// The same IPC block continues with the halo mailbox: flags[2][2] (sequence numbers; [slot][0] = row -1 from the lower
+// neighbour, [slot][1] = row Y from the upper neighbour), then data[2][2][kHaloCap] complex.
+constexpr size_t kHaloOffset = (kMailBytes + 255) & ~(size_t)255;
+constexpr size_t kHaloCap = (size_t)1 << 18;          // complex elements per row slot (4 MB): X * dof of one boundary row
+constexpr size_t kHaloDataOffset = kHaloOffset + 256;
+constexpr size_t kPeerBlockBytes = kHaloDataOffset + sizeof(double) * 2 * 4 * kHaloCap;
 
 int fail(const char* what, cudaError_t e, const char* file, int line);
 int fail_msg(const char* msg);
@@ -117,6 +152,64 @@ __device__ __forceinline__ void block_sum(double (&v)[W], double* smem)
   __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p)
+{ unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v)
+{ asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ double ld_sys_f64(const double* p)
+{ double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_sys_f64(double* p, double v)
+{ asm volatile("st.relaxed.sys.global.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory"); }
+
+// Called by ALL threads of the last block once result[0..W) holds this rank's sums (written by one of its threads and
+// followed by __syncthreads()).  tid / nthreads: flattened thread index and count of the block.
+__device__ __forceinline__ void publish_result(unsigned int* counter, double* result, int W, int op_max, int tid, int nthreads)
+{
+  RedState* st = reinterpret_cast<RedState*>(counter);
+  const unsigned long long seq = st->seq + 1;
+  if (st->p2p)
+  {
+    const int nr = st->nranks, me = st->rank, buf = (int)(seq & 1);
+    for (int i = tid; i < W * nr; i += nthreads)
+    {
+      const int r = i / W, w = i - r * W;
+      st_sys_f64(st->mail[r] + ((size_t)buf * kMaxRanks + me) * kMailWidth + w, result[w]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < nr)
+    {
+      unsigned long long* peer_flags = reinterpret_cast<unsigned long long*>(st->mail[tid] + kMailDataDoubles);
+      st_sys_u64(peer_flags + buf * kMaxRanks + me, seq);
+      const unsigned long long* my_flags = reinterpret_cast<const unsigned long long*>(st->mail[me] + kMailDataDoubles);
+      const long long t0 = clock64();
+      while (ld_sys_u64(my_flags + buf * kMaxRanks + tid) < seq)
+        if (clock64() - t0 > 60000000000LL) { printf("[QMG-ERROR]: rank %d waited 30 s for rank %d in reduction %llu\n", me, tid, seq); __trap(); }
+    }
+    __syncthreads();
+    for (int w = tid; w < W; w += nthreads)
+    {
+      const double* slot = st->mail[me] + (size_t)buf * kMaxRanks * kMailWidth + w;
+      double acc = ld_sys_f64(slot);
+      for (int r = 1; r < nr; r++) { const double v = ld_sys_f64(slot + (size_t)r * kMailWidth); acc = op_max ? fmax(acc, v) : acc + v; }
+      result[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (st->publish)
+  {
+    for (int w = tid; w < W; w += nthreads) st->host_out[w] = result[w];
+    __threadfence_system();
+    __syncthreads();
+  }
+  if (tid == 0)
+  {
+    st->seq = seq;
+    st->counter = 0u;
+    if (st->publish) st_sys_u64(st->host_flag, seq);
+  }
+}
+
 // Deterministic grid reduction tail: every block stores its W partials; the
 // last block to arrive sums them in block order and writes result[0..W).
 template <int W>
@@ -149,8 +242,9 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[W], double* smem,
     {
 #pragma unroll
       for (int w = 0; w < W; w++) result[w] = acc[w];
-      *counter = 0u;
     }
+    __syncthreads();
+    publish_result(counter, result, W, 0, threadIdx.x, blockDim.x);
   }
 }
 

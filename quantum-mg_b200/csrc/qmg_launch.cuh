@@ -49,7 +49,8 @@ template <int W, class F> static inline int launch_reduce(long n, F f, double* h
   if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
   reduce_kernel<W><<<grid, kEwBlock, 0, r.stream>>>(n, f, r.d_partials, r.d_counter, r.d_result);
   QMG_LAUNCH_CHECK();
-  return host_out ? fetch_result(host_out, W) : 0;
+  double sink[W];
+  return fetch_result(host_out ? host_out : sink, W);     // every reduction is fetched: host and device count them alike
 }
 
 

@@ -77,11 +77,48 @@ int allreduce_result(double* d_buf, int count, int op_max);   // qmg_comm.cu
 int fetch_result(double* host_out, int count, int op_max)
 {
   Runtime& r = rt();
+  r.red_seq++;
+  if (r.publish_now)
+  {
+    // the last block of the reducing kernel wrote the (all-reduced) values and then the sequence number into mapped
+    // pinned memory: poll for it instead of a device-to-host copy and a stream synchronisation
+    volatile unsigned long long* flag = r.h_flag;
+    unsigned long spins = 0;
+    while (*flag < r.red_seq)
+    {
+      if ((++spins & 0xfff) == 0)
+      {
+        cudaError_t e = cudaStreamQuery(r.stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return fail("reduction kernel", e, __FILE__, __LINE__);
+        if (e == cudaSuccess && *flag < r.red_seq) return fail_msg("reduction finished without publishing its result");
+      }
+    }
+    __sync_synchronize();
+    for (int i = 0; i < count; i++) host_out[i] = r.h_result[i];
+    return 0;
+  }
   int rc = allreduce_result(r.d_result, count, op_max);
   if (rc) return rc;
   QMG_CUDA(cudaMemcpyAsync(r.h_result, r.d_result, sizeof(double) * count, cudaMemcpyDeviceToHost, r.stream));
   QMG_CUDA(cudaStreamSynchronize(r.stream));
   for (int i = 0; i < count; i++) host_out[i] = r.h_result[i];
+  return 0;
+}
+
+// (re)write the device-resident reduction state: called at init and whenever the communicator changes
+int upload_red_state(int nranks, int rank, int p2p, double* const* mail)
+{
+  Runtime& r = rt();
+  QMG_CUDA(cudaStreamSynchronize(r.stream));
+  RedState st;
+  memset(&st, 0, sizeof(st));
+  st.seq = r.red_seq;
+  // with several ranks the kernels only hold final values when they all-reduce through the peer mailboxes themselves
+  r.publish_now = (r.publish && (nranks == 1 || p2p)) ? 1 : 0;
+  st.nranks = nranks; st.rank = rank; st.p2p = p2p; st.publish = r.publish_now;
+  for (int i = 0; i < kMaxRanks; i++) st.mail[i] = (mail != nullptr && i < nranks) ? mail[i] : nullptr;
+  st.host_out = r.h_result; st.host_flag = r.h_flag;
+  QMG_CUDA(cudaMemcpy(r.d_counter, &st, sizeof(st), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -133,10 +170,16 @@ int qmg_init(int device)
   r.device = device;
   r.sm_count = prop.multiProcessorCount;
   if (ensure_partials((size_t)kMaxRedBlocks * kMaxRedWidth) == nullptr) return 1;
-  QMG_CUDA(cudaMalloc(&r.d_counter, sizeof(unsigned int)));
-  QMG_CUDA(cudaMemset(r.d_counter, 0, sizeof(unsigned int)));
+  QMG_CUDA(cudaMalloc(&r.d_counter, sizeof(RedState)));
   QMG_CUDA(cudaMalloc(&r.d_result, sizeof(double) * 2 * kMaxPtrs));
-  QMG_CUDA(cudaMallocHost(&r.h_result, sizeof(double) * 2 * kMaxPtrs));
+  QMG_CUDA(cudaHostAlloc(&r.h_result, sizeof(double) * 2 * kMaxPtrs + sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+  r.h_flag = reinterpret_cast<unsigned long long*>(r.h_result + 2 * kMaxPtrs);
+  *r.h_flag = 0; r.red_seq = 0;
+  {
+    const char* pe = getenv("QMG_PUBLISH");
+    r.publish = (pe != nullptr && pe[0] == '0') ? 0 : 1;
+  }
+  if (upload_red_state(1, 0, 0, nullptr)) return 1;
   QMG_CUDA(cudaMalloc(&r.d_ptrs, sizeof(void*) * kMaxPtrs));
   QMG_CUDA(cudaMalloc(&r.d_scalars, sizeof(double) * 2 * kMaxPtrs));
   QMG_CUDA(cudaDeviceSynchronize());

@@ -170,8 +170,10 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
       {
 #pragma unroll
         for (int w = 0; w < 3; w++) { double t = (lane < nwarp) ? smem[lane * 3 + w] : 0.0; accr[w] = warp_sum(t); }
-        if (lane == 0) { result[0] = accr[0]; result[1] = accr[1]; result[2] = accr[2]; *counter = 0u; }
+        if (lane == 0) { result[0] = accr[0]; result[1] = accr[1]; result[2] = accr[2]; }
       }
+      __syncthreads();
+      publish_result(counter, result, 3, 0, tid, nthreads);
     }
   }
 }

@@ -237,8 +237,9 @@ def comm_counters():
     l = lib()
     l.qmg_comm_halo_exchanges.restype = C.c_long
     l.qmg_comm_allreduces.restype = C.c_long
+    l.qmg_comm_p2p_halo_exchanges.restype = C.c_long
     return dict(halo_exchanges=int(l.qmg_comm_halo_exchanges()), allreduces=int(l.qmg_comm_allreduces()),
-                size=int(l.qmg_comm_size()), rank=int(l.qmg_comm_rank()), active=bool(l.qmg_comm_active()))
+                size=int(l.qmg_comm_size()), rank=int(l.qmg_comm_rank()), active=bool(l.qmg_comm_active()), p2p=bool(l.qmg_comm_p2p()), p2p_halo_exchanges=int(l.qmg_comm_p2p_halo_exchanges()))
 
 
 def u1_ape_smear(gauge, X, Y, alpha, n_iter, textbook=False):

@@ -43,6 +43,8 @@ def main():
     kc = capi.KCycle(be, L, a.mass, g, **kw)
     x_one, info_one = kc.solve(b, tol=a.tol, want_x=True)
     ops_one = [kc.tracker(l)["total"] for l in range(a.levels)]
+    warm_one = kc.solve(b, tol=a.tol)["seconds"]          # second solve: warm allocator
+    prec_one = kc.time_precond(1, 3)
     kc.free()
 
     qmg.comm_init()
@@ -52,6 +54,8 @@ def main():
     kc = capi.KCycle(be, L, a.mass, g_loc, Y=sl.Yl, **kw)
     x_loc, info = kc.solve(sl.take(b, 2), tol=a.tol, want_x=True)
     ops = [kc.tracker(l)["total"] for l in range(a.levels)]
+    warm = kc.solve(sl.take(b, 2), tol=a.tol)["seconds"]
+    prec = kc.time_precond(1, 3)
     kc.free()
     cnt = qmg.comm_counters()
     qmg.comm_finalize()
@@ -59,9 +63,9 @@ def main():
     err = latutil.rel_l2(x_loc, sl.take(x_one, 2))
     ok = abs(info["iter"] - info_one["iter"]) <= 1 and err < 1e-8 and info["success"]
     ok = ok and all(abs(p - q) <= max(2, 0.05 * q) for p, q in zip(ops, ops_one))
-    print("[rank %d] one GPU: iter %d ops %s relres %.2e | %d slabs: iter %d ops %s relres %.2e | slab error %.2e | halo exchanges %d all-reduces %d"
+    print("[rank %d] one GPU: iter %d ops %s relres %.2e | %d slabs: iter %d ops %s relres %.2e | slab error %.2e | halo exchanges %d nccl all-reduces %d p2p %s | warm solve %.4f s, K-cycle apply %.5f s (one GPU %.4f s, %.5f s)"
           % (rank, info_one["iter"], ops_one, info_one["check_relres"], world, info["iter"], ops, info["check_relres"], err,
-             cnt["halo_exchanges"], cnt["allreduces"]), flush=True)
+             cnt["halo_exchanges"], cnt["allreduces"], cnt["p2p"], warm, prec, warm_one, prec_one), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
