@@ -650,7 +650,8 @@ int CAPI(mg_storage_counts)(void* h_, int level, int* out)
 // iterations, tol 5e-5), orthogonalised, chirally doubled and normalised; TransferMG with block
 // orthonormalisation and QMG_DOUBLE_PROJECTION; Galerkin coarse operators; MR(pre, post) smoothing.
 // iparams: n_refine, x_block, y_block, coarse_dof, pre_iters, post_iters, inner_iters, inner_restart,
-//          coarsest_iters, coarsest_restart, null_max_iter, null_L, fine_stencil_app (all levels), coarsest_stencil_app
+//          coarsest_iters, coarsest_restart, null_max_iter, null_L, fine_stencil_app (all levels), coarsest_stencil_app,
+//          fine operator (0 Wilson2D, 1 Staggered2D: nc = 1, null vectors doubled by the even / odd projection, staggered.h:176-181)
 // dparams: inner_tol, coarsest_tol, null_tol, pre_tol, post_tol
 namespace capi {
 struct KCycleH
@@ -664,7 +665,7 @@ struct KCycleH
   std::mt19937 generator;
   double setup_seconds;
   int null_ops;
-  int ip[14]; double dp[5]; int verbosity;
+  int ip[15]; double dp[5]; int verbosity;
 };
 
 // null vectors -> TransferMG -> Galerkin coarse operator, level by level, on top of h->op (n13 :250-416, n16 :318-440)
@@ -740,13 +741,15 @@ void* CAPI(kcycle_new)(int X, int Y, double mass, const capi_cd* gauge, const in
   capi::KCycleH* h = new capi::KCycleH;
   h->generator.seed(seed);
   h->null_ops = 0;
-  for (int i = 0; i < 14; i++) h->ip[i] = ip[i];
+  for (int i = 0; i < 15; i++) h->ip[i] = ip[i];
   for (int i = 0; i < 5; i++) h->dp[i] = dp[i];
   h->verbosity = verbosity;
-  h->lats.push_back(new Lattice2D(X, Y, 2));
+  const bool staggered = (ip[14] == 1);
+  h->lats.push_back(new Lattice2D(X, Y, staggered ? 1 : 2));
   {
     capi::Stage g(gauge, 2L * X * Y, true, false);
-    h->op = new Wilson2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
+    if (staggered) h->op = new Staggered2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
+    else h->op = new Wilson2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
   }
   h->coarsest = new StatefulMultigridMG::CoarsestSolveMG;
   h->coarsest->coarsest_stencil_app = (QMGStencilType)ip[13];
@@ -758,6 +761,139 @@ void* CAPI(kcycle_new)(int X, int Y, double mass, const capi_cd* gauge, const in
   h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return h;
 }
+// ---- adaptive set-up (tests/n22_wilson_kcycle_adaptive/wilson_kcycle.cpp:226-440): test vectors relaxed with
+// Richardson(10, omega = 0.33) build a first hierarchy, then n_setup rounds re-solve every test vector with 10 iterations
+// of flexible GCR preconditioned by the CURRENT K-cycle (on coarser levels: starting from the restriction of the
+// vector one level up), rebuild that level's transfer / coarse operator (update_level) and re-relax everything below.
+namespace capi {
+typedef std::vector<std::vector<capi_cd*> > TestVectors;
+
+// relax fresh gaussian vectors on level `fine` and build (or update) level fine + 1 from them (n22 :620-705)
+inline TransferMG* adaptive_build_below(KCycleH* h, TestVectors& test, int fine, StatefulMultigridMG::LevelSolveMG* ls, bool fresh, inversion_verbose_struct* verb)
+{
+  Lattice2D* fl = h->mg->get_lattice(fine); Lattice2D* cl = h->lats[fine + 1];
+  const int coarse_dof = cl->get_nc(); const long nf = fl->get_size_cv();
+  std::vector<capi_cd*> nv(coarse_dof);
+  for (int j = 0; j < coarse_dof / 2; j++)
+  {
+    nv[j] = capi_alloc(nf); nv[j + coarse_dof / 2] = capi_alloc(nf);
+    zero_vector(nv[j], nf); zero_vector(nv[j + coarse_dof / 2], nf);
+    capi_cd* rnd = h->mg->get_storage(fine)->check_out();
+    gaussian(rnd, nf, h->generator);
+    inversion_info inv = minv_vector_richardson(test[fine][j], rnd, nf, 10, 1e-10, 0.33, 250, apply_stencil_2D_M, (void*)h->mg->get_stencil(fine), verb);
+    h->mg->add_tracker_count(QMG_DSLASH_TYPE_NULLVEC, inv.ops_count, fine);
+    h->null_ops += inv.ops_count;
+    h->mg->get_storage(fine)->check_in(rnd);
+    for (int k = 0; k < j; k++) orthogonal(test[fine][j], test[fine][k], nf);
+    normalize(test[fine][j], nf);
+    copy_vector(nv[j], test[fine][j], nf);
+    h->mg->get_stencil(fine)->chiral_projection_both(nv[j], nv[j + coarse_dof / 2]);
+  }
+  // level 0 states the doubling (n22 :308); the levels below use the 4-argument constructor (n22 :680)
+  TransferMG* tr = (fine == 0) ? new TransferMG(fl, cl, &nv[0], true, false, QMG_DOUBLE_PROJECTION) : new TransferMG(fl, cl, &nv[0], true);
+  if (fresh) h->mg->push_level(cl, tr, ls, true, true, MultigridMG::QMG_MULTIGRID_PRECOND_ORIGINAL, &nv[0]);
+  else h->mg->update_level(fine + 1, cl, tr, ls, true, true, MultigridMG::QMG_MULTIGRID_PRECOND_ORIGINAL, &nv[0]);
+  for (int j = 0; j < coarse_dof; j++) capi_free(nv[j]);
+  return tr;
+}
+}
+
+// iparams / dparams as kcycle_new (null_max_iter, null_L, null_tol unused: the relaxation is Richardson); Wilson only.
+void* CAPI(kcycle_new_adaptive)(int X, int Y, double mass, const capi_cd* gauge, const int* ip, const double* dp, int n_setup, unsigned seed, int verbosity)
+{
+  capi_barrier();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  capi::KCycleH* h = new capi::KCycleH;
+  h->generator.seed(seed);
+  h->null_ops = 0;
+  for (int i = 0; i < 15; i++) h->ip[i] = ip[i];
+  for (int i = 0; i < 5; i++) h->dp[i] = dp[i];
+  h->verbosity = verbosity;
+  const int n_refine = ip[0], xb = ip[1], yb = ip[2], coarse_dof = ip[3];
+  h->lats.push_back(new Lattice2D(X, Y, 2));
+  {
+    capi::Stage g(gauge, 2L * X * Y, true, false);
+    h->op = new Wilson2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
+  }
+  h->coarsest = new StatefulMultigridMG::CoarsestSolveMG;
+  h->coarsest->coarsest_stencil_app = QMG_MATVEC_ORIGINAL;
+  h->coarsest->coarsest_tol = dp[1];
+  h->coarsest->coarsest_iters = ip[8];
+  h->coarsest->coarsest_restart_freq = ip[9];
+  h->mg = new StatefulMultigridMG(h->lats[0], h->op, h->coarsest);
+  inversion_verbose_struct verb((inversion_verbose_level)verbosity, "[CAPI-ADAPTIVE]: ");
+  int cx = X, cy = Y;
+  capi::TestVectors test(n_refine);
+  for (int i = 0; i < n_refine; i++)
+  {
+    cx /= xb; cy /= yb;
+    h->lats.push_back(new Lattice2D(cx, cy, coarse_dof));
+    const long nf = h->lats[i]->get_size_cv();
+    test[i].resize(coarse_dof / 2);
+    for (int j = 0; j < coarse_dof / 2; j++) { test[i][j] = capi_alloc(nf); zero_vector(test[i][j], nf); }
+    // while setting up, every level below the top runs 8 unrestarted flexible-GCR iterations (n22 :248-256)
+    StatefulMultigridMG::LevelSolveMG* ls = new StatefulMultigridMG::LevelSolveMG;
+    ls->fine_stencil_app = QMG_MATVEC_ORIGINAL;
+    ls->intermediate_tol = 1e-10; ls->intermediate_iters = 8; ls->intermediate_restart_freq = 1024;
+    ls->pre_tol = dp[3]; ls->pre_iters = ip[4];
+    ls->post_tol = dp[4]; ls->post_iters = ip[5];
+    h->level_solves.push_back(ls);
+  }
+  h->transfers.resize(n_refine, (TransferMG*)0);
+  for (int i = 0; i < n_refine; i++) h->transfers[i] = capi::adaptive_build_below(h, test, i, h->level_solves[i], true, &verb);
+
+  for (int m = 0; m < n_setup; m++)
+  {
+    for (int i = 0; i < n_refine; i++)
+    {
+      Lattice2D* fl = h->lats[i]; Lattice2D* cl = h->lats[i + 1];
+      const long nf = fl->get_size_cv();
+      std::vector<capi_cd*> nv(coarse_dof);
+      for (int j = 0; j < coarse_dof / 2; j++)
+      {
+        nv[j] = capi_alloc(nf); nv[j + coarse_dof / 2] = capi_alloc(nf);
+        capi_cd* rhs = h->mg->get_storage(i)->check_out();
+        if (i == 0) copy_vector(rhs, test[0][j], nf);
+        else { zero_vector(rhs, nf); h->mg->get_transfer(i - 1)->restrict_f2c(test[i - 1][j], rhs); }
+        zero_vector(test[i][j], nf);
+        inversion_info inv = minv_vector_gcr_var_precond(test[i][j], rhs, nf, 10, 1e-10, apply_stencil_2D_M, (void*)h->mg->get_stencil(i),
+                                                         StatefulMultigridMG::mg_preconditioner, (void*)h->mg, &verb);
+        h->mg->get_storage(i)->check_in(rhs);
+        h->mg->add_tracker_count(QMG_DSLASH_TYPE_NULLVEC, inv.ops_count + 1, i);
+        h->null_ops += inv.ops_count + 1;
+        for (int k = 0; k < j; k++) orthogonal(test[i][j], test[i][k], nf);
+        normalize(test[i][j], nf);
+        zero_vector(nv[j + coarse_dof / 2], nf);
+        copy_vector(nv[j], test[i][j], nf);
+        h->mg->get_stencil(i)->chiral_projection_both(nv[j], nv[j + coarse_dof / 2]);
+      }
+      delete h->transfers[i];
+      h->transfers[i] = new TransferMG(fl, cl, &nv[0], true, false, QMG_DOUBLE_PROJECTION);
+      h->mg->update_level(i + 1, cl, h->transfers[i], h->level_solves[i], true, true, MultigridMG::QMG_MULTIGRID_PRECOND_ORIGINAL, &nv[0]);
+      for (int j = i + 1; j < n_refine; j++)
+      {
+        delete h->transfers[j];
+        h->transfers[j] = capi::adaptive_build_below(h, test, j, h->level_solves[j], false, &verb);
+      }
+      for (int j = 0; j < coarse_dof; j++) capi_free(nv[j]);
+      if (i < n_refine - 1) h->mg->go_coarser();
+    }
+    for (int i = 0; i < n_refine - 1; i++) h->mg->go_finer();
+  }
+  for (int i = 0; i <= n_refine; i++) h->mg->shift_all_to_nullvec(i);
+  for (int i = 0; i < n_refine; i++)
+  {
+    // the solve uses the n13 parameters again (n22 :420-433)
+    StatefulMultigridMG::LevelSolveMG* ls = h->level_solves[i];
+    ls->intermediate_tol = dp[0]; ls->intermediate_iters = ip[6]; ls->intermediate_restart_freq = ip[7];
+  }
+  for (int i = 0; i < n_refine; i++)
+    for (size_t j = 0; j < test[i].size(); j++) capi_free(test[i][j]);
+  capi_barrier();
+  h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return h;
+}
+
 // The measurement-loop step of tests/n16_wilson_kcycle_heatbath/wilson_kcycle_heatbath.cpp:300-440: new links into the
 // SAME Wilson operator (Wilson2D::update_links drops its derived link sets, wilson.h:211-225), then a fresh hierarchy.
 void CAPI(kcycle_update_links)(void* h_, const capi_cd* gauge)
@@ -768,7 +904,8 @@ void CAPI(kcycle_update_links)(void* h_, const capi_cd* gauge)
   capi::kcycle_drop_hierarchy(h);
   {
     capi::Stage g(gauge, 2L * h->lats[0]->get_volume(), true, false);
-    static_cast<Wilson2D*>(h->op)->update_links((capi_cd*)g);
+    if (h->ip[14] == 1) static_cast<Staggered2D*>(h->op)->update_links((capi_cd*)g);
+    else static_cast<Wilson2D*>(h->op)->update_links((capi_cd*)g);
   }
   capi::kcycle_build_hierarchy(h);
   capi_barrier();
@@ -791,7 +928,7 @@ void CAPI(kcycle_pion)(void* h_, int x0, int y0, int max_iter, double tol, int r
   info[0] = 0.0; info[1] = 1.0;
   capi_barrier();
   std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  for (int spin = 0; spin < 2; spin++)
+  for (int spin = 0; spin < l0->get_nc(); spin++)
   {
     std::fill(hsrc.begin(), hsrc.end(), capi_cd(0.0, 0.0));
     hsrc[l0->cv_coord_to_index(x0, y0, spin)] = 1.0;

@@ -380,21 +380,25 @@ class KCycle:
 
     def __init__(self, be, L, mass, gauge, n_refine=1, block=4, coarse_dof=8, pre_iters=2, post_iters=2, inner_tol=0.2, inner_iters=1000,
                  inner_restart=32, coarsest_tol=0.2, coarsest_iters=1000, coarsest_restart=32, null_max_iter=500, null_tol=5e-5, null_L=6,
-                 level_app=0, coarsest_app=0, pre_tol=1e-15, post_tol=1e-15, seed=1337, verbosity=0, Y=None):
+                 level_app=0, coarsest_app=0, pre_tol=1e-15, post_tol=1e-15, seed=1337, verbosity=0, Y=None, staggered=False, adaptive_setups=None):
         self.be, self.X, self.Y = be, L, (L if Y is None else Y)
-        for name in ("kcycle_new", "kcycle_mg"):
+        self.nc0 = 1 if staggered else 2
+        for name in ("kcycle_new", "kcycle_new_adaptive", "kcycle_mg"):
             be.fn(name).restype = C.c_void_p
         be.fn("kcycle_time_precond").restype = C.c_double
-        ip = (C.c_int * 14)(n_refine, block, block, coarse_dof, pre_iters, post_iters, inner_iters, inner_restart, coarsest_iters,
-                            coarsest_restart, null_max_iter, null_L, level_app, coarsest_app)
+        ip = (C.c_int * 15)(n_refine, block, block, coarse_dof, pre_iters, post_iters, inner_iters, inner_restart, coarsest_iters,
+                            coarsest_restart, null_max_iter, null_L, level_app, coarsest_app, 1 if staggered else 0)
         dp = (C.c_double * 5)(inner_tol, coarsest_tol, null_tol, pre_tol, post_tol)
         g = carr(gauge)
         self.n_levels = n_refine + 1
-        self.h = C.c_void_p(be.fn("kcycle_new")(self.X, self.Y, C.c_double(mass), _c(g), ip, dp, C.c_uint(seed), verbosity))
+        if adaptive_setups is None:
+            self.h = C.c_void_p(be.fn("kcycle_new")(self.X, self.Y, C.c_double(mass), _c(g), ip, dp, C.c_uint(seed), verbosity))
+        else:       # tests/n22_wilson_kcycle_adaptive: Richardson-relaxed test vectors refined by the K-cycle itself
+            self.h = C.c_void_p(be.fn("kcycle_new_adaptive")(self.X, self.Y, C.c_double(mass), _c(g), ip, dp, int(adaptive_setups), C.c_uint(seed), verbosity))
         self._mg = C.c_void_p(be.fn("kcycle_mg")(self.h))
 
     def solve(self, b=None, outer_type=0, max_iter=1000, tol=1e-10, restart=32, verbosity=0, want_x=False):
-        n = self.X * self.Y * 2
+        n = self.X * self.Y * self.nc0
         bb = None if b is None else carr(b)
         x = np.zeros(n, CD) if want_x else None
         info = (C.c_double * 8)()

@@ -419,3 +419,78 @@ def test_n16_measurement_loop(ref, gpu):
         assert pg[0] > pg[L // 4] > pg[L // 2] > 0                        # decays away from the source
     for kc in kcs.values():
         kc.free()
+
+
+def test_staggered_kcycle_parity(ref, gpu):
+    """BASELINE config 3 at a size the oracle finishes in seconds: 3-level K-cycle on the staggered operator (nc = 1; four
+    BiCGstab-L null vectors doubled by the even / odd projection, staggered.h:176-181; 4x4 blocks twice) on the shipped
+    64^2 beta = 6 configuration.  The un-preconditioned staggered operator is a hard case for this cycle (about 160 outer
+    iterations at m = 0.1), which makes it a long lock-step comparison of the two back ends."""
+    L, mass = 64, 0.1
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L, 5)
+    res = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        kc = capi.KCycle(be, L, mass, g, n_refine=2, block=4, coarse_dof=8, seed=3, staggered=True)
+        x, info = kc.solve(b, tol=1e-10, want_x=True)
+        res[name] = (x, info, [kc.tracker(l)["total"] for l in range(3)])
+        kc.free()
+    (xr, ir, opr), (xg, ig, opg) = res["ref"], res["gpu"]
+    assert ir["success"] and ig["success"]
+    assert abs(ir["iter"] - ig["iter"]) <= 2
+    assert ig["check_relres"] < 2e-10
+    assert all(abs(p - q) <= 0.03 * q + 2 for p, q in zip(opg, opr))
+    assert latutil.rel_l2(xg, xr) < 1e-8
+
+
+def test_staggered_kcycle_full_size(gpu):
+    """BASELINE config 3 at full size (1024^2, 3 levels: 1024 -> 256 -> 64) through size-independent properties: the solve
+    converges, the explicit residual of the ORIGINAL system meets the tolerance, and the iteration count stays in the
+    range the 64^2 run sets (the cycle's convergence rate does not depend on the volume)."""
+    L, mass = 1024, 0.1
+    g = latutil.synthetic_gauge(L, L, 6.0, 21)
+    kc = capi.KCycle(gpu, L, mass, g, n_refine=2, block=4, coarse_dof=8, seed=3, staggered=True, inner_iters=100, coarsest_iters=400)
+    out = kc.solve(tol=1e-10, max_iter=600)
+    ops = [kc.tracker(l)["total"] for l in range(3)]
+    kc.free()
+    assert out["success"] and out["check_relres"] < 2e-10
+    assert 50 < out["iter"] < 400, (out, ops)
+
+
+@pytest.mark.parametrize("n_setup", [0, 1])
+def test_n22_adaptive_setup_parity(ref, gpu, n_setup):
+    """tests/n22_wilson_kcycle_adaptive: test vectors relaxed by Richardson(10, 0.33), then refined by 10 iterations of
+    flexible GCR preconditioned by the current K-cycle, update_level + rebuild of the levels below (go_coarser / go_finer),
+    outer VPGCR(64).  Same driver text on both back ends; the refinement must pay off identically (132 -> 21 iterations)."""
+    L = 64
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L * 2, 5)
+    res = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        kc = capi.KCycle(be, L, -0.05, g, n_refine=2, block=4, coarse_dof=8, seed=3, adaptive_setups=n_setup)
+        x, info = kc.solve(b, tol=1e-10, restart=64, want_x=True)
+        res[name] = (x, info, [kc.tracker(l)["total"] for l in range(3)])
+        kc.free()
+    (xr, ir, opr), (xg, ig, opg) = res["ref"], res["gpu"]
+    assert ir["success"] and ig["success"]
+    assert abs(ir["iter"] - ig["iter"]) <= 1 + ir["iter"] // 50
+    assert ir["null_ops"] == ig["null_ops"]
+    assert latutil.rel_l2(xg, xr) < 1e-8
+    if n_setup == 1:
+        assert ig["iter"] < 40
+
+
+def test_n22_adaptive_full_size(gpu):
+    """BASELINE config 4 at full size (4096^2, 3 levels, one adaptive set-up round) through size-independent properties:
+    convergence to 1e-10 on the explicit residual of the original system in about as many iterations as at 64^2 / 128^2."""
+    L = 4096
+    g = latutil.synthetic_gauge(L, L, 6.0, 1337, slab=True)
+    kc = capi.KCycle(gpu, L, -0.05, g, n_refine=2, block=4, coarse_dof=8, seed=3, adaptive_setups=1, inner_iters=100, coarsest_iters=400)
+    del g
+    out = kc.solve(tol=1e-10, restart=16, max_iter=100)
+    ops = [kc.tracker(l)["total"] for l in range(3)]
+    kc.free()
+    import qmg
+    qmg.check(qmg.lib().qmg_trim())
+    assert out["success"] and out["check_relres"] < 2e-10, (out, ops)
+    assert out["iter"] <= 40, (out, ops)
