@@ -44,11 +44,11 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
     for (k = 1; k <= max_iter; k++)
     {
       const int c = k - 1;
-      double d[3];
-      QMG_CHK(qmg_dot_norm(P(Ap[c]), P(r), size, d));
-      ApNormSq.push_back(d[2]);
-      const complex<double> alpha = complex<double>(d[0], d[1]) / d[2];
-      QMG_CHK(qmg_update_xr_norm(alpha.real(), alpha.imag(), P(p[c]), P(Ap[c]), P(phi), P(r), size, &rsq));
+      // alpha = <Ap|r> / <Ap|Ap> formed on the device; x += alpha p ; r -= alpha Ap ; |r|^2 : one host wait per step
+      double step[4];
+      QMG_CHK(qmg_step_xr_norm(1.0, P(p[c]), P(Ap[c]), P(phi), P(r), size, step));
+      rsq = step[0];
+      ApNormSq.push_back(step[3]);
       say(verb, VERB_DETAIL, name, "", false, false, k, invif.ops_count, sqrt(rsq) / bsqrt);
       if (sqrt(rsq) < eps * bsqrt) { converged = true; break; }
       if (k == max_iter) break;

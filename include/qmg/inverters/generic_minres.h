@@ -31,11 +31,11 @@ inline inversion_info minv_vector_minres(complex<double>* phi, complex<double>* 
   else for (k = 1; k <= max_iter; k++)
   {
     matrix_vector(p, r, extra_info); invif.ops_count++;
-    double d[3];
-    QMG_CHK(qmg_dot_norm(qmg_host::P(p), qmg_host::P(r), size, d));
-    const complex<double> alpha = omega * complex<double>(d[0], d[1]) / d[2];
-    // x += alpha r ; r -= alpha p ; |r|^2  (x is updated from the old r inside the same thread)
-    QMG_CHK(qmg_update_xr_norm(alpha.real(), alpha.imag(), qmg_host::P(r), qmg_host::P(p), qmg_host::P(phi), qmg_host::P(r), size, &rsq));
+    // alpha = omega <Ar|r> / <Ar|Ar> ; x += alpha r ; r -= alpha A r ; |r|^2 -- alpha is formed on the device, one host wait
+    // (x is updated from the old r inside the same thread)
+    double step[4];
+    QMG_CHK(qmg_step_xr_norm(omega, qmg_host::P(r), qmg_host::P(p), qmg_host::P(phi), qmg_host::P(r), size, step));
+    rsq = step[0];
     qmg_host::say(verb, VERB_DETAIL, "MR", "", false, false, k, invif.ops_count, sqrt(rsq) / bsqrt);
     if (sqrt(rsq) < eps * bsqrt) { converged = true; break; }
   }

@@ -201,6 +201,9 @@ int qmg_multi_dot(const qmg_cplx* const* xs_host, int k, const qmg_cplx* y, long
 /* fused Krylov updates */
 /* x += a p ; r -= a q ; result = |r|^2   (MR / GCR step) */
 int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p, const qmg_cplx* q, qmg_cplx* x, qmg_cplx* r, long n, double* result);
+/* One MR / GCR step with a single host wait: alpha = omega <q|r>/<q|q> formed on the device, x += alpha p, r -= alpha q;
+ * result4 = { |r|^2, Re<q|r>, Im<q|r>, <q|q> }.  Bit-identical to qmg_dot_norm(q, r) + qmg_update_xr_norm(alpha, p, q, x, r). */
+int qmg_step_xr_norm(double omega, const qmg_cplx* p, const qmg_cplx* q, qmg_cplx* x, qmg_cplx* r, long n, double* result4);
 /* y += sum_j a_j xs[j]   (GCR: p_k += sum beta_i p_i) ; a: HOST 2k doubles; xs: HOST array of k device pointers */
 int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y, long n);
 /* y = x0 + sum_j a_j xs[j]   (GCR: p_k = r + sum beta_i p_i without a separate copy); x0 == y allowed */

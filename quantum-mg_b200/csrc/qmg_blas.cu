@@ -384,6 +384,50 @@ int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p_, const qmg_cplx*
   }, result);
 }
 
+// One Krylov step with ONE host wait:  alpha = omega <q|r> / <q|q> ;  x += alpha p ;  r -= alpha q ;
+// result4 = { |r|^2, Re<q|r>, Im<q|r>, <q|q> }.
+// (MR: p = r, q = A r; GCR: p = direction, q = A p, omega = 1.)  The dot products stay on the device: the first kernel
+// leaves them (all-reduced) in device memory, every thread of the second forms alpha from them exactly as the host would
+// -- (omega d0) / d2, (omega d1) / d2, no contraction -- so the step is bit-identical to qmg_dot_norm followed by
+// qmg_update_xr_norm with one round trip instead of two.  The dot products reach the host through a side slot of the
+// mapped result buffer, written by element 0's thread.
+int qmg_step_xr_norm(double omega, const qmg_cplx* p_, const qmg_cplx* q_, qmg_cplx* x_, qmg_cplx* r_, long n, double* result4)
+{
+  QMG_REQUIRE_INIT();
+  if (n <= 0) return fail_msg("qmg_step_xr_norm: empty vector");
+  Runtime& rtm = rt();
+  const cd* p = CCD(p_); const cd* q = CCD(q_); cd* x = CD(x_); cd* r = CD(r_);
+  double* dres = rtm.d_result + 64;                    // device slot of the dot products
+  double* aux = rtm.h_result + 256;                    // mapped host slot the second kernel copies them to
+  int rc = launch_reduce_keep<3>(n, [=] __device__(long i, double (&acc)[3]) {
+    cd a = q[i], b = r[i];
+    acc[0] += a.x * b.x + a.y * b.y;
+    acc[1] += a.x * b.y - a.y * b.x;
+    acc[2] += a.x * a.x + a.y * a.y;
+  }, dres);
+  if (rc) return rc;
+  double out[1];
+  rc = launch_reduce<1>(n, [=] __device__(long i, double (&acc)[1]) {
+    const double d0 = dres[0], d1 = dres[1], d2 = dres[2];
+    const cd a = cmake(__ddiv_rn(__dmul_rn(omega, d0), d2), __ddiv_rn(__dmul_rn(omega, d1), d2));
+    const cd ma = cmake(-a.x, -a.y);
+    if (i == 0) { aux[0] = d0; aux[1] = d1; aux[2] = d2; __threadfence_system(); }
+    cd pi = p[i];
+    cd xi = x[i]; cfma(xi, a, pi); x[i] = xi;
+    cd ri = r[i]; cfma(ri, ma, q[i]); r[i] = ri;
+    acc[0] += ri.x * ri.x + ri.y * ri.y;
+  }, out);
+  if (rc) return rc;
+  result4[0] = out[0];
+  if (rtm.publish_now) { result4[1] = aux[0]; result4[2] = aux[1]; result4[3] = aux[2]; }
+  else
+  {
+    // copy-and-synchronise mode: the stream has been synchronised by the fetch above
+    QMG_CUDA(cudaMemcpy(result4 + 1, dres, sizeof(double) * 3, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
 } // extern "C"
 
 // ------------------------------------------------------- time-slice reductions --

@@ -250,6 +250,8 @@ __device__ __forceinline__ void grid_reduce_finish(double (&v)[W], double* smem,
 
 // fetch `count` doubles of the reduction result to the host (synchronises the stream)
 int fetch_result(double* host_out, int count, int op_max = 0);   // all-reduced over the ranks when sharded
+// count a reduction whose result is consumed on the device (NCCL fallback: all-reduce it in place, stream-ordered)
+int skip_result(double* result_dev, int count);
 // make sure the per-block partial scratch holds `ndoubles`; returns nullptr on failure
 double* ensure_partials(size_t ndoubles);
 int reduction_grid(long n_items, int items_per_block);

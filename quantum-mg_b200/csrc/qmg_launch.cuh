@@ -81,4 +81,16 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t ctr_lo, u
   n0 = rad * co; n1 = rad * s;
 }
 
+// A reduction whose result stays on the device (all-reduced over the ranks like any other) for the NEXT kernel to read:
+// nothing is fetched, the host only keeps its reduction count in step.  result_dev: W doubles of device memory.
+template <int W, class F> static inline int launch_reduce_keep(long n, F f, double* result_dev)
+{
+  Runtime& r = rt();
+  int grid = ew_grid(n > 0 ? n : 1);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  reduce_kernel<W><<<grid, kEwBlock, 0, r.stream>>>(n, f, r.d_partials, r.d_counter, result_dev);
+  QMG_LAUNCH_CHECK();
+  return skip_result(result_dev, W);
+}
+
 } // namespace qmg

@@ -285,6 +285,34 @@ def test_blas(qmg_gpu):
     assert latutil.rel_l2(host(dyy), yy + sum(c * v for c, v in zip(coef, vs))) < 1e-14
 
 
+def test_fused_krylov_step(qmg_gpu):
+    """qmg_step_xr_norm (alpha formed on the device between two kernels, one host wait) == qmg_dot_norm + host alpha +
+    qmg_update_xr_norm, bit for bit, including the MR aliasing p == r."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    for n in (5, 4096, 100003):
+        for alias in (False, True):
+            p0, q0, x0, r0 = (latutil.gaussian_cv(n, s) for s in (1, 2, 3, 4))
+            omega = 0.85
+            # reference sequence
+            q, x, r = dev(qmg, q0), dev(qmg, x0), dev(qmg, r0)
+            p = r if alias else dev(qmg, p0)
+            d = (C.c_double * 3)()
+            qmg.check(lib.qmg_dot_norm(qmg.ptr(q), qmg.ptr(r), C.c_long(n), d))
+            alpha = omega * complex(d[0], d[1]) / d[2]
+            rsq = C.c_double()
+            qmg.check(lib.qmg_update_xr_norm(C.c_double(alpha.real), C.c_double(alpha.imag), qmg.ptr(p), qmg.ptr(q), qmg.ptr(x), qmg.ptr(r), C.c_long(n), C.byref(rsq)))
+            want = (host(x), host(r), rsq.value, tuple(d))
+            # fused step
+            q, x, r = dev(qmg, q0), dev(qmg, x0), dev(qmg, r0)
+            p = r if alias else dev(qmg, p0)
+            out = (C.c_double * 4)()
+            qmg.check(lib.qmg_step_xr_norm(C.c_double(omega), qmg.ptr(p), qmg.ptr(q), qmg.ptr(x), qmg.ptr(r), C.c_long(n), out))
+            assert np.array_equal(host(x), want[0]) and np.array_equal(host(r), want[1]), (n, alias)
+            assert out[0] == want[2] and (out[1], out[2], out[3]) == want[3], (n, alias)
+
+
 def test_fused_apply_dot(ref, qmg_gpu):
     qmg = qmg_gpu
     L = 64
