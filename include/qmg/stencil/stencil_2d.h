@@ -87,6 +87,9 @@ protected:
 
   std::complex<double> shift_backup, eo_shift_backup, dof_shift_backup;
   bool swap_dagger, swap_rbjacobi, swap_rbj_dagger;
+  // link-compressed apply (see enable_gamma5_hermitian_apply)
+  bool gamma5_hermitian;
+  complex<double>* herm_halo_ym;
 
   complex<double>* scratch_extra() { if (extra_cvector == 0) extra_cvector = allocate_vector<complex<double> >(lat->get_size_cv()); return extra_cvector; }
   complex<double>* scratch_eo() { if (eo_cvector == 0) eo_cvector = allocate_vector<complex<double> >(lat->get_size_cv()); return eo_cvector; }
@@ -113,6 +116,10 @@ public:
     d.eo_shift[0] = eo.real(); d.eo_shift[1] = eo.imag();
     d.dof_shift[0] = dof.real(); d.dof_shift[1] = dof.imag();
     d.halo_ym = 0; d.halo_yp = 0;
+    // the link-compressed apply is only valid for the ORIGINAL link set (not while a variant is swapped in)
+    const bool original = !swap_dagger && !swap_rbjacobi && !swap_rbj_dagger && (cl == clover || cl == 0) && hp == hopping && hp != 0;
+    d.gamma5_hermitian = (gamma5_hermitian && original) ? 1 : 0;
+    d.hop_halo_ym = d.gamma5_hermitian ? qmg_host::P(herm_halo_ym) : 0;
     return d;
   }
   qmg_stencil_desc describe() const { return describe(clover, hopping, shift, eo_shift, dof_shift); }
@@ -158,10 +165,43 @@ public:
     if (pieces & QMG_PIECE_CORNER) corner = allocate_vector<complex<double> >(lat->get_size_corner());
     shift_backup = shift; eo_shift_backup = eo_shift; dof_shift_backup = dof_shift;
     swap_dagger = swap_rbjacobi = swap_rbj_dagger = false;
+    gamma5_hermitian = false; herm_halo_ym = 0;
   }
+
+  // B200 extension (not in the reference): for an operator with D^dag = gamma5 D gamma5 -- Wilson2D and the Galerkin
+  // coarsenings built from chirality-doubled null vectors -- the stored backward blocks repeat the neighbours' forward
+  // blocks, hopping_{-mu}(x) = gamma5 hopping_{+mu}(x - mu)^dag gamma5.  After this call apply_M on the ORIGINAL link set
+  // reads 3 of the 5 blocks per site (clover, +x, +y) and takes the backward hops out of L2.  The relation is CHECKED on
+  // the stored blocks first (relative deviation <= tol, else nothing changes and false is returned); anything that edits
+  // the links (update_links, clear_stencils, writing through the public pointers) must be followed by a new call.
+  bool enable_gamma5_hermitian_apply(double tol = 1e-12)
+  {
+    gamma5_hermitian = false;
+    const int nc = lat->get_nc();
+    if (hopping == 0 || nc % 2 != 0 || nc > 32 || swap_dagger || swap_rbjacobi || swap_rbj_dagger) return false;
+    qmg_stencil_desc d = describe();
+    double dev[2] = {0.0, 0.0};
+    QMG_CHK(qmg_stencil_gamma5_deviation(&d, dev));
+    if (!(dev[1] > 0.0) || sqrt(dev[0] / dev[1]) > tol) return false;
+    if (qmg_comm_active())
+    {
+      // on a y-slab row -1 of the +y blocks lives on the lower rank: fetched once
+      const long row = (long)lat->get_dim_mu(0) * nc * nc;
+      if (herm_halo_ym == 0) herm_halo_ym = allocate_vector<complex<double> >(row);
+      complex<double>* unused = allocate_vector<complex<double> >(row);
+      QMG_CHK(qmg_halo_exchange(qmg_host::P(hopping + lat->get_size_cm()), lat->get_dim_mu(0), lat->get_dim_mu(1), nc * nc,
+                                qmg_host::P(herm_halo_ym), qmg_host::P(unused)));
+      deallocate_vector(&unused);
+    }
+    gamma5_hermitian = true;
+    return true;
+  }
+  void disable_gamma5_hermitian_apply() { gamma5_hermitian = false; }
+  bool uses_gamma5_hermitian_apply() const { return gamma5_hermitian; }
 
   virtual ~Stencil2D()
   {
+    if (herm_halo_ym != 0) deallocate_vector(&herm_halo_ym);
     complex<double>** all[] = { &clover, &hopping, &twolink, &corner, &extra_cvector, &eo_cvector,
                                 &dagger_clover, &dagger_hopping, &dagger_twolink, &dagger_corner,
                                 &rbjacobi_clover, &rbjacobi_hopping, &rbjacobi_twolink, &rbjacobi_corner, &rbjacobi_cinv,
@@ -176,12 +216,14 @@ public:
     complex<double>** der[] = { &dagger_clover, &dagger_hopping, &rbjacobi_clover, &rbjacobi_hopping, &rbjacobi_cinv };
     for (unsigned i = 0; i < sizeof(der) / sizeof(der[0]); i++) if (*der[i] != 0) deallocate_vector(der[i]);
     built_dagger = built_rbjacobi = false;
+    gamma5_hermitian = false;      // the links changed: the relation has to be re-checked
   }
 
   // stencil_2d.h:339-376 (including the reference's reset of built_rbjacobi where built_rbj_dagger is meant)
   void clear_stencils()
   {
     const long cm = lat->get_size_cm(), hp = lat->get_size_hopping(), cr = lat->get_size_corner();
+    gamma5_hermitian = false;
     if (clover != 0) zero_vector(clover, cm);
     if (hopping != 0) zero_vector(hopping, hp);
     if (twolink != 0) zero_vector(twolink, hp);

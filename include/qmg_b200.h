@@ -106,6 +106,14 @@ typedef struct qmg_stencil_desc
    * lattice (cshift/cshift_2d.h:101,114 "Becomes MPI"). */
   const qmg_cplx* halo_ym;     /* row below y=0   */
   const qmg_cplx* halo_yp;     /* row above y=Y-1 */
+  /* Opt-in traffic saving for operators with D^dag = gamma5 D gamma5 (Wilson, and its Galerkin coarsenings under
+   * chirality-preserving transfers): the stored backward blocks satisfy
+   *   hopping_{-mu}(x)[a][b] = s_a s_b conj(hopping_{+mu}(x - mu)[b][a]),  s = +1 / -1 on the top / bottom half of the dof,
+   * so the apply reads clover, +x and +y blocks only (3 of 5) and takes the backward hops from the neighbours' forward
+   * blocks.  The backward blocks stay stored (the layout contract is unchanged) but are NOT read: set this only after
+   * qmg_stencil_gamma5_deviation reports they obey the relation, and clear it when blocks are edited.  nc must be even. */
+  int gamma5_hermitian;
+  const qmg_cplx* hop_halo_ym; /* gamma5_hermitian on a y-slab: row -1 of hopping_{+y} (X*nc*nc, layout (parity, x/2, nc*nc)) */
 } qmg_stencil_desc;
 
 /* pieces bitmask (mirrors apply_M_clover/_eo/_oe/_shift, stencil_2d.h:694-909) */
@@ -130,6 +138,10 @@ int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
  * (tests/n11_wilson_test/wilson_test.cpp:96-104) calls in place of apply_stencil_2D_M. */
 int qmg_stencil_apply_host(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs_host, const qmg_cplx* rhs_host,
                            qmg_cplx* dev_lhs, qmg_cplx* dev_rhs, int rows_per_chunk);
+
+/* result2 = { sum |hopping_{-mu}(x) - s s conj(hopping_{+mu}(x-mu))^T|^2 over sites and mu, sum |hopping|^2 }: how far the
+ * stored backward blocks are from the gamma5-hermitian relation (see qmg_stencil_desc.gamma5_hermitian). */
+int qmg_stencil_gamma5_deviation(const qmg_stencil_desc* st, double* result2);
 
 /* Fused apply + reductions for the Krylov updates: out3 = { <lhs|rhs_dot>, |lhs|^2 } after lhs = A rhs.
  * (MR step: alpha = <Ar|r>/<Ar|Ar>, stateful_multigrid.h:860 via qlinalg minres.)

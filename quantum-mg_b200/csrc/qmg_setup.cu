@@ -3,6 +3,7 @@
 // None of these is on the per-iteration path; they are written to be
 // coalesced (one thread per OUTPUT element) and correct, not tuned.
 #include "qmg_comm.cuh"
+#include "qmg_launch.cuh"
 
 namespace qmg {
 
@@ -240,6 +241,35 @@ int qmg_build_dagger(int X, int Y, int nc, const qmg_cplx* clover_, const qmg_cp
     });
   }
   return rc;
+}
+
+// distance of the stored backward blocks from  H_{-mu}(x)[a][b] = s_a s_b conj(H_{+mu}(x - mu)[b][a])
+int qmg_stencil_gamma5_deviation(const qmg_stencil_desc* st, double* result2)
+{
+  QMG_REQUIRE_INIT();
+  if (st == nullptr || st->hopping == nullptr) return fail_msg("qmg_stencil_gamma5_deviation: needs a hopping term");
+  if (check_dims(st->X, st->Y, "qmg_stencil_gamma5_deviation: X and Y must be even and >= 2")) return 2;
+  const int nc = st->nc;
+  if (nc % 2) return fail_msg("qmg_stencil_gamma5_deviation: nc must be even");
+  const cd* hop = CCD(st->hopping);
+  Geom g; g.xh = st->X / 2; g.Y = st->Y; g.half = (unsigned)(st->X / 2) * st->Y;
+  const long V = (long)st->X * st->Y; const long nc2 = (long)nc * nc; const long per = V * nc2;
+  HaloTemp halo;
+  int rc = halo.fetch(hop + per, 0, 1, st->X, st->Y, (int)nc2); if (rc) return rc;     // rows -1 / Y of the +y blocks
+  const HaloRows hr = halo.rows(0, st->X, (int)nc2);
+  return launch_reduce<2>(per * 2, [=] __device__(long e, double (&acc)[2]) {
+    const int mu = 2 + (int)(e / per);                 // backward direction
+    const long r = e % per;
+    const long site = r / nc2; const int c = (int)(r - site * nc2);
+    const int row = c / nc, col = c % nc;
+    const cd back = hop[(long)mu * per + r];
+    const cd* fwd = (mu == 3) ? field_nbr(g, hop + per, hr, site, 3, (int)nc2) : hop + site_nbr(g, site, 2) * nc2;
+    const cd f = fwd[(long)col * nc + row];
+    const double sg = ((2 * row < nc) == (2 * col < nc)) ? 1.0 : -1.0;
+    const double dx = back.x - sg * f.x, dy = back.y + sg * f.y;
+    acc[0] += dx * dx + dy * dy;
+    acc[1] += back.x * back.x + back.y * back.y;
+  }, result2);
 }
 
 // cshift/cshift_2d.h:225: lhs(x) = rhs(x + dir), written on the parity OPPOSITE to each source parity in eo.

@@ -40,11 +40,19 @@ struct StencilKArgs
   int p_begin;          // first parity written
   int n_par;            // parities written; the parity is the FASTEST block index so that the even and the odd
                         // output rows y are in flight together and each input row is fetched from HBM once
+  int herm;             // gamma5-hermitian link set: backward hops are read from the neighbours' forward blocks
+  const cd* hop_ym;     // herm + y-slab: row -1 of the +y hopping blocks (from the lower rank), layout (parity, x/2, nc nc)
   int y_off, y_stride, y_cnt;   // rows of this launch: y = y_off + i * y_stride, i < y_cnt (all rows: 0, 1, Y; the two
                                 // slab-boundary rows of a sharded apply: 0, Y-1, 2; its interior: 1, 1, Y-2)
 };
 
-template <int NC, bool REDUCE>
+// HERM: for an operator with D^dag = gamma5 D gamma5 (Wilson and its Galerkin coarsenings with chirality-preserving
+// transfers) the backward block is determined by the forward block of the neighbour,
+//   H_{-mu}(x)[a][b] = s_a s_b conj( H_{+mu}(x - mu)[b][a] ),   s = +1 on the top half of the dof, -1 on the bottom half,
+// so only clover, H_{+x}, H_{+y} are fetched from HBM (3 of the 5 blocks); the neighbour's forward block was read by the
+// neighbouring site moments ago (same row for -x, previous row for -y) and comes out of L2.  The lane that owns element
+// (c1, c2) reads element (c2, c1) of that block: the same 16 nc^2 bytes per site, permuted inside the block.
+template <int NC, bool REDUCE, bool HERM>
 __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, double* partials, unsigned int* counter, double* result)
 {
   constexpr int LPS = NC * NC;   // lanes per site
@@ -84,10 +92,29 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
   const cd* s3 = (a.halo_ym != nullptr && y == 0) ? a.halo_ym + ((size_t)q * a.g.xh + k) * NC + c2 : in_q + ((size_t)ym1 * a.g.xh + k) * NC;
   const cd* hp = a.hop + site * LPS + c;
 
-  const cd H0 = m0 ? ld_stream(hp) : zero;
-  const cd H1 = m1 ? ld_stream(hp + a.size_cm) : zero;
-  const cd H2 = m2 ? ld_stream(hp + 2 * a.size_cm) : zero;
-  const cd H3 = m3 ? ld_stream(hp + 3 * a.size_cm) : zero;
+  cd H0, H1, H2, H3;
+  if (HERM)
+  {
+    // forward blocks stay cacheable (the neighbour in -mu direction re-reads them); the re-read is their last use
+    const int ct = c2 * NC + c1;
+    const cd* hb2 = a.hop + ((size_t)q * a.g.half + (size_t)y * a.g.xh + kxm) * LPS + ct;
+    const cd* hb3 = (a.hop_ym != nullptr && y == 0) ? a.hop_ym + ((size_t)q * a.g.xh + k) * LPS + ct
+                                                    : a.hop + a.size_cm + ((size_t)q * a.g.half + (size_t)ym1 * a.g.xh + k) * LPS + ct;
+    H0 = m0 ? ld_keep(hp) : zero;
+    H1 = m1 ? ld_keep(hp + a.size_cm) : zero;
+    const cd B2 = m2 ? ld_stream(hb2) : zero;
+    const cd B3 = m3 ? ld_stream(hb3) : zero;
+    const double sg = ((2 * c1 < NC) == (2 * c2 < NC)) ? 1.0 : -1.0;
+    H2 = cmake(sg * B2.x, -sg * B2.y);
+    H3 = cmake(sg * B3.x, -sg * B3.y);
+  }
+  else
+  {
+    H0 = m0 ? ld_stream(hp) : zero;
+    H1 = m1 ? ld_stream(hp + a.size_cm) : zero;
+    H2 = m2 ? ld_stream(hp + 2 * a.size_cm) : zero;
+    H3 = m3 ? ld_stream(hp + 3 * a.size_cm) : zero;
+  }
   const cd CL = has_cl ? ld_stream(a.clover + site * LPS + c) : zero;
   const cd V0 = m0 ? ld_keep(s0) : zero;
   const cd V1 = m1 ? ld_keep(s1) : zero;
@@ -235,6 +262,9 @@ static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   a.dotw = nullptr;
   a.halo_ym = reinterpret_cast<const cd*>(st->halo_ym);
   a.halo_yp = reinterpret_cast<const cd*>(st->halo_yp);
+  a.herm = (st->gamma5_hermitian != 0 && st->nc % 2 == 0 && st->nc <= 32) ? 1 : 0;
+  a.hop_ym = reinterpret_cast<const cd*>(st->hop_halo_ym);
+  if (a.herm && comm().active && a.hop_ym == nullptr) return fail_msg("qmg_stencil_apply: a gamma5-hermitian link set on a y-slab needs hop_halo_ym (row -1 of the +y blocks)");
   a.g.xh = st->X / 2; a.g.Y = st->Y; a.g.half = (unsigned)(st->X / 2) * st->Y;
   if (single_site) { a.g.xh = 1; a.g.Y = 1; a.g.half = 1; a.hop = nullptr; }
   a.size_cm = (long)st->X * st->Y * st->nc * st->nc;
@@ -280,10 +310,12 @@ static int launch_stencil(const StencilKArgs& a, int n_par, bool reduce)
   {
     double* partials = ensure_partials((size_t)grid.x * grid.y * grid.z * 3);
     if (partials == nullptr) return 1;
-    stencil_kernel<NC, true><<<grid, block, 0, r.stream>>>(a, partials, r.d_counter, r.d_result);
+    stencil_kernel<NC, true, false><<<grid, block, 0, r.stream>>>(a, partials, r.d_counter, r.d_result);
   }
+  else if (a.herm && NC > 1)
+    stencil_kernel<NC, false, (NC > 1)><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
   else
-    stencil_kernel<NC, false><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
+    stencil_kernel<NC, false, false><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
   QMG_LAUNCH_CHECK();
   return 0;
 }
@@ -301,6 +333,7 @@ static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduc
     default: break;
   }
   if (reduce) return fail_msg("qmg_stencil_apply_dot: fused reduction needs nc in {1,2,4,8,16,32}");
+  if (a.herm) return fail_msg("qmg_stencil_apply: the gamma5-hermitian apply needs nc in {2,4,8,16,32}");
   Runtime& r = rt();
   const long rows = (long)n_par * a.y_cnt * a.g.xh * nc;
   long blocks = (rows + 255) / 256, cap = (long)r.sm_count * 8;
@@ -501,6 +534,7 @@ int qmg_stencil_apply_dot(const qmg_stencil_desc* st, int pieces, qmg_cplx* lhs,
   int rc = build_args(st, pieces, 15, lhs, rhs, a, n_par);
   if (rc) return rc;
   a.dotw = reinterpret_cast<const cd*>(dot_with);
+  a.herm = 0;        // the fused-reduction flavour always reads the stored backward blocks
   if (needs_exchange(a))
   {
     // the fused reduction finishes in ONE launch (last-block tail), so the rows are fetched first, without overlap

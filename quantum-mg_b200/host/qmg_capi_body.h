@@ -196,6 +196,19 @@ int CAPI(stencil_built)(void* h_)
   return (s->built_dagger ? 1 : 0) | (s->built_rbjacobi ? 2 : 0) | (s->built_rbj_dagger ? 4 : 0);
 }
 
+// B200 extension: switch the link-compressed (gamma5-hermitian) apply on / off for this operator; returns 1 when active.
+// The reference build has no such mode: it answers 0 and changes nothing.
+int CAPI(stencil_gamma5_hermitian)(void* h_, int on)
+{
+#ifdef QMG_B200_HOST
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  if (!on) { s->disable_gamma5_hermitian_apply(); return 0; }
+  return s->enable_gamma5_hermitian_apply() ? 1 : 0;
+#else
+  (void)h_; (void)on; return 0;
+#endif
+}
+
 // lhs = M_type rhs through the function-pointer wrappers apply_stencil_2D_* (stencil_2d.h:2571-2716)
 void CAPI(stencil_apply)(void* h_, int type, capi_cd* lhs, const capi_cd* rhs)
 {
@@ -1000,6 +1013,26 @@ void CAPI(kcycle_solve)(void* h_, const capi_cd* b, capi_cd* x_out, int outer_ty
   if (x_out != 0) capi_get(x_out, xfull, n);
   h->mg->check_in(bd, 0); h->mg->check_in(x, 0); h->mg->check_in(bprep, 0); h->mg->check_in(xfull, 0);
 }
+// B200 extension: link-compressed applies on every level of the hierarchy whose stored blocks obey the gamma5-hermitian
+// relation (checked per level); returns the number of levels switched.  Reference build: 0.
+int CAPI(kcycle_gamma5_hermitian)(void* h_, int on)
+{
+#ifdef QMG_B200_HOST
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  int count = 0;
+  for (int l = 0; l < h->mg->get_num_levels(); l++)
+  {
+    Stencil2D* s = h->mg->get_stencil(l);
+    if (s == 0) continue;
+    if (!on) s->disable_gamma5_hermitian_apply();
+    else if (s->enable_gamma5_hermitian_apply()) count++;
+  }
+  return count;
+#else
+  (void)h_; (void)on; return 0;
+#endif
+}
+
 void* CAPI(kcycle_mg)(void* h_)
 {
   capi::KCycleH* h = (capi::KCycleH*)h_;

@@ -26,6 +26,7 @@
 #include "u1/u1_utils.h"
 #include "reductions/reductions.h"
 
+#define QMG_B200_HOST 1
 #define CAPI(name) qmgh_##name
 static inline std::complex<double>* capi_alloc(long n) { return allocate_vector<std::complex<double> >(n); }
 static inline void capi_free(std::complex<double>* p) { deallocate_vector(&p); }

@@ -25,7 +25,8 @@ class StencilDesc(C.Structure):
     _fields_ = [("X", C.c_int), ("Y", C.c_int), ("nc", C.c_int),
                 ("clover", C.c_void_p), ("hopping", C.c_void_p),
                 ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2),
-                ("halo_ym", C.c_void_p), ("halo_yp", C.c_void_p)]
+                ("halo_ym", C.c_void_p), ("halo_yp", C.c_void_p),
+                ("gamma5_hermitian", C.c_int), ("hop_halo_ym", C.c_void_p)]
 
 
 class TransferDesc(C.Structure):
@@ -97,7 +98,8 @@ def to_device(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.complex128)).cuda()
 
 
-def stencil_desc(X, Y, nc, clover=None, hopping=None, shift=0.0, eo_shift=0.0, dof_shift=0.0, halo_ym=None, halo_yp=None):
+def stencil_desc(X, Y, nc, clover=None, hopping=None, shift=0.0, eo_shift=0.0, dof_shift=0.0, halo_ym=None, halo_yp=None,
+                 gamma5_hermitian=False, hop_halo_ym=None):
     d = StencilDesc()
     d.X, d.Y, d.nc = int(X), int(Y), int(nc)
     d.clover = clover.data_ptr() if clover is not None else None
@@ -108,8 +110,17 @@ def stencil_desc(X, Y, nc, clover=None, hopping=None, shift=0.0, eo_shift=0.0, d
         getattr(d, name)[1] = v.imag
     d.halo_ym = halo_ym.data_ptr() if halo_ym is not None else None
     d.halo_yp = halo_yp.data_ptr() if halo_yp is not None else None
-    d._keep = (clover, hopping, halo_ym, halo_yp)
+    d.gamma5_hermitian = 1 if gamma5_hermitian else 0
+    d.hop_halo_ym = hop_halo_ym.data_ptr() if hop_halo_ym is not None else None
+    d._keep = (clover, hopping, halo_ym, halo_yp, hop_halo_ym)
     return d
+
+
+def stencil_gamma5_deviation(desc):
+    """Relative distance of the stored backward blocks from the gamma5-hermitian relation (0 for Wilson up to rounding)."""
+    out = (C.c_double * 2)()
+    check(lib().qmg_stencil_gamma5_deviation(C.byref(desc), out))
+    return (out[0] / out[1]) ** 0.5 if out[1] > 0 else 0.0
 
 
 def stencil_apply(desc, lhs, rhs, pieces=APPLY_ALL, dir_mask=15):

@@ -243,6 +243,9 @@ class Stencil:
         self.be.fn("stencil_chiral")(self.h, op, _c(a), _c(bb))
         return a, bb
 
+    def gamma5_hermitian(self, on=True):
+        return int(self.be.fn("stencil_gamma5_hermitian")(self.h, 1 if on else 0))
+
     def coarse_sigma(self, type, v):
         """CoarseOperator2D::apply_sigma(out, v, QMGSigmaTypeCoarse type in 6..9); out starts as zeros."""
         out = np.zeros(self.lat.size_cv, CD)
@@ -424,6 +427,10 @@ class KCycle:
         info = (C.c_double * 3)()
         self.be.fn("kcycle_pion")(self.h, x0, y0, max_iter, C.c_double(tol), restart, verbosity, _c(out), info)
         return out, dict(iters=int(info[0]), success=bool(info[1]), seconds=info[2])
+
+    def gamma5_hermitian(self, on=True):
+        """B200 extension: link-compressed applies on every level that passes the check; returns how many levels switched."""
+        return int(self.be.fn("kcycle_gamma5_hermitian")(self.h, 1 if on else 0))
 
     def time_precond(self, warm=1, reps=3):
         return self.be.fn("kcycle_time_precond")(self.h, warm, reps) / reps

@@ -494,3 +494,30 @@ def test_n22_adaptive_full_size(gpu):
     qmg.check(qmg.lib().qmg_trim())
     assert out["success"] and out["check_relres"] < 2e-10, (out, ops)
     assert out["iter"] <= 40, (out, ops)
+
+
+def test_kcycle_with_link_compressed_applies(ref, gpu):
+    """B200 extension on the whole hierarchy: every level of the Wilson K-cycle passes the gamma5-hermiticity check, the
+    solve takes the same iterations and lands on the same solution (and the oracle's iteration count); an operator whose
+    blocks were edited (the n18 mutation) is refused."""
+    L = 64
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L * 2, 5)
+    kr = capi.KCycle(ref, L, -0.03, g, n_refine=2, seed=5)
+    ir = kr.solve(b, tol=1e-10)
+    kr.free()
+    kc = capi.KCycle(gpu, L, -0.03, g, n_refine=2, seed=5)
+    x0, i0 = kc.solve(b, tol=1e-10, want_x=True)
+    assert kc.gamma5_hermitian(True) == 3
+    x1, i1 = kc.solve(b, tol=1e-10, want_x=True)
+    assert kc.gamma5_hermitian(False) == 0
+    x2, i2 = kc.solve(b, tol=1e-10, want_x=True)
+    kc.free()
+    assert i0["iter"] == i1["iter"] == i2["iter"] and abs(i1["iter"] - ir["iter"]) <= 1
+    assert latutil.rel_l2(x1, x0) < 1e-9 and np.array_equal(x2, x0)
+    lat = gpu.lattice(L, L, 2)
+    op = lat.wilson(-0.03, g)
+    assert op.gamma5_hermitian(True) == 1
+    op.add_to("hopping", 1e-3 * latutil.gaussian_cv(16 * L * L, 2))
+    assert op.gamma5_hermitian(True) == 0
+    op.free()

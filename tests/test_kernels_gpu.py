@@ -285,6 +285,57 @@ def test_blas(qmg_gpu):
     assert latutil.rel_l2(host(dyy), yy + sum(c * v for c, v in zip(coef, vs))) < 1e-14
 
 
+def test_gamma5_hermitian_apply(ref, qmg_gpu):
+    """Link-compressed apply (B200 extension): for Wilson, and for its Galerkin coarsening with chirally doubled null
+    vectors, the backward blocks equal gamma5 (forward block of the neighbour)^dag gamma5, the deviation check says so, and
+    the apply that reads only clover / +x / +y blocks reproduces the stored-block apply (and the oracle) to rounding.
+    A generic stencil fails the check."""
+    qmg = qmg_gpu
+    if qmg.comm_counters()["active"]:
+        pytest.skip("kernel-level descriptors here carry no hop_halo_ym; the slab flavour is covered by test_shard_gpu.py")
+    L = 32
+    lat, op, cl, hp, d = make_op(ref, qmg, "wilson", L)
+    assert qmg.stencil_gamma5_deviation(d) < 1e-15
+    dh = qmg.stencil_desc(L, L, 2, cl, hp, shift=-0.055, gamma5_hermitian=True)
+    rhs = latutil.gaussian_cv(lat.size_cv, 7)
+    want = op.apply(rhs, 0)
+    out, outh = qmg.cvec(lat.size_cv), qmg.cvec(lat.size_cv)
+    qmg.stencil_apply(d, out, dev(qmg, rhs))
+    qmg.stencil_apply(dh, outh, dev(qmg, rhs))
+    assert latutil.rel_l2(host(outh), want) < TOL and latutil.rel_l2(host(outh), host(out)) < 1e-15
+    # pieces and directions go through the same code
+    for pieces, dm in ((qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_EVEN_ROWS_ONLY, 15), (qmg.APPLY_HOP_TO_ODD | qmg.APPLY_ODD_ROWS_ONLY, 4),
+                       (qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_HOP_TO_ODD, 8), (qmg.APPLY_ALL | qmg.APPLY_ACCUMULATE, 15)):
+        a, b = qmg.cvec(lat.size_cv) + 1.0, qmg.cvec(lat.size_cv) + 1.0
+        qmg.stencil_apply(d, a, dev(qmg, rhs), pieces, dm)
+        qmg.stencil_apply(dh, b, dev(qmg, rhs), pieces, dm)
+        assert latutil.rel_l2(host(b), host(a)) < 1e-15, (pieces, dm)
+    # Galerkin coarsening with projection-doubled null vectors (what the K-cycle builds): nc = 8
+    Lc, ncc = 8, 8
+    half = [latutil.gaussian_cv(lat.size_cv, 40 + v) for v in range(ncc // 2)]
+    up = [v.copy() for v in half]
+    dn = [v.copy() for v in half]
+    for u_, d_ in zip(up, dn):
+        u_[1::2] = 0.0          # chirality "up" = spin component 0
+        d_[0::2] = 0.0
+    nv = [dev(qmg, v) for v in up + dn]
+    td = qmg.transfer_desc(L, L, 2, Lc, Lc, ncc)
+    qmg.block_orthonormalize(td, nv)
+    ccl, chp = qmg.coarse_build(td, d, nv)
+    dc = qmg.stencil_desc(Lc, Lc, ncc, ccl, chp, shift=-0.055)
+    assert qmg.stencil_gamma5_deviation(dc) < 1e-13
+    dch = qmg.stencil_desc(Lc, Lc, ncc, ccl, chp, shift=-0.055, gamma5_hermitian=True)
+    x = dev(qmg, latutil.gaussian_cv(Lc * Lc * ncc, 3))
+    y0, y1 = qmg.cvec(Lc * Lc * ncc), qmg.cvec(Lc * Lc * ncc)
+    qmg.stencil_apply(dc, y0, x)
+    qmg.stencil_apply(dch, y1, x)
+    assert latutil.rel_l2(host(y1), host(y0)) < 1e-13
+    # a generic stencil does not obey the relation
+    gcl, ghp = random_stencil(16, 4, 3)
+    assert qmg.stencil_gamma5_deviation(qmg.stencil_desc(16, 16, 4, dev(qmg, gcl), dev(qmg, ghp))) > 0.5
+    op.free()
+
+
 def test_fused_krylov_step(qmg_gpu):
     """qmg_step_xr_norm (alpha formed on the device between two kernels, one host wait) == qmg_dot_norm + host alpha +
     qmg_update_xr_norm, bit for bit, including the MR aliasing p == r."""

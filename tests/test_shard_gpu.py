@@ -109,6 +109,23 @@ def test_loopback_classes_and_kcycle(qmg_gpu, loop):
     assert np.array_equal(x0, x1)
 
 
+def test_loopback_link_compressed_kcycle(qmg_gpu, loop):
+    """gamma5-hermitian applies on a slab: row -1 of the +y blocks comes from the lower rank (here: itself)."""
+    be = capi.Backend("gpu")
+    L = 64
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L * 2, 9)
+
+    def fn():
+        kc = capi.KCycle(be, L, -0.03, g, n_refine=2, seed=5)
+        n = kc.gamma5_hermitian(True)
+        x, info = kc.solve(b, tol=1e-10, want_x=True)
+        kc.free()
+        return n, x, info["iter"]
+    (n0, x0, it0), (n1, x1, it1) = loop(fn)
+    assert n0 == n1 == 3 and it0 == it1 and np.array_equal(x0, x1)
+
+
 def test_two_rank_kcycle():
     import torch
     if torch.cuda.device_count() < 2:

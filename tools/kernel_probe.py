@@ -53,6 +53,10 @@ if not args.only or "stencil" in args.only:
         d = qmg.stencil_desc(L, L, nc, cl, hp, shift=0.1)
         sec = timed(lambda: qmg.stencil_apply(d, y, x))
         report("stencil apply nc=%d %dx%d" % (nc, L, L), sec, 16.0 * V * (nc * nc * 5 + 2 * nc))
+        if nc % 2 == 0:
+            dh = qmg.stencil_desc(L, L, nc, cl, hp, shift=0.1, gamma5_hermitian=True)
+            sec = timed(lambda: qmg.stencil_apply(dh, y, x))
+            report("  link-compressed (3 of 5 blocks) nc=%d %dx%d" % (nc, L, L), sec, 16.0 * V * (nc * nc * 5 + 2 * nc))
         d2 = qmg.stencil_desc(L, L, nc, None, hp)
         sec = timed(lambda: qmg.stencil_apply(d2, y, x, qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_HOP_TO_ODD | qmg.APPLY_IDENTITY_CLOVER))
         report("  rbjacobi (identity clover) nc=%d %dx%d" % (nc, L, L), sec, 16.0 * V * (nc * nc * 4 + 2 * nc))
