@@ -95,7 +95,7 @@ def cpu_reference_apply(L, reps, warm=1):
     return BYTES_PER_SITE * L * L / sec / 1e9, sec
 
 
-def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=None, world=1, rank=0, Yl=None):
+def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=None, world=1, rank=0, Yl=None, link_compressed=False):
     """3-level (n_refine=2) Wilson K-cycle as tests/n13_wilson_kcycle sets it up (4x4 blocks, 8 coarse dof, BiCGstab-6 null
     vectors, MR(2,2) smoothing, inner tol 0.2), gaussian right-hand side; returns the solve record.
     world > 1 (after qmg.comm_init): this rank owns an L x L y-slab of the L x (world L) lattice (weak scaling); the
@@ -129,6 +129,15 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
         first = out
         out = kc.solve(tol=tol, restart=restart, max_iter=100)
         out["first_solve_seconds"], out["first_solve_iter"] = first["seconds"], first["iter"]
+        if link_compressed:
+            # B200 extension: every level whose stored blocks pass the gamma5-hermiticity check applies its
+            # operator from clover / +x / +y blocks only (coarse levels: shared-memory tile kernel).  Same iteration counts.
+            stored = out
+            n_sw = kc.gamma5_hermitian(True)
+            out = kc.solve(tol=tol, restart=restart, max_iter=100)
+            out["first_solve_seconds"], out["first_solve_iter"] = first["seconds"], first["iter"]
+            out["link_compressed_levels"] = n_sw
+            out["seconds_stored_blocks"], out["iter_stored_blocks"] = stored["seconds"], stored["iter"]
     out["mass"] = mass
     out["levels"] = n_refine + 1
     out["L"] = L
@@ -275,7 +284,7 @@ def run_gpu(args):
         del clover, hopping, rhs, lhs, desc
         torch.cuda.empty_cache()
         kcycle = kcycle_run("gpu", args.kcycle_L, restart=args.kcycle_restart, world=world, rank=rank,
-                            Yl=(args.kcycle_L // world if strong else None))
+                            Yl=(args.kcycle_L // world if strong else None), link_compressed=not args.kcycle_stored_blocks)
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([kcycle["seconds"], kcycle["setup_seconds"], kcycle["precond_apply_s"]], device="cuda", dtype=torch.float64)
@@ -341,6 +350,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--L", type=int, default=8192, help="per-GPU lattice is L x L")
+    ap.add_argument("--kcycle-stored-blocks", action="store_true", dest="kcycle_stored_blocks",
+                    help="time the K-cycle with the stored-block applies only (default: also with the link-compressed applies, which is the reported time)")
     ap.add_argument("--scaling", choices=("weak", "strong"), default="weak",
                     help="weak: L x L per GPU (an L x N L lattice); strong: the L x L lattice cut into N slabs of L / N rows")
     ap.add_argument("--cpu-L", type=int, default=2048, dest="cpu_L")

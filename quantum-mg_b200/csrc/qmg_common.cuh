@@ -27,6 +27,7 @@ struct Runtime
   unsigned long long* h_flag = nullptr;   // pinned, mapped: number of reductions published so far
   unsigned long long red_seq = 0;   // host mirror of that number (reductions launched)
   int publish = 1;                  // 1: results arrive through h_result / h_flag; 0 (QMG_PUBLISH=0): copy + stream synchronise
+  int tile_kernel = 1;              // gamma5-hermitian applies use the shared-memory tile kernel (QMG_TILE=0: streaming HERM kernel)
   int publish_now = 1;              // publish, and the kernels hold the final (all-reduced) values themselves
   void** d_ptrs = nullptr;          // small device table for pointer arrays (multi-dot etc.)
   double* d_scalars = nullptr;      // small device table for coefficient arrays
@@ -79,8 +80,10 @@ int fail_msg(const char* msg);
 struct ProfScope
 {
   const char* name; double t0; bool on;
+  char tag[48];                      // optional detail appended to the name (e.g. the lattice an apply ran on)
   explicit ProfScope(const char* n);
   ~ProfScope();
+  void detail(int nc, int X, int Y);
 };
 #define QMG_REQUIRE_INIT() if (!qmg::rt().ready) { int r__ = qmg_init(-1); if (r__) return r__; } qmg::ProfScope prof_scope__(__func__)
 #define QMG_LAUNCH_CHECK() do { qmg::rt().launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return qmg::fail("kernel launch", e__, __FILE__, __LINE__); } while (0)

@@ -17,8 +17,11 @@ static std::map<std::string, ProfEntry>& prof_table() { static std::map<std::str
 static thread_local int prof_depth = 0;
 static double now_seconds() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
+void ProfScope::detail(int nc, int X, int Y) { if (on) snprintf(tag, sizeof(tag), " nc%d %dx%d", nc, X, Y); }
+
 ProfScope::ProfScope(const char* n) : name(n), t0(0.0), on(false)
 {
+  tag[0] = 0;
   if (!rt().profile || !rt().ready) return;
   on = (prof_depth++ == 0);          // nested entries (one C-ABI call using another) are charged to the outer one
   if (on) { cudaStreamSynchronize(rt().stream); t0 = now_seconds(); }
@@ -29,7 +32,7 @@ ProfScope::~ProfScope()
   prof_depth--;
   if (!on) return;
   cudaStreamSynchronize(rt().stream);
-  ProfEntry& e = prof_table()[name];
+  ProfEntry& e = prof_table()[std::string(name) + tag];
   e.seconds += now_seconds() - t0; e.calls++;
 }
 
@@ -191,6 +194,8 @@ int qmg_init(int device)
   QMG_CUDA(cudaDeviceSynchronize());
   const char* env = getenv("QMG_MANAGED");
   if (env != nullptr && env[0] == '1') r.managed = 1;
+  env = getenv("QMG_TILE");
+  r.tile_kernel = (env != nullptr && env[0] >= '0' && env[0] <= '9') ? (env[0] - '0') : 1;
   env = getenv("QMG_PROFILE");
   if (env != nullptr && env[0] == '1') r.profile = 1;
   r.ready = true;
@@ -299,10 +304,10 @@ double qmg_profile_report(void)
   double total = 0.0;
   for (auto& kv : prof_table()) { rows.push_back(std::make_pair(kv.second.seconds, kv.first)); total += kv.second.seconds; }
   std::sort(rows.begin(), rows.end());
-  printf("[QMG-PROFILE] %-28s %10s %12s %7s\n", "entry point", "calls", "seconds", "share");
+  printf("[QMG-PROFILE] %-40s %10s %12s %7s\n", "entry point", "calls", "seconds", "share");
   for (size_t i = rows.size(); i-- > 0;)
-    printf("[QMG-PROFILE] %-28s %10ld %12.6f %6.1f%%\n", rows[i].second.c_str(), prof_table()[rows[i].second].calls, rows[i].first, 100.0 * rows[i].first / (total > 0 ? total : 1.0));
-  printf("[QMG-PROFILE] %-28s %10s %12.6f\n", "total", "", total);
+    printf("[QMG-PROFILE] %-40s %10ld %12.6f %6.1f%%\n", rows[i].second.c_str(), prof_table()[rows[i].second].calls, rows[i].first, 100.0 * rows[i].first / (total > 0 ? total : 1.0));
+  printf("[QMG-PROFILE] %-40s %10s %12.6f\n", "total", "", total);
   fflush(stdout);
   return total;
 }

@@ -205,6 +205,194 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
   }
 }
 
+// ---- tile kernel for gamma5-hermitian link sets --------------------------------------------------------------------
+// The streaming kernel above sits on the L2 -> SM fabric (every one of the 5 blocks of a site crosses it once, and with
+// HERM the backward blocks cross it a second time out of L2).  Here a CTA owns a patch of TY rows x 2 TK columns, stages
+// the FORWARD blocks (+x, +y) of its sites -- plus the one column to the left and the one row below that its backward hops
+// need -- and the input spinors of the patch and its 1-site ring in shared memory with cp.async, and every lane then
+// takes its forward elements [c1][c2] and its backward elements s s conj([c2][c1]) from shared memory: per site
+// 1 (clover) + 2 (1 + halo share) blocks cross the fabric instead of 5, and every spinor once per CTA instead of once
+// per lane group.  Block rows are padded to NC + 1 elements so that both the row-wise and the transposed reads of a
+// quarter warp fall into distinct banks.  Same lane <-> matrix element mapping and the same shuffle tree as above, so the
+// sums are formed in the same order.
+template <int NC, int TK, int TY> struct TileDims
+{
+  static const int S = TY * 2 * TK;                               // sites of the patch
+  static const int THREADS = (S * NC >= 256) ? 256 : S * NC;      // one thread per (site, column), at most 256 per pass
+  static const int PASSES = S * NC / THREADS;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem_src) : "memory");
+}
+
+template <int NC, int TK, int TY>
+__global__ void __launch_bounds__(TileDims<NC, TK, TY>::THREADS) stencil_tile_kernel(const StencilKArgs a)
+{
+  constexpr int S = TileDims<NC, TK, TY>::S;
+  constexpr int NT = TileDims<NC, TK, TY>::THREADS;
+  constexpr int LPS = NC * NC;
+  constexpr int RS = NC + 1;                // padded row stride of a staged block
+  constexpr int BS = NC * RS;               // elements per staged block
+  constexpr int NHX = S + TY, NHY = S + 2 * TK;
+  constexpr int VK = TK + 2;
+  extern __shared__ cd tile_smem[];
+  cd* sHx = tile_smem;                      // [NHX][NC][RS]
+  cd* sHy = sHx + (size_t)NHX * BS;         // [NHY][NC][RS]
+  cd* sV = sHy + (size_t)NHY * BS;          // [TY + 2][2][VK][NC]
+  const int tid = threadIdx.x;
+  const int xh = a.g.xh, Y = a.g.Y;
+  const int k0 = blockIdx.x * TK, y0 = a.y_off + blockIdx.y * TY;
+  const size_t half = a.g.half;
+  const cd* hopx = a.hop;
+  const cd* hopy = a.hop + a.size_cm;
+
+  // ---- stage forward blocks and spinors
+  for (int e = tid; e < NHX * LPS; e += NT)
+  {
+    const int slot = e / LPS, c = e - slot * LPS;
+    int ty, p, k;
+    if (slot < S) { ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; p = r / TK; k = k0 + (r - p * TK); }
+    else { ty = slot - S; p = 1 - ((y0 + ty) & 1); k = (k0 == 0) ? xh - 1 : k0 - 1; }      // left neighbour of the sft = 0 site of this row
+    const size_t site = (size_t)p * half + (size_t)(y0 + ty) * xh + k;
+    cp_async16(sHx + (size_t)slot * BS + (c / NC) * RS + (c % NC), hopx + site * LPS + c);
+  }
+  for (int e = tid; e < NHY * LPS; e += NT)
+  {
+    const int slot = e / LPS, c = e - slot * LPS;
+    int y, p, k;
+    if (slot < S) { const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; p = r / TK; k = k0 + (r - p * TK); y = y0 + ty; }
+    else { const int r = slot - S; p = r / TK; k = k0 + (r - p * TK); y = (y0 == 0) ? Y - 1 : y0 - 1; }
+    const size_t site = (size_t)p * half + (size_t)y * xh + k;
+    cp_async16(sHy + (size_t)slot * BS + (c / NC) * RS + (c % NC), hopy + site * LPS + c);
+  }
+  for (int e = tid; e < (TY + 2) * 2 * VK * NC; e += NT)
+  {
+    const int c = e % NC; int r = e / NC;
+    const int kk = r % VK; r /= VK;
+    const int p = r & 1, ry = r >> 1;
+    int y = y0 + ry - 1; y = (y < 0) ? Y - 1 : ((y >= Y) ? 0 : y);
+    int k = k0 + kk - 1; k = (k < 0) ? xh - 1 : ((k >= xh) ? 0 : k);
+    cp_async16(sV + e, a.in + ((size_t)p * half + (size_t)y * xh + k) * NC + c);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // ---- compute: one thread per (site, column c2).  It holds in(neighbour)[c2] in a register and walks down column c2 of
+  // each block, accumulating all NC output rows; the NC threads of a site then exchange partial sums with a transposing
+  // butterfly (NC - 1 complex shuffles) that leaves row t on thread t.  Per block a thread reads NC matrix elements and
+  // ONE spinor element from shared memory (the element-per-lane mapping of the streaming kernel would read one of each
+  // per element: twice the shared-memory traffic, which is what bounds this kernel).
+  constexpr int PASSES = TileDims<NC, TK, TY>::PASSES;
+  const int c2 = tid % NC;
+  const cd zero = cmake(0.0, 0.0);
+  cd CLc[PASSES][NC];                       // clover column c2, straight from global memory while the tile is in flight
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ps++)
+  {
+    const int slot = ps * (NT / NC) + tid / NC;
+    const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; const int p = r / TK, tk = r - p * TK;
+    const size_t site = (size_t)p * half + (size_t)(y0 + ty) * xh + (k0 + tk);
+#pragma unroll
+    for (int c1 = 0; c1 < NC; c1++) CLc[ps][c1] = (a.clover != nullptr) ? ld_stream(a.clover + site * LPS + c1 * NC + c2) : zero;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const bool top = (2 * c2 < NC);
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ps++)
+  {
+    const int slot = ps * (NT / NC) + tid / NC;
+    const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; const int p = r / TK, tk = r - p * TK;
+    const int q = 1 - p, y = y0 + ty, sft = (y + p) & 1;
+    const int nx = sft ? (ty * 2 + q) * TK + tk : (tk > 0 ? (ty * 2 + q) * TK + tk - 1 : S + ty);
+    const int ny = (ty > 0) ? ((ty - 1) * 2 + q) * TK + tk : S + q * TK + tk;
+    const cd* vrow = sV + ((size_t)((ty + 1) * 2) * VK) * NC + c2;       // row ty of the patch, parity 0, kk = 0
+    const cd VC = vrow[((size_t)p * VK + tk + 1) * NC];
+    const cd V0 = vrow[((size_t)q * VK + tk + 1 + sft) * NC];
+    const cd V2 = vrow[((size_t)q * VK + tk + sft) * NC];
+    const cd V1 = vrow[((size_t)(2 + q) * VK + tk + 1) * NC];
+    const cd V3 = vrow[((ptrdiff_t)q * VK + tk + 1 - 2 * VK) * NC];
+    const cd* hx = sHx + (size_t)slot * BS + c2;          // column c2: element [c1][c2] at + c1 * RS
+    const cd* hy = sHy + (size_t)slot * BS + c2;
+    const cd* bx = sHx + (size_t)nx * BS + c2 * RS;       // row c2 of the neighbour's block: element [c2][c1] at + c1
+    const cd* by = sHy + (size_t)ny * BS + c2 * RS;
+    cd acc[NC];
+#pragma unroll
+    for (int c1 = 0; c1 < NC; c1++)
+    {
+      cd t = zero;
+      cfma(t, CLc[ps][c1], VC);
+      cfma(t, hx[c1 * RS], V0);
+      cfma(t, hy[c1 * RS], V1);
+      // backward blocks: s_{c1} s_{c2} conj(B[c2][c1])
+      const double sg = ((2 * c1 < NC) == top) ? 1.0 : -1.0;
+      const cd b2 = bx[c1], b3 = by[c1];
+      cfma(t, cmake(sg * b2.x, -sg * b2.y), V2);
+      cfma(t, cmake(sg * b3.x, -sg * b3.y), V3);
+      acc[c1] = t;
+    }
+    if (a.use_diag)
+    {
+      // diag shift on row c2 of this thread's column: a predicated add keeps acc[] in registers (no dynamic indexing)
+      const cd dg = a.diag[p][top ? 0 : 1];
+#pragma unroll
+      for (int c1 = 0; c1 < NC; c1++) if (c1 == c2) cfma(acc[c1], dg, VC);
+    }
+    // transposing butterfly over the NC threads of the site: thread t ends up with row t
+#pragma unroll
+    for (int off = NC / 2; off > 0; off >>= 1)
+    {
+      const bool upper = (c2 & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; i++)
+      {
+        const cd send = upper ? acc[i] : acc[i + off];
+        const cd keep = upper ? acc[i + off] : acc[i];
+        acc[i] = cadd(keep, shfl_xor_c(send, off));
+      }
+    }
+    const size_t site = (size_t)p * half + (size_t)y * xh + (k0 + tk);
+    cd res = acc[0];
+    if (a.accumulate) res = cadd(res, a.out[site * NC + c2]);
+    a.out[site * NC + c2] = res;
+  }
+}
+
+template <int NC, int TK, int TY> static size_t tile_smem_bytes()
+{
+  constexpr int S = TileDims<NC, TK, TY>::S;
+  return sizeof(cd) * ((size_t)(S + TY + S + 2 * TK) * NC * (NC + 1) + (size_t)(TY + 2) * 2 * (TK + 2) * NC);
+}
+
+// A full (all pieces, both parities, all directions) out-of-place or accumulating apply of a gamma5-hermitian link set on
+// a lattice whose dimensions the patch divides ...
+template <int TK, int TY> static bool tile_shape_fits(const StencilKArgs& a, int n_par)
+{
+  return a.herm && n_par == 2 && a.hop != nullptr && a.hop_to[0] && a.hop_to[1] && a.dir_mask == 15 &&
+         a.g.xh % TK == 0 && a.g.Y % TY == 0 && (const void*)a.in != (const void*)a.out;
+}
+// ... over ALL rows of a periodic lattice (rows that wrap read their neighbours inside this lattice)
+template <int TK, int TY> static bool tile_applicable(const StencilKArgs& a, int n_par)
+{
+  return tile_shape_fits<TK, TY>(a, n_par) && a.halo_ym == nullptr && a.halo_yp == nullptr && a.hop_ym == nullptr &&
+         a.y_off == 0 && a.y_stride == 1 && a.y_cnt == a.g.Y;
+}
+
+template <int NC, int TK, int TY> static int launch_tile(const StencilKArgs& a)
+{
+  static bool configured = false;
+  const size_t smem = tile_smem_bytes<NC, TK, TY>();
+  if (!configured) { QMG_CUDA(cudaFuncSetAttribute(stencil_tile_kernel<NC, TK, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+  dim3 grid(a.g.xh / TK, a.y_cnt / TY, 1);       // rows [y_off, y_off + y_cnt): whole patches
+  if (grid.y > 65535) return fail_msg("qmg_stencil_apply: Y too large for the launch grid");
+  stencil_tile_kernel<NC, TK, TY><<<grid, TileDims<NC, TK, TY>::THREADS, smem, rt().stream>>>(a);
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+
 // Any nc (DWF Ls = 6, 12, 24, 32 give nc = 12, 24, 48, 64): one thread per
 // (site, row), looping over the columns.  Slow path, same arithmetic.
 __global__ void __launch_bounds__(256) stencil_kernel_generic(const StencilKArgs a, int nc, int n_par)
@@ -322,6 +510,14 @@ static int launch_stencil(const StencilKArgs& a, int n_par, bool reduce)
 
 static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduce)
 {
+  if (!reduce && a.herm && rt().tile_kernel)
+  {
+    // patch shapes: nc = 8: 8 x 4 sites (97 KB of shared memory, two CTAs per SM; 8x2, 4x4, 16x2 and 4x2 patches measured
+    // within 10 % of it, profiles/r02f_tile_shapes.txt); nc = 4: 16 x 8.  nc = 2 blocks are too small to win (the
+    // column-wise clover loads waste half of every sector): the fine level keeps the streaming kernel.
+    if (nc == 8 && tile_applicable<4, 4>(a, n_par)) return launch_tile<8, 4, 4>(a);
+    if (nc == 4 && tile_applicable<8, 8>(a, n_par)) return launch_tile<4, 8, 8>(a);
+  }
   switch (nc)
   {
     case 1: return launch_stencil<1>(a, n_par, reduce);
@@ -363,6 +559,21 @@ static int apply_sharded(StencilKArgs& a, int nc, int n_par)
   HaloRows rows;
   int rc = halo_exchange_begin(a.in, 2 * a.g.xh, a.g.Y, nc, exchange_parities(a, n_par), &rows);
   if (rc) return rc;
+  // gamma5-hermitian link set: the rows that touch no other slab go through the shared-memory tile kernel, one band of
+  // patch height at either end through the streaming kernel once the neighbours' rows have arrived
+  constexpr int TY8 = 4, TK8 = 4;
+  if (nc == 8 && rt().tile_kernel && tile_shape_fits<TK8, TY8>(a, n_par) && a.g.Y >= 3 * TY8)
+  {
+    StencilKArgs in = a;
+    in.hop_ym = nullptr; in.y_off = TY8; in.y_stride = 1; in.y_cnt = a.g.Y - 2 * TY8;
+    rc = launch_tile<8, TK8, TY8>(in); if (rc) return rc;
+    rc = halo_exchange_end(); if (rc) return rc;
+    a.halo_ym = rows.ym; a.halo_yp = rows.yp;
+    a.y_off = 0; a.y_stride = 1; a.y_cnt = TY8;
+    rc = dispatch_stencil(a, nc, n_par, false); if (rc) return rc;
+    a.y_off = a.g.Y - TY8;
+    return dispatch_stencil(a, nc, n_par, false);
+  }
   if (a.g.Y > 2)
   {
     a.y_off = 1; a.y_stride = 1; a.y_cnt = a.g.Y - 2;
@@ -520,6 +731,7 @@ int qmg_stencil_apply_host(const qmg_stencil_desc* st, int pieces, int dir_mask,
 int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs)
 {
   QMG_REQUIRE_INIT();
+  if (st != nullptr) prof_scope__.detail(st->nc, st->X, st->Y);
   StencilKArgs a; int n_par;
   int rc = build_args(st, pieces, dir_mask, lhs, rhs, a, n_par);
   if (rc) return rc;

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--levels", type=int, default=3)
     ap.add_argument("--mass", type=float, default=-0.03)
     ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--hermitian", action="store_true", help="link-compressed (gamma5-hermitian) applies on every level")
     a = ap.parse_args()
     os.environ["QMG_DEVICE_RNG"] = "1"
     import torch
@@ -41,6 +42,8 @@ def main():
     kw = dict(n_refine=a.levels - 1, block=4, coarse_dof=8, seed=5)
 
     kc = capi.KCycle(be, L, a.mass, g, **kw)
+    if a.hermitian:
+        assert kc.gamma5_hermitian(True) == a.levels
     x_one, info_one = kc.solve(b, tol=a.tol, want_x=True)
     ops_one = [kc.tracker(l)["total"] for l in range(a.levels)]
     warm_one = kc.solve(b, tol=a.tol)["seconds"]          # second solve: warm allocator
@@ -52,6 +55,8 @@ def main():
     V = L * L
     g_loc = np.concatenate([sl.take(g[:V], 1), sl.take(g[V:], 1)])
     kc = capi.KCycle(be, L, a.mass, g_loc, Y=sl.Yl, **kw)
+    if a.hermitian:
+        assert kc.gamma5_hermitian(True) == a.levels
     x_loc, info = kc.solve(sl.take(b, 2), tol=a.tol, want_x=True)
     ops = [kc.tracker(l)["total"] for l in range(a.levels)]
     warm = kc.solve(sl.take(b, 2), tol=a.tol)["seconds"]

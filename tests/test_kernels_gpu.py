@@ -302,14 +302,14 @@ def test_gamma5_hermitian_apply(ref, qmg_gpu):
     out, outh = qmg.cvec(lat.size_cv), qmg.cvec(lat.size_cv)
     qmg.stencil_apply(d, out, dev(qmg, rhs))
     qmg.stencil_apply(dh, outh, dev(qmg, rhs))
-    assert latutil.rel_l2(host(outh), want) < TOL and latutil.rel_l2(host(outh), host(out)) < 1e-15
+    assert latutil.rel_l2(host(outh), want) < TOL and latutil.rel_l2(host(outh), host(out)) < 1e-14
     # pieces and directions go through the same code
     for pieces, dm in ((qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_EVEN_ROWS_ONLY, 15), (qmg.APPLY_HOP_TO_ODD | qmg.APPLY_ODD_ROWS_ONLY, 4),
                        (qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_HOP_TO_ODD, 8), (qmg.APPLY_ALL | qmg.APPLY_ACCUMULATE, 15)):
         a, b = qmg.cvec(lat.size_cv) + 1.0, qmg.cvec(lat.size_cv) + 1.0
         qmg.stencil_apply(d, a, dev(qmg, rhs), pieces, dm)
         qmg.stencil_apply(dh, b, dev(qmg, rhs), pieces, dm)
-        assert latutil.rel_l2(host(b), host(a)) < 1e-15, (pieces, dm)
+        assert latutil.rel_l2(host(b), host(a)) < 1e-14, (pieces, dm)
     # Galerkin coarsening with projection-doubled null vectors (what the K-cycle builds): nc = 8
     Lc, ncc = 8, 8
     half = [latutil.gaussian_cv(lat.size_cv, 40 + v) for v in range(ncc // 2)]

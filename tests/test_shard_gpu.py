@@ -123,7 +123,8 @@ def test_loopback_link_compressed_kcycle(qmg_gpu, loop):
         kc.free()
         return n, x, info["iter"]
     (n0, x0, it0), (n1, x1, it1) = loop(fn)
-    assert n0 == n1 == 3 and it0 == it1 and np.array_equal(x0, x1)
+    # (periodic: shared-memory tile kernel; slab: streaming kernel with the halo row -- different summation trees)
+    assert n0 == n1 == 3 and it0 == it1 and latutil.rel_l2(x1, x0) < 1e-9
 
 
 def test_two_rank_kcycle():
