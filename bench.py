@@ -261,6 +261,14 @@ def run_gpu(args):
     qmg.check(lib.qmg_malloc_host(C.byref(hout), C.c_size_t(16 * n)))
     qmg.check(lib.qmg_memcpy_d2h(hin, qmg.ptr(rhs), C.c_size_t(16 * n)))
     qmg.stencil_apply_host(desc, hout, hin, dev_lhs=lhs, dev_rhs=rhs)      # warm-up (streams, events)
+    # what this box's PCIe gives for the same buffers, one direction at a time (context for the e2e number, not part of it)
+    barrier()
+    t0 = time.perf_counter()
+    qmg.check(lib.qmg_memcpy_h2d(qmg.ptr(rhs), hin, C.c_size_t(16 * n)))
+    t1 = time.perf_counter()
+    qmg.check(lib.qmg_memcpy_d2h(hout, qmg.ptr(lhs), C.c_size_t(16 * n)))
+    t2 = time.perf_counter()
+    pcie = {"h2d_GBps": 16 * n / (t1 - t0) / 1e9, "d2h_GBps": 16 * n / (t2 - t1) / 1e9}
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -318,7 +326,8 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(X, Y),
                          "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0, "kernel": "qmg::stencil_kernel<2>"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps},
+            "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps,
+                    "pcie_one_direction_at_a_time": pcie},
             "gpu_launches": launches,
             "clocks": clocks,
             "kcycle": kcycle,
