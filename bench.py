@@ -119,6 +119,10 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
             cfg = "synthetic non-compact U(1), beta 6.0, seed %d + rank, one stackable slab per rank (tests/latutil.py synthetic_phases)" % seed
     else:
         cfg = "caller-supplied"
+    if world > 1:
+        # the ranks finish drawing their slabs at different times: meet on the host before the first device-side collective
+        import torch.distributed as dist
+        dist.barrier()
     t0 = time.perf_counter()
     kc = capi.KCycle(be, L, mass, gauge, n_refine=n_refine, seed=seed, inner_iters=100, coarsest_iters=400, Y=Yl)
     del gauge

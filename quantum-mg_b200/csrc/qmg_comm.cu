@@ -113,7 +113,8 @@ int ring_exchange(const cd* lo, const cd* hi, cd* ym, cd* yp, size_t first, size
 // Two slots alternate: a neighbour can only be one exchange ahead (it waits for my flag of every exchange).
 __global__ void __launch_bounds__(256) halo_p2p_kernel(const cd* __restrict__ field, int rowlen, long half_elems, int Y, int parity_mask,
                                                        cd* up_ym, cd* down_yp, unsigned long long* up_flag, unsigned long long* down_flag,
-                                                       const unsigned long long* my_flags, unsigned long long seq, unsigned int* counter, int rank)
+                                                       const unsigned long long* my_flags, unsigned long long seq, unsigned int* counter, int rank,
+                                                       long long watchdog_cycles)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 2 * rowlen)
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(256) halo_p2p_kernel(const cd* __restrict__ fi
   {
     const long long t0 = clock64();
     while (ld_sys_u64(my_flags + threadIdx.x) < seq)
-      if (clock64() - t0 > 60000000000LL) { printf("[QMG-ERROR]: rank %d waited 30 s for a halo row (exchange %llu, side %d)\n", rank, seq, (int)threadIdx.x); __trap(); }
+      if (clock64() - t0 > watchdog_cycles) { printf("[QMG-ERROR]: rank %d gave up waiting for a halo row (exchange %llu, side %d)\n", rank, seq, (int)threadIdx.x); __trap(); }
   }
 }
 
@@ -168,7 +169,7 @@ int exchange_on(cudaStream_t s, const cd* field, int X, int Y, int dof, int pari
     {
       halo_p2p_kernel<<<(2 * rowlen + 255) / 256, 256, 0, s>>>(field, rowlen, (long)rowlen * Y, Y, parity_mask,
           halo_slot(c.mail[up], slot, 0), halo_slot(c.mail[down], slot, 1), halo_flags(c.mail[up], slot) + 0, halo_flags(c.mail[down], slot) + 1,
-          halo_flags(c.mail[c.rank], slot), seq, c.d_halo_counter, c.rank);
+          halo_flags(c.mail[c.rank], slot), seq, c.d_halo_counter, c.rank, p2p_watchdog_cycles());
       QMG_LAUNCH_CHECK();
       c.halo_exchanges++; c.p2p_halo_exchanges++;
       if (out_ym != nullptr) QMG_CUDA(cudaMemcpyAsync(out_ym + first, my_ym + first, sizeof(cd) * count, cudaMemcpyDeviceToDevice, s));

@@ -30,6 +30,7 @@ struct Comm
   double* mail[kMaxRanks] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 };
 int upload_red_state(int nranks, int rank, int p2p, double* const* mail);   // qmg_runtime.cu
+long long p2p_watchdog_cycles();                                            // qmg_runtime.cu
 Comm& comm();
 
 // rows -1 and Y of a field as received from the ring neighbours, layout (parity, x/2, dof)

@@ -59,6 +59,7 @@ struct RedState
   double* mail[kMaxRanks];          // mail[r]: rank r's mailbox (own: local pointer; others: IPC-mapped peer memory)
   double* host_out;
   unsigned long long* host_flag;
+  long long watchdog_cycles;        // how long a last block waits for its peers before it gives up (QMG_P2P_TIMEOUT_S, default 120 s)
 };
 // mailbox layout: data[2][kMaxRanks][kMailWidth] doubles, then flags[2][kMaxRanks] (unsigned long long)
 constexpr size_t kMailDataDoubles = (size_t)2 * kMaxRanks * kMailWidth;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void publish_result(unsigned int* counter, double* re
       const unsigned long long* my_flags = reinterpret_cast<const unsigned long long*>(st->mail[me] + kMailDataDoubles);
       const long long t0 = clock64();
       while (ld_sys_u64(my_flags + buf * kMaxRanks + tid) < seq)
-        if (clock64() - t0 > 60000000000LL) { printf("[QMG-ERROR]: rank %d waited 30 s for rank %d in reduction %llu\n", me, tid, seq); __trap(); }
+        if (clock64() - t0 > st->watchdog_cycles) { printf("[QMG-ERROR]: rank %d gave up waiting for rank %d in reduction %llu\n", me, tid, seq); __trap(); }
     }
     __syncthreads();
     for (int w = tid; w < W; w += nthreads)

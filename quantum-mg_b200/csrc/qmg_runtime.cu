@@ -108,6 +108,16 @@ int fetch_result(double* host_out, int count, int op_max)
   return 0;
 }
 
+// Ranks can be far apart in HOST time when they meet in a collective (one still generating its gauge field, say), so the
+// in-kernel waits are generous; a peer that died still ends the wait with an error instead of a hang.
+long long p2p_watchdog_cycles()
+{
+  double seconds = 120.0;
+  const char* e = getenv("QMG_P2P_TIMEOUT_S");
+  if (e != nullptr && atof(e) > 0.0) seconds = atof(e);
+  return (long long)(seconds * 2.0e9);
+}
+
 int skip_result(double* result_dev, int count)
 {
   rt().red_seq++;
@@ -127,6 +137,7 @@ int upload_red_state(int nranks, int rank, int p2p, double* const* mail)
   st.nranks = nranks; st.rank = rank; st.p2p = p2p; st.publish = r.publish_now;
   for (int i = 0; i < kMaxRanks; i++) st.mail[i] = (mail != nullptr && i < nranks) ? mail[i] : nullptr;
   st.host_out = r.h_result; st.host_flag = r.h_flag;
+  st.watchdog_cycles = p2p_watchdog_cycles();
   QMG_CUDA(cudaMemcpy(r.d_counter, &st, sizeof(st), cudaMemcpyHostToDevice));
   return 0;
 }

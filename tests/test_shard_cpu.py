@@ -136,3 +136,21 @@ def test_stackable_synthetic_slabs_form_one_configuration():
     assert abs(seams.std() - 1 / np.sqrt(beta)) < 0.08
     g = latutil.phases_to_gauge(ph.ravel(), X, Yl * N)
     assert abs(latutil.average_plaquette(g, X, Yl * N) - np.exp(-0.5 / beta)) < 0.01
+
+
+def test_global_index_rng_mapping_matches_slab_layout():
+    """qmg_gaussian on a y-slab keys its counter by  p * (N half) + rank * half + i'  (csrc/qmg_blas.cu): that must be the
+    position of local element i = p * half + i' in the global even-odd field, i.e. exactly what shard.Slab.take selects --
+    so N slabs together draw the vector one GPU draws for the whole lattice."""
+    X, Y, N = 8, 16, 4
+    for dof in (1, 2, 8):
+        glob = np.arange(X * Y * dof)
+        for rank in range(N):
+            sl = shard.Slab(X, Y, N, rank)
+            local = sl.take(glob, dof)
+            n = local.size
+            half = n // 2
+            i = np.arange(n)
+            p = (i >= half).astype(np.int64)
+            gi = p * N * half + rank * half + (i - p * half)
+            assert np.array_equal(local, gi)
