@@ -521,3 +521,45 @@ def test_kcycle_with_link_compressed_applies(ref, gpu):
     op.add_to("hopping", 1e-3 * latutil.gaussian_cv(16 * L * L, 2))
     assert op.gamma5_hermitian(True) == 0
     op.free()
+
+
+def test_kcycle_shapes_the_reference_uses(ref, gpu):
+    """Hierarchy shapes beyond the square 3-level case: four levels down to a SINGLE coarsest site (n16's 64 -> 16 -> 4 -> 1,
+    wilson_kcycle_heatbath.cpp:116: the coarsest operator is clover-only and its lattice has volume 1) and a non-square
+    64 x 32 lattice (what a y-slab is).  Iteration counts +-1, per-level operator counts within 3 %, same solution."""
+    import shard
+    L = 64
+    g = latutil.load_gauge(L)
+    V = L * L
+    sl = shard.Slab(L, L, 2, 0)
+    cases = [("4 levels to one site", dict(n_refine=3), g, L, latutil.gaussian_cv(V * 2, 5)),
+             ("64 x 32", dict(n_refine=2, Y=32), np.concatenate([sl.take(g[:V], 1), sl.take(g[V:], 1)]), 32, latutil.gaussian_cv(L * 32 * 2, 6))]
+    for name, kw, gauge, Y, b in cases:
+        res = {}
+        for bn, be in (("ref", ref), ("gpu", gpu)):
+            kc = capi.KCycle(be, L, -0.01, gauge, block=4, coarse_dof=8, seed=3, **kw)
+            x, info = kc.solve(b, tol=1e-10, want_x=True)
+            res[bn] = (x, info, [kc.tracker(l)["total"] for l in range(kw["n_refine"] + 1)])
+            kc.free()
+        (xr, ir, opr), (xg, ig, opg) = res["ref"], res["gpu"]
+        assert ir["success"] and ig["success"], name
+        assert abs(ir["iter"] - ig["iter"]) <= 1, name
+        assert all(abs(p - q) <= 0.03 * q + 2 for p, q in zip(opg, opr)), (name, opg, opr)
+        assert latutil.rel_l2(xg, xr) < 1e-8, name
+
+
+def test_unbuilt_variants_and_bad_requests_behave_like_the_reference(ref, gpu, capfd):
+    """Error behaviour of the class API (SURVEY.md 8b "Errors"): applying a link set that was never built prints a
+    [QMG-WARNING] and leaves the (zeroed) output alone, on both back ends alike; nothing throws, nothing aborts."""
+    L = 16
+    g = latutil.phases_to_gauge(np.random.default_rng(3).normal(0, 0.3, size=L * L * 2), L, L)
+    rhs = latutil.gaussian_cv(L * L * 2, 1)
+    outs = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        op = be.lattice(L, L, 2).wilson(0.1, g)
+        assert op.built() == 0
+        outs[name] = [op.apply(rhs, t) for t in (1, 2, 3, 4, 5, 6, 7, 8)]      # every variant needs a build that did not happen
+        op.free()
+    capfd.readouterr()          # the warnings themselves sit in the libraries' stdio buffers; what is compared is the effect
+    for a_, b_ in zip(outs["ref"], outs["gpu"]):
+        assert np.array_equal(a_, b_)
