@@ -73,19 +73,25 @@ public:
     void reset_tracker() { counts[0] = counts[1] = counts[2] = counts[3] = 0; total = 0; iterations = 0; }
   };
 
-  // the coarsest solve (stateful_multigrid.h:204-241); deflation needs ARPACK and is outside this build (NO_ARPACK)
+  // the coarsest solve (stateful_multigrid.h:204-241)
   struct CoarsestSolveMG
   {
     QMGStencilType coarsest_stencil_app;
     double coarsest_tol; int coarsest_iters; int coarsest_restart_freq;
+    bool deflate;                 // use the eigenpairs of deflate_coarsest, once computed, to start the coarsest solve (:225)
     double normal_shift;
-    CoarsestSolveMG() : coarsest_stencil_app(QMG_MATVEC_ORIGINAL), coarsest_tol(1e-20), coarsest_iters(100000000), coarsest_restart_freq(32), normal_shift(0.0) { }
+    CoarsestSolveMG() : coarsest_stencil_app(QMG_MATVEC_ORIGINAL), coarsest_tol(1e-20), coarsest_iters(100000000), coarsest_restart_freq(32),
+                        deflate(true), normal_shift(0.0) { }
   };
 
 protected:
   std::vector<LevelSolveMG*> level_solve_list;
   std::vector<DslashTrackerMG*> dslash_tracker_list;
   CoarsestSolveMG* coarsest_solve;
+  // deflation space of the coarsest normal operator (stateful_multigrid.h:256-259)
+  int coarsest_deflated;
+  complex<double>* coarsest_evals;
+  complex<double>** coarsest_evecs;
 
   static void check_level_solve(LevelSolveMG* s, const char* where)
   {
@@ -102,9 +108,72 @@ protected:
 
 public:
   StatefulMultigridMG(Lattice2D* in_lat, Stencil2D* in_stencil, CoarsestSolveMG* in_coarsest_solve)
-    : MultigridMG(in_lat, in_stencil), current_level(0), coarsest_solve(in_coarsest_solve)
+    : MultigridMG(in_lat, in_stencil), current_level(0), coarsest_solve(in_coarsest_solve), coarsest_deflated(0), coarsest_evals(0), coarsest_evecs(0)
   { dslash_tracker_list.push_back(new DslashTrackerMG()); }
-  ~StatefulMultigridMG() { for (size_t i = 0; i < dslash_tracker_list.size(); i++) delete dslash_tracker_list[i]; }
+  ~StatefulMultigridMG()
+  {
+    for (size_t i = 0; i < dslash_tracker_list.size(); i++) delete dslash_tracker_list[i];
+    clear_deflation();
+  }
+
+  // ---- coarsest-level deflation (stateful_multigrid.h:613-711): num_low smallest and num_high largest eigenpairs of the
+  // coarsest NORMAL operator, from the Lanczos restatement of arpack_dcn (interfaces/arpack/generic_arpack.h; ncv = 3 nev,
+  // tol 1e-5 as the reference asks of ARPACK).  mg_preconditioner then starts every coarsest solve from the projection of
+  // its right-hand side onto that space.
+  void clear_deflation()
+  {
+    if (coarsest_evecs != 0)
+    {
+      for (int i = 0; i < coarsest_deflated; i++) if (coarsest_evecs[i] != 0) deallocate_vector(&coarsest_evecs[i]);
+      delete[] coarsest_evecs;
+    }
+    if (coarsest_evals != 0) delete[] coarsest_evals;
+    coarsest_evecs = 0; coarsest_evals = 0; coarsest_deflated = 0;
+  }
+  void deflate_coarsest(int num_low, int num_high, bool print_evals = false)
+  {
+    if (!coarsest_solve->deflate)
+      std::cout << "[QMG-WARNING]: Coarsest level is not set to deflate. Skipping computing eigenvectors.\n";
+    const QMGStencilType app = coarsest_solve->coarsest_stencil_app;
+    if (app != QMG_MATVEC_M_MDAGGER && app != QMG_MATVEC_MDAGGER_M && app != QMG_MATVEC_RBJ_M_MDAGGER && app != QMG_MATVEC_RBJ_MDAGGER_M)
+    {
+      std::cout << "[QMG-ERROR]: Cannot deflate coarsest operator unless it's a normal op solve.\n";
+      return;
+    }
+    if (coarsest_deflated != 0 || coarsest_evals != 0 || coarsest_evecs != 0)
+    {
+      std::cout << "[QMG-WARNING]: Coarsest operator space already deflated.\n";
+      return;
+    }
+    if (num_low + num_high == 0) return;
+    Stencil2D* coarsest = get_stencil(get_num_levels() - 1);
+    const int n = coarsest->get_lattice()->get_size_cv();
+    const int total = num_low + num_high;
+    coarsest_evals = new complex<double>[total];
+    coarsest_evecs = new complex<double>*[total];
+    for (int i = 0; i < total; i++) coarsest_evecs[i] = allocate_vector<complex<double> >(n);
+    coarsest_deflated = total;
+    bool ok = true;
+    if (num_low > 0)
+    {
+      arpack_dcn eig(n, 100000, 1e-5, Stencil2D::get_apply_function(app), (void*)coarsest, num_low, 3 * num_low);
+      ok = eig.prepare_eigensystem(arpack_dcn::ARPACK_SMALLEST_REAL, num_low, 3 * num_low) &&
+           eig.get_eigensystem(coarsest_evals, coarsest_evecs, arpack_dcn::ARPACK_SMALLEST_REAL);
+    }
+    if (ok && num_high > 0)
+    {
+      arpack_dcn eig(n, 100000, 1e-5, Stencil2D::get_apply_function(app), (void*)coarsest, num_high, 3 * num_high);
+      ok = eig.prepare_eigensystem(arpack_dcn::ARPACK_LARGEST_REAL, num_high, 3 * num_high) &&
+           eig.get_eigensystem(coarsest_evals + num_low, coarsest_evecs + num_low, arpack_dcn::ARPACK_LARGEST_REAL);
+    }
+    if (!ok) { clear_deflation(); return; }
+    for (int i = 0; i < total; i++) normalize(coarsest_evecs[i], n);
+    if (print_evals)
+      for (int i = 0; i < total; i++) std::cout << "[QMG-COARSEST-EVALS]: " << i << " " << real(coarsest_evals[i]) << "\n";
+  }
+  unsigned int get_coarsest_deflated() { return coarsest_deflated; }
+  complex<double>* get_coarsest_evals() { return coarsest_evals; }
+  complex<double>** get_coarsest_evecs() { return coarsest_evecs; }
 
   // ---- the level cursor the preconditioner callback reads (the object is stateful and not re-entrant)
   void set_multigrid_level(int level)
@@ -326,6 +395,18 @@ public:
         shifted.function = coarse_op; shifted.extra_data = (void*)coarse;
         shifted.extra_shift = mg->get_coarsest_solve()->normal_shift; shifted.length = nc_solve;
         op = shift_function; op_data = (void*)&shifted;
+      }
+      // start from the projection of the right-hand side onto the deflation space (stateful_multigrid.h:895-907)
+      if (normal && mg->get_coarsest_solve()->deflate && mg->get_coarsest_deflated() > 0)
+      {
+        const int num_evecs = mg->get_coarsest_deflated();
+        complex<double>* evals = mg->get_coarsest_evals();
+        complex<double>** evecs = mg->get_coarsest_evecs();
+        for (int i = 0; i < num_evecs; i++)
+        {
+          const complex<double> bra_n_ket_b = dot(evecs[i], r_c_prep, nc_solve);
+          caxpy(bra_n_ket_b / evals[i], evecs[i], e_c, nc_solve);
+        }
       }
       if (!normal)
         inv = (c_restart == -1) ? minv_vector_gcr(e_c, r_c_prep, nc_solve, c_iters, tol, op, op_data, &verb2)

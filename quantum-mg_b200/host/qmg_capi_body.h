@@ -687,7 +687,10 @@ inline void kcycle_build_hierarchy(KCycleH* h)
   const int* ip = h->ip; const double* dp = h->dp;
   const int n_refine = ip[0], xb = ip[1], yb = ip[2], coarse_dof = ip[3];
   const QMGStencilType level_app = (QMGStencilType)ip[12];
-  const bool need_rbj = (level_app != QMG_MATVEC_ORIGINAL) || ((QMGStencilType)ip[13] != QMG_MATVEC_ORIGINAL);
+  const QMGStencilType coarsest_app = (QMGStencilType)ip[13];
+  // a coarsest NORMAL-equation solve on the original operator needs M^dag on the coarse levels, nothing else
+  const bool coarsest_normal_plain = (coarsest_app == QMG_MATVEC_M_MDAGGER || coarsest_app == QMG_MATVEC_MDAGGER_M);
+  const bool need_rbj = (level_app != QMG_MATVEC_ORIGINAL) || (coarsest_app != QMG_MATVEC_ORIGINAL && !coarsest_normal_plain);
   if (need_rbj) h->op->build_rbjacobi_stencil();
   h->mg = new StatefulMultigridMG(h->lats[0], h->op, h->coarsest);
   inversion_verbose_struct verb((inversion_verbose_level)h->verbosity, "[CAPI-NULLVEC]: ");
@@ -732,7 +735,8 @@ inline void kcycle_build_hierarchy(KCycleH* h)
     h->level_solves.push_back(ls);
     h->mg->push_level(h->lats[i], h->transfers[i - 1], ls, true, true,
                       level_app == QMG_MATVEC_ORIGINAL ? MultigridMG::QMG_MULTIGRID_PRECOND_ORIGINAL : MultigridMG::QMG_MULTIGRID_PRECOND_RIGHT_BLOCK_JACOBI,
-                      need_rbj ? CoarseOperator2D::QMG_COARSE_BUILD_RBJACOBI : CoarseOperator2D::QMG_COARSE_BUILD_ORIGINAL, (capi_cd**)0);
+                      need_rbj ? CoarseOperator2D::QMG_COARSE_BUILD_RBJACOBI
+                               : (coarsest_normal_plain ? CoarseOperator2D::QMG_COARSE_BUILD_DAGGER : CoarseOperator2D::QMG_COARSE_BUILD_ORIGINAL), (capi_cd**)0);
     for (int j = 0; j < coarse_dof; j++) capi_free(nv[j]);
   }
 }
@@ -1030,6 +1034,49 @@ int CAPI(kcycle_gamma5_hermitian)(void* h_, int on)
   return count;
 #else
   (void)h_; (void)on; return 0;
+#endif
+}
+
+// B200 build only (the reference needs ARPACK for this, absent here): StatefulMultigridMG::deflate_coarsest
+// (multigrid/stateful_multigrid.h:613) -- num_low / num_high eigenpairs of the coarsest normal operator; evals_out
+// (num_low + num_high doubles, may be NULL) receives the eigenvalues.  Returns the size of the deflation space.
+int CAPI(kcycle_deflate_coarsest)(void* h_, int num_low, int num_high, double* evals_out)
+{
+#ifdef QMG_B200_HOST
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  h->mg->clear_deflation();
+  h->mg->deflate_coarsest(num_low, num_high, false);
+  const int n = (int)h->mg->get_coarsest_deflated();
+  if (evals_out != 0) for (int i = 0; i < n; i++) evals_out[i] = real(h->mg->get_coarsest_evals()[i]);
+  return n;
+#else
+  (void)h_; (void)num_low; (void)num_high; (void)evals_out; return 0;
+#endif
+}
+// B200 build only: nev eigenpairs at the low (which = 0) or high (1) end of the spectrum of the HERMITIAN operator
+// `type` of this stencil (e.g. QMG_MATVEC_MDAGGER_M) through arpack_dcn; evecs_out: nev * size_cv or NULL.
+// Returns 1 on success.
+int CAPI(stencil_eigs)(void* h_, int type, int nev, int ncv, int which, double tol, double* evals_out, capi_cd* evecs_out)
+{
+#ifdef QMG_B200_HOST
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  const int n = s->lat->get_size_cv();
+  arpack_dcn eig(n, 100000, tol, Stencil2D::get_apply_function((QMGStencilType)type), (void*)s, nev, ncv);
+  const arpack_dcn::arpack_spectrum_piece piece = which ? arpack_dcn::ARPACK_LARGEST_REAL : arpack_dcn::ARPACK_SMALLEST_REAL;
+  if (!eig.prepare_eigensystem(piece, nev, ncv)) return 0;
+  std::vector<capi_cd> ev(nev);
+  std::vector<capi_cd*> vec(nev);
+  for (int i = 0; i < nev; i++) vec[i] = capi_alloc(n);
+  const bool ok = eig.get_eigensystem(&ev[0], &vec[0], piece);
+  for (int i = 0; i < nev; i++)
+  {
+    evals_out[i] = real(ev[i]);
+    if (ok && evecs_out != 0) capi_get(evecs_out + (long)i * n, vec[i], n);
+    capi_free(vec[i]);
+  }
+  return ok ? 1 : 0;
+#else
+  (void)h_; (void)type; (void)nev; (void)ncv; (void)which; (void)tol; (void)evals_out; (void)evecs_out; return 0;
 #endif
 }
 

@@ -246,6 +246,14 @@ class Stencil:
     def gamma5_hermitian(self, on=True):
         return int(self.be.fn("stencil_gamma5_hermitian")(self.h, 1 if on else 0))
 
+    def eigs(self, type, nev, ncv=None, high=False, tol=1e-8, want_vectors=False):
+        """B200 build only: nev extreme eigenpairs of the Hermitian operator `type` (arpack_dcn's Lanczos restatement)."""
+        ncv = 3 * nev if ncv is None else ncv
+        ev = np.zeros(nev, np.float64)
+        vec = np.zeros((nev, self.lat.size_cv), CD) if want_vectors else None
+        ok = self.be.fn("stencil_eigs")(self.h, type, nev, ncv, 1 if high else 0, C.c_double(tol), _c(ev), _c(vec))
+        return (ok == 1), ev, vec
+
     def coarse_sigma(self, type, v):
         """CoarseOperator2D::apply_sigma(out, v, QMGSigmaTypeCoarse type in 6..9); out starts as zeros."""
         out = np.zeros(self.lat.size_cv, CD)
@@ -431,6 +439,12 @@ class KCycle:
     def gamma5_hermitian(self, on=True):
         """B200 extension: link-compressed applies on every level that passes the check; returns how many levels switched."""
         return int(self.be.fn("kcycle_gamma5_hermitian")(self.h, 1 if on else 0))
+
+    def deflate_coarsest(self, num_low, num_high=0):
+        """B200 build only: eigenpairs of the coarsest normal operator for the deflated coarsest solve; returns their eigenvalues."""
+        ev = np.zeros(num_low + num_high, np.float64)
+        n = int(self.be.fn("kcycle_deflate_coarsest")(self.h, num_low, num_high, _c(ev)))
+        return ev[:n]
 
     def time_precond(self, warm=1, reps=3):
         return self.be.fn("kcycle_time_precond")(self.h, warm, reps) / reps

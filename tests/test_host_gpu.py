@@ -563,3 +563,44 @@ def test_unbuilt_variants_and_bad_requests_behave_like_the_reference(ref, gpu, c
     capfd.readouterr()          # the warnings themselves sit in the libraries' stdio buffers; what is compared is the effect
     for a_, b_ in zip(outs["ref"], outs["gpu"]):
         assert np.array_equal(a_, b_)
+
+
+def test_lanczos_eigensolver_and_coarsest_deflation(ref, gpu):
+    """SURVEY.md 8f rank 4: the eigensolver behind StatefulMultigridMG::deflate_coarsest (the reference calls ARPACK, absent
+    here and in the oracle, so this is checked against numpy): extreme eigenpairs of M^dag M on a small Wilson lattice
+    against a dense diagonalisation, residuals |A v - lambda v|, refusal of a non-Hermitian operator; then a 3-level K-cycle
+    whose coarsest solve is CG on the normal equations, with and without a deflation space: same answer, fewer coarsest
+    iterations."""
+    L = 8
+    g = latutil.phases_to_gauge(np.random.default_rng(5).normal(0, 0.4, size=L * L * 2), L, L)
+    lat = gpu.lattice(L, L, 2)
+    op = lat.wilson(0.05, g)
+    op.build(dagger=True)
+    n = lat.size_cv
+    cols = np.stack([op.apply(np.eye(n, dtype=np.complex128)[j], 5) for j in range(n)], axis=1)      # M^dag M, column by column
+    assert np.allclose(cols, cols.conj().T, atol=1e-12)
+    want = np.linalg.eigvalsh(cols)
+    ok, ev, vec = op.eigs(5, 6, tol=1e-9, want_vectors=True)
+    assert ok and np.allclose(ev, want[:6], rtol=1e-7)
+    for lam, v in zip(ev, vec):
+        assert np.linalg.norm(cols @ v - lam * v) < 1e-6 * np.linalg.norm(v) * want[-1]
+    ok, evh, _ = op.eigs(5, 4, high=True, tol=1e-9)
+    assert ok and np.allclose(np.sort(evh), want[-4:], rtol=1e-7)
+    ok, _, _ = op.eigs(0, 4)                 # the Wilson operator itself is not Hermitian: refused
+    assert not ok
+    op.free()
+
+    L = 64
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L * 2, 5)
+    kc = capi.KCycle(gpu, L, -0.06, g, n_refine=2, seed=5, coarsest_app=5, coarsest_tol=0.05)     # coarsest: CG on M^dag M
+    x0, i0 = kc.solve(b, tol=1e-10, want_x=True)
+    plain = kc.tracker(2)["total"]
+    ev = kc.deflate_coarsest(16)
+    assert ev.size == 16 and np.all(ev > 0) and np.all(np.diff(ev) >= -1e-12)
+    x1, i1 = kc.solve(b, tol=1e-10, want_x=True)
+    deflated = kc.tracker(2)["total"]
+    kc.free()
+    assert i0["success"] and i1["success"] and abs(i0["iter"] - i1["iter"]) <= 2
+    assert latutil.rel_l2(x1, x0) < 1e-8
+    assert deflated < 0.8 * plain, (plain, deflated)
