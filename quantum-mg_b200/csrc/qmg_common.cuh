@@ -219,6 +219,7 @@ __device__ __forceinline__ void publish_result(unsigned int* counter, double* re
 template <int W>
 __device__ __forceinline__ void grid_reduce_finish(double (&v)[W], double* smem, double* partials, unsigned int* counter, double* result)
 {
+  static_assert(W <= kMailWidth && W <= kMaxRedWidth, "reduction wider than the result slots");
   block_sum<W>(v, smem);
   __shared__ bool is_last;
   if (threadIdx.x == 0)
