@@ -323,6 +323,7 @@ int qmg_comm_init(int nranks, int rank, const void* unique_id128)
 {
   QMG_REQUIRE_INIT();
   Comm& c = comm();
+  if (c.active && c.loopback) { int frc = qmg_comm_finalize(); if (frc) return frc; }    // a real communicator replaces the loopback
   if (c.active) return fail_msg("qmg_comm_init: already initialised");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail_msg("qmg_comm_init: bad rank / size");
   c.nranks = nranks; c.rank = rank;

@@ -132,6 +132,7 @@ def test_two_rank_kcycle():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ, QMG_DEVICE_RNG="1")
+    env.pop("QMG_LOOPBACK", None)          # the workers build a real two-rank communicator
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "shard_worker.py"), "--L", "256", "--levels", "3"]
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
