@@ -534,8 +534,8 @@ static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduc
 {
   if (!reduce && a.herm && rt().tile_kernel)
   {
-    // patch shapes: nc = 8: 8 x 4 sites (97 KB of shared memory, two CTAs per SM; 8x2, 4x4, 16x2 and 4x2 patches measured
-    // within 10 % of it, profiles/r02f_tile_shapes.txt); nc = 4: 16 x 8.  nc = 2 blocks are too small to win (the
+    // patch shapes: nc = 8: 8 x 4 sites (97 KB of shared memory, two CTAs per SM; 4x4, 8x2, 4x2 and 16x4 patches measured
+    // 3-23 % slower, profiles/r02q_tile_shapes.txt); nc = 4: 16 x 8.  nc = 2 blocks are too small to win (the
     // column-wise clover loads waste half of every sector): the fine level keeps the streaming kernel.
     if (nc == 8 && tile_applicable<4, 4>(a, n_par)) return launch_tile<8, 4, 4>(a);
     if (nc == 4 && tile_applicable<8, 8>(a, n_par)) return launch_tile<4, 8, 8>(a);
