@@ -62,8 +62,11 @@ template <typename T> inline void deallocate_vector(T** v) { if (*v != 0) { QMG_
 // ------------------------------------------------------------ fill/copy ----
 typedef std::complex<double> qmg_cd;
 
-inline void zero_vector(qmg_cd* v, long n) { QMG_CHK(qmg_zero(qmg_host::P(v), n)); }
-inline void copy_vector(qmg_cd* dst, const qmg_cd* src, long n) { QMG_CHK(qmg_copy(qmg_host::P(dst), qmg_host::P(src), n)); }
+// templates, because drivers also spell the element type out (tests/n07_free_laplace_mg/free_laplace_mg.cpp:480:
+// zero_vector<complex<double>>(e, n)) and call them on real phase fields (tests/n13_wilson_kcycle/wilson_kcycle.cpp:203)
+template <typename T> inline void zero_vector(T* v, long n) { QMG_CHK(qmg_zero_bytes(v, sizeof(T) * (size_t)(n > 0 ? n : 0))); }
+template <typename T> inline void copy_vector(T* dst, const T* src, long n) { if (n > 0 && dst != src) QMG_CHK(qmg_memcpy_d2d(dst, src, sizeof(T) * (size_t)n)); }
+template <typename T> inline void copy_vector(T* dst, T* src, long n) { copy_vector<T>(dst, static_cast<const T*>(src), n); }
 template <typename U> inline void constant_vector(qmg_cd* v, U val, long n) { qmg_cd a(val); QMG_CHK(qmg_constant(qmg_host::P(v), a.real(), a.imag(), n)); }
 inline void zero_vector_blas(qmg_cd* v, int stride, long n) { QMG_CHK(qmg_zero_strided(qmg_host::P(v), stride, n)); }
 template <typename U> inline void constant_vector_blas(qmg_cd* v, int stride, U val, long n) { qmg_cd a(val); QMG_CHK(qmg_constant_strided(qmg_host::P(v), stride, a.real(), a.imag(), n)); }
@@ -183,6 +186,21 @@ inline void gaussian_real(qmg_cd* v, long n, std::mt19937& gen, double dev = 1.0
   std::normal_distribution<double> dist(0.0, dev);
   for (long i = 0; i < n; i++) h[i] = qmg_cd(dist(gen), 0.0);
   qmg_host::upload(v, h.data(), n);
+}
+// real fields (phases: tests/n04_staggered_test/staggered_test.cpp:144)
+inline void random_uniform(double* v, long n, std::mt19937& gen, double lo, double hi)
+{
+  std::vector<double> h((size_t)n);
+  std::uniform_real_distribution<double> dist(lo, hi);
+  for (long i = 0; i < n; i++) h[i] = dist(gen);
+  qmg_host::check(qmg_memcpy_h2d(v, h.data(), sizeof(double) * (size_t)n), "upload");
+}
+inline void gaussian(double* v, long n, std::mt19937& gen, double dev = 1.0)
+{
+  std::vector<double> h((size_t)n);
+  std::normal_distribution<double> dist(0.0, dev);
+  for (long i = 0; i < n; i++) h[i] = dist(gen);
+  qmg_host::check(qmg_memcpy_h2d(v, h.data(), sizeof(double) * (size_t)n), "upload");
 }
 inline void random_uniform(qmg_cd* v, long n, std::mt19937& gen, double lo, double hi)
 {

@@ -203,6 +203,12 @@ public:
     return true;
   }
 
+  // ARPACK's own default for the Krylov dimension when the caller gives none (tests/n12_wilson_eigenvalue_test/wilson_test.cpp:208)
+  bool prepare_eigensystem(arpack_spectrum_piece piece, int nev_in) { return prepare_eigensystem(piece, nev_in, std::min(n, std::max(2 * nev_in + 1, 20))); }
+  // what the reference reads after a failure (n12 :210): the ARPACK return codes have no meaning here
+  struct arpack_solve_info { int znaupd_code, zneupd_code, nconv, niter; bool is_error; };
+  arpack_solve_info get_solve_info() const { arpack_solve_info i; i.znaupd_code = ready ? 0 : -9999; i.zneupd_code = i.znaupd_code; i.nconv = ready ? nev : 0; i.niter = restarts; i.is_error = !ready; return i; }
+
   // copy the eigenpairs computed by prepare_eigensystem (evecs: nev device vectors of the caller)
   bool get_eigensystem(std::complex<double>* evals, std::complex<double>** evecs, arpack_spectrum_piece)
   {

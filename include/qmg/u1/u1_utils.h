@@ -48,8 +48,7 @@ template <class F> inline void for_each_link_in_file_order(Lattice2D* lat, F f)
 }
 
 // double-field flavours of the quantum-linalg calls the drivers make on phase fields (n13 :203, :212)
-inline void zero_vector(double* v, long n) { QMG_CHK(qmg_zero_bytes(v, sizeof(double) * (size_t)n)); }
-inline void copy_vector(double* dst, const double* src, long n) { QMG_CHK(qmg_memcpy_d2d(dst, src, sizeof(double) * (size_t)n)); }
+// (zero_vector / copy_vector on real fields: the templates of blas/generic_vector.h)
 inline void polar_vector(const double* phases, complex<double>* out, long n) { QMG_CHK(qmg_polar_vector(phases, qmg_host::P(out), n)); }
 
 // ---- file format: one phase per line, x outer, y, mu inner (u1_utils.h:38-168)

@@ -20,6 +20,8 @@
 #include "inverters/generic_minres.h"
 #include "inverters/generic_bicgstab_l.h"
 #include "inverters/generic_richardson.h"
+#include "inverters/generic_bicgstab.h"
+#include "inverters/generic_tfqmr.h"
 
 // the reference (resolved through -I/root/reference)
 #include "lattice/lattice.h"

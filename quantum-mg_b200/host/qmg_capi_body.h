@@ -299,7 +299,7 @@ double CAPI(stencil_time_apply)(void* h_, int type, int warm, int reps, const ca
 
 // ------------------------------------------------------------------- solvers --
 // solver: 0 CG  1 CG(restart=iparam)  2 GCR  3 GCR(restart)  4 MR(omega=dparam)  5 BiCGstab-L(L=iparam)
-//         6 Richardson(omega=dparam, check_freq=iparam)
+//         6 Richardson(omega=dparam, check_freq=iparam)  7 BiCGstab  8 TFQMR (the oracle's shim only declares it)
 // n = number of complex unknowns handed to the solver (size_cv, or size_cv/2 for Schur systems)
 // info: resSq, iter, success, ops_count
 void CAPI(solve)(void* h_, int solver, int type, capi_cd* x, const capi_cd* b, int n, int max_iter, double tol, int iparam, double dparam, int verbosity, double* info)
@@ -319,6 +319,8 @@ void CAPI(solve)(void* h_, int solver, int type, capi_cd* x, const capi_cd* b, i
     case 4: inv = minv_vector_minres((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, dparam, fn, (void*)s, &verb); break;
     case 5: inv = minv_vector_bicgstab_l((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, iparam, fn, (void*)s, &verb); break;
     case 6: inv = minv_vector_richardson((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, dparam, iparam, fn, (void*)s, &verb); break;
+    case 7: inv = minv_vector_bicgstab((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, fn, (void*)s, &verb); break;
+    case 8: inv = minv_vector_tfqmr((capi_cd*)dx, (capi_cd*)db, n, max_iter, tol, fn, (void*)s, &verb); break;
   }
   info[0] = inv.resSq; info[1] = inv.iter; info[2] = inv.success ? 1.0 : 0.0; info[3] = inv.ops_count;
 }

@@ -12,6 +12,8 @@
 #include "inverters/generic_minres.h"
 #include "inverters/generic_bicgstab_l.h"
 #include "inverters/generic_richardson.h"
+#include "inverters/generic_bicgstab.h"
+#include "inverters/generic_tfqmr.h"
 
 #include "lattice/lattice.h"
 #include "cshift/cshift_2d.h"

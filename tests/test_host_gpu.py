@@ -604,3 +604,25 @@ def test_lanczos_eigensolver_and_coarsest_deflation(ref, gpu):
     assert i0["success"] and i1["success"] and abs(i0["iter"] - i1["iter"]) <= 2
     assert latutil.rel_l2(x1, x0) < 1e-8
     assert deflated < 0.8 * plain, (plain, deflated)
+
+
+def test_n11_solver_survey_extras(ref, gpu):
+    """tests/n11_wilson_test also calls minv_vector_bicgstab and minv_vector_tfqmr (wilson_test.cpp:185, :241).  BiCGstab is
+    BiCGstab(1) on both back ends (iteration parity); TFQMR exists only as a declaration in the oracle's shim, so the device
+    version is held to its own contract: it converges and the reported residual is the true one."""
+    L = 32
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L * 2, 4)
+    res = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        op = be.lattice(L, L, 2).wilson(0.1, g)
+        res[name] = op.solve(7, b, max_iter=2000, tol=1e-9)
+        if name == "gpu":
+            x, info = op.solve(8, b, max_iter=2000, tol=1e-9)
+            assert info["success"] and 0 < info["iter"] < 400
+            assert latutil.rel_l2(op.apply(x, 0), b) < 2e-9
+            assert abs(np.sqrt(info["resSq"]) / np.linalg.norm(b) - latutil.rel_l2(op.apply(x, 0), b)) < 1e-12
+        op.free()
+    (xr, ir), (xg, ig) = res["ref"], res["gpu"]
+    assert ir["success"] and ig["success"] and abs(ir["iter"] - ig["iter"]) <= 2
+    assert latutil.rel_l2(xg, xr) < 1e-7
