@@ -38,7 +38,7 @@ def ncu_traffic(X, Y):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             e = json.load(f).get("stencil_kernel<2>@%dx%d" % (X, Y))
-        return None if e is None else {"GB_per_launch": e["traffic_GB"], "algorithmic_GB_per_launch": e["algorithmic_GB"], "source": e["source"]}
+        return None if e is None else {"bytes": e["traffic_GB"] * 1e9, "algorithmic_bytes": e["algorithmic_GB"] * 1e9, "source": e["source"]}
     except Exception:
         return None
 
@@ -308,6 +308,7 @@ def run_gpu(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic = ncu_traffic(X, Y)
         achieved = BYTES_PER_SITE * V / (kern_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -327,7 +328,8 @@ def run_gpu(args):
             "config": {"workload": "wilson_stencil_apply_%dx%d_u1" % (X, Y * world), "per_gpu_lattice": [X, Y], "beta": beta, "mass": -0.075,
                        "bytes_per_site": BYTES_PER_SITE, "l2": "operands (%.1f GB per apply) far larger than the 126 MB L2; no flush needed" % (BYTES_PER_SITE * V / 1e9),
                        "parallelism": "y-slabs x%d, 1-row halo ring" % world},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(X, Y),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get("bytes"), "traffic_unit": "DRAM bytes per launch (ncu --set full)",
+                         "algorithmic_bytes_per_launch": BYTES_PER_SITE * V, "traffic_source": (traffic or {}).get("source"),
                          "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0, "kernel": "qmg::stencil_kernel<2>"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n, "ms_per_step": e2e_sec * 1e3, "steps": e2e_steps,
