@@ -215,11 +215,13 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
 // per lane group.  Block rows are padded to NC + 1 elements so that both the row-wise and the transposed reads of a
 // quarter warp fall into distinct banks.  Same lane <-> matrix element mapping and the same shuffle tree as above, so the
 // sums are formed in the same order.
-template <int NC, int TK, int TY> struct TileDims
+// SPLIT threads share one (site, column): each walks NC / SPLIT of the rows (more warps per staged byte)
+template <int NC, int TK, int TY, int SPLIT = 1> struct TileDims
 {
   static const int S = TY * 2 * TK;                               // sites of the patch
-  static const int THREADS = (S * NC >= 256) ? 256 : S * NC;      // one thread per (site, column), at most 256 per pass
-  static const int PASSES = S * NC / THREADS;
+  static const int CAP = 256 * SPLIT;
+  static const int THREADS = (S * NC * SPLIT >= CAP) ? CAP : S * NC * SPLIT;
+  static const int PASSES = S * NC * SPLIT / THREADS;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
@@ -229,9 +231,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 // the three pieces of a patch's life: stage (asynchronous), fetch the clover column (registers), compute
-template <int NC, int TK, int TY> struct Tile
+template <int NC, int TK, int TY, int SPLIT = 1> struct Tile
 {
-  static const int S = TileDims<NC, TK, TY>::S, NT = TileDims<NC, TK, TY>::THREADS, PASSES = TileDims<NC, TK, TY>::PASSES;
+  static const int S = TileDims<NC, TK, TY, SPLIT>::S, NT = TileDims<NC, TK, TY, SPLIT>::THREADS, PASSES = TileDims<NC, TK, TY, SPLIT>::PASSES;
+  static const int R = NC / SPLIT;             // rows per thread
   static const int LPS = NC * NC;
   static const int RS = NC + 1;                // padded row stride of a staged block
   static const int BS = NC * RS;               // elements per staged block
@@ -276,18 +279,18 @@ template <int NC, int TK, int TY> struct Tile
   }
 
   // clover column c2 of this thread's site(s), straight from global memory while a tile is in flight
-  __device__ static __forceinline__ void clover(const StencilKArgs& a, int k0, int y0, int tid, cd (&CLc)[PASSES][NC])
+  __device__ static __forceinline__ void clover(const StencilKArgs& a, int k0, int y0, int tid, cd (&CLc)[PASSES][R])
   {
-    const int c2 = tid % NC;
+    const int c2 = tid % NC, hf = (tid / NC) % SPLIT;
     const cd zero = cmake(0.0, 0.0);
 #pragma unroll
     for (int ps = 0; ps < PASSES; ps++)
     {
-      const int slot = ps * (NT / NC) + tid / NC;
+      const int slot = ps * (NT / (NC * SPLIT)) + tid / (NC * SPLIT);
       const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; const int p = r / TK, tk = r - p * TK;
       const size_t site = (size_t)p * a.g.half + (size_t)(y0 + ty) * a.g.xh + (k0 + tk);
 #pragma unroll
-      for (int c1 = 0; c1 < NC; c1++) CLc[ps][c1] = (a.clover != nullptr) ? ld_stream(a.clover + site * LPS + c1 * NC + c2) : zero;
+      for (int i = 0; i < R; i++) CLc[ps][i] = (a.clover != nullptr) ? ld_stream(a.clover + site * LPS + (hf * R + i) * NC + c2) : zero;
     }
   }
 
@@ -296,16 +299,16 @@ template <int NC, int TK, int TY> struct Tile
   // (NC - 1 complex shuffles) that leaves row t on thread t.  Per block a thread reads NC matrix elements and ONE spinor
   // element from shared memory (an element-per-lane mapping reads one of each per element: twice the shared-memory
   // traffic, which is what bounds this kernel).
-  __device__ static __forceinline__ void compute(const StencilKArgs& a, const cd* buf, int k0, int y0, int tid, const cd (&CLc)[PASSES][NC])
+  __device__ static __forceinline__ void compute(const StencilKArgs& a, const cd* buf, int k0, int y0, int tid, const cd (&CLc)[PASSES][R])
   {
     const cd* sHx = buf; const cd* sHy = sHx + (size_t)NHX * BS; const cd* sV = sHy + (size_t)NHY * BS;
-    const int c2 = tid % NC;
+    const int c2 = tid % NC, hf = (tid / NC) % SPLIT;
     const cd zero = cmake(0.0, 0.0);
     const bool top = (2 * c2 < NC);
 #pragma unroll
     for (int ps = 0; ps < PASSES; ps++)
     {
-      const int slot = ps * (NT / NC) + tid / NC;
+      const int slot = ps * (NT / (NC * SPLIT)) + tid / (NC * SPLIT);
       const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; const int p = r / TK, tk = r - p * TK;
       const int q = 1 - p, y = y0 + ty, sft = (y + p) & 1;
       const int nx = sft ? (ty * 2 + q) * TK + tk : (tk > 0 ? (ty * 2 + q) * TK + tk - 1 : S + ty);
@@ -316,63 +319,77 @@ template <int NC, int TK, int TY> struct Tile
       const cd V2 = vrow[((size_t)q * VK + tk + sft) * NC];
       const cd V1 = vrow[((size_t)(2 + q) * VK + tk + 1) * NC];
       const cd V3 = vrow[((ptrdiff_t)q * VK + tk + 1 - 2 * VK) * NC];
-      const cd* hx = sHx + (size_t)slot * BS + c2;          // column c2: element [c1][c2] at + c1 * RS
-      const cd* hy = sHy + (size_t)slot * BS + c2;
-      const cd* bx = sHx + (size_t)nx * BS + c2 * RS;       // row c2 of the neighbour's block: element [c2][c1] at + c1
-      const cd* by = sHy + (size_t)ny * BS + c2 * RS;
-      cd acc[NC];
+      const cd* hx = sHx + (size_t)slot * BS + (hf * R) * RS + c2;   // column c2, rows of this thread: element [c1][c2] at + i * RS
+      const cd* hy = sHy + (size_t)slot * BS + (hf * R) * RS + c2;
+      const cd* bx = sHx + (size_t)nx * BS + c2 * RS + hf * R;       // row c2 of the neighbour's block: element [c2][c1] at + i
+      const cd* by = sHy + (size_t)ny * BS + c2 * RS + hf * R;
+      cd acc[R];
 #pragma unroll
-      for (int c1 = 0; c1 < NC; c1++)
+      for (int i = 0; i < R; i++)
       {
+        const int c1 = hf * R + i;
         cd t = zero;
-        cfma(t, CLc[ps][c1], VC);
-        cfma(t, hx[c1 * RS], V0);
-        cfma(t, hy[c1 * RS], V1);
+        cfma(t, CLc[ps][i], VC);
+        cfma(t, hx[i * RS], V0);
+        cfma(t, hy[i * RS], V1);
         // backward blocks: s_{c1} s_{c2} conj(B[c2][c1])
         const double sg = ((2 * c1 < NC) == top) ? 1.0 : -1.0;
-        const cd b2 = bx[c1], b3 = by[c1];
+        const cd b2 = bx[i], b3 = by[i];
         cfma(t, cmake(sg * b2.x, -sg * b2.y), V2);
         cfma(t, cmake(sg * b3.x, -sg * b3.y), V3);
-        acc[c1] = t;
+        acc[i] = t;
       }
       if (a.use_diag)
       {
         // diag shift on row c2 of this thread's column: a predicated add keeps acc[] in registers (no dynamic indexing)
         const cd dg = a.diag[p][top ? 0 : 1];
 #pragma unroll
-        for (int c1 = 0; c1 < NC; c1++) if (c1 == c2) cfma(acc[c1], dg, VC);
+        for (int i = 0; i < R; i++) if (hf * R + i == c2) cfma(acc[i], dg, VC);
       }
-      // transposing butterfly over the NC threads of the site: thread t ends up with row t
+      // butterfly over the NC threads (c2) that share this site and row set: transposing while more than one row is
+      // left on a thread, a plain pairwise sum afterwards; row hf * R + (c2 / SPLIT) ends up on thread c2
+      int left = R;
 #pragma unroll
       for (int off = NC / 2; off > 0; off >>= 1)
       {
-        const bool upper = (c2 & off) != 0;
-#pragma unroll
-        for (int i = 0; i < off; i++)
+        if (left > 1)
         {
-          const cd send = upper ? acc[i] : acc[i + off];
-          const cd keep = upper ? acc[i + off] : acc[i];
-          acc[i] = cadd(keep, shfl_xor_c(send, off));
+          const int hl = left / 2;
+          const bool upper = (c2 & off) != 0;
+#pragma unroll
+          for (int i = 0; i < R / 2; i++)
+            if (i < hl)
+            {
+              const cd send = upper ? acc[i] : acc[i + hl];
+              const cd keep = upper ? acc[i + hl] : acc[i];
+              acc[i] = cadd(keep, shfl_xor_c(send, off));
+            }
+          left = hl;
         }
+        else acc[0] = cadd(acc[0], shfl_xor_c(acc[0], off));
       }
-      const size_t site = (size_t)p * a.g.half + (size_t)y * a.g.xh + (k0 + tk);
-      cd res = acc[0];
-      if (a.accumulate) res = cadd(res, a.out[site * NC + c2]);
-      a.out[site * NC + c2] = res;
+      if (SPLIT == 1 || (c2 % SPLIT) == 0)
+      {
+        const int row = hf * R + c2 / SPLIT;
+        const size_t site = (size_t)p * a.g.half + (size_t)y * a.g.xh + (k0 + tk);
+        cd res = acc[0];
+        if (a.accumulate) res = cadd(res, a.out[site * NC + row]);
+        a.out[site * NC + row] = res;
+      }
     }
   }
 };
 
 // one patch per CTA
-template <int NC, int TK, int TY>
-__global__ void __launch_bounds__(TileDims<NC, TK, TY>::THREADS) stencil_tile_kernel(const StencilKArgs a)
+template <int NC, int TK, int TY, int SPLIT>
+__global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT > 1 ? 2 : 1)) stencil_tile_kernel(const StencilKArgs a)
 {
-  typedef Tile<NC, TK, TY> T;
+  typedef Tile<NC, TK, TY, SPLIT> T;
   extern __shared__ cd tile_smem[];
   const int tid = threadIdx.x;
   const int k0 = blockIdx.x * TK, y0 = a.y_off + blockIdx.y * TY;
   T::stage(a, tile_smem, k0, y0, tid);
-  cd CLc[T::PASSES][NC];
+  cd CLc[T::PASSES][T::R];
   T::clover(a, k0, y0, tid, CLc);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -403,14 +420,14 @@ template <int TK, int TY> static bool tile_applicable(const StencilKArgs& a, int
          a.y_off == 0 && a.y_stride == 1 && a.y_cnt == a.g.Y;
 }
 
-template <int NC, int TK, int TY> static int launch_tile(const StencilKArgs& a)
+template <int NC, int TK, int TY, int SPLIT = 1> static int launch_tile(const StencilKArgs& a)
 {
   static bool configured = false;
   const size_t smem = tile_smem_bytes<NC, TK, TY>();
-  if (!configured) { QMG_CUDA(cudaFuncSetAttribute(stencil_tile_kernel<NC, TK, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+  if (!configured) { QMG_CUDA(cudaFuncSetAttribute(stencil_tile_kernel<NC, TK, TY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
   dim3 grid(a.g.xh / TK, a.y_cnt / TY, 1);       // rows [y_off, y_off + y_cnt): whole patches
   if (grid.y > 65535) return fail_msg("qmg_stencil_apply: Y too large for the launch grid");
-  stencil_tile_kernel<NC, TK, TY><<<grid, TileDims<NC, TK, TY>::THREADS, smem, rt().stream>>>(a);
+  stencil_tile_kernel<NC, TK, TY, SPLIT><<<grid, TileDims<NC, TK, TY, SPLIT>::THREADS, smem, rt().stream>>>(a);
   QMG_LAUNCH_CHECK();
   return 0;
 }
@@ -537,7 +554,10 @@ static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduc
     // patch shapes: nc = 8: 8 x 4 sites (97 KB of shared memory, two CTAs per SM; 4x4, 8x2, 4x2 and 16x4 patches measured
     // 3-23 % slower, profiles/r02q_tile_shapes.txt); nc = 4: 16 x 8.  nc = 2 blocks are too small to win (the
     // column-wise clover loads waste half of every sector): the fine level keeps the streaming kernel.
-    if (nc == 8 && tile_applicable<4, 4>(a, n_par)) return launch_tile<8, 4, 4>(a);
+    // nc = 8: two threads per (site, column), four rows each -- 32 instead of 16 warps per SM on the same staged bytes:
+    // 3.00 -> 2.51 ms sustained on 2048^2 (profiles/r02w_tile_split.txt; QMG_TILE=2 selects the one-thread flavour)
+    if (nc == 8 && rt().tile_kernel == 2 && tile_applicable<4, 4>(a, n_par)) return launch_tile<8, 4, 4, 1>(a);
+    if (nc == 8 && tile_applicable<4, 4>(a, n_par)) return launch_tile<8, 4, 4, 2>(a);
     if (nc == 4 && tile_applicable<8, 8>(a, n_par)) return launch_tile<4, 8, 8>(a);
   }
   switch (nc)
@@ -588,7 +608,7 @@ static int apply_sharded(StencilKArgs& a, int nc, int n_par)
   {
     StencilKArgs in = a;
     in.hop_ym = nullptr; in.y_off = TY8; in.y_stride = 1; in.y_cnt = a.g.Y - 2 * TY8;
-    rc = launch_tile<8, TK8, TY8>(in); if (rc) return rc;
+    rc = launch_tile<8, TK8, TY8, 2>(in); if (rc) return rc;
     rc = halo_exchange_end(); if (rc) return rc;
     a.halo_ym = rows.ym; a.halo_yp = rows.yp;
     a.y_off = 0; a.y_stride = 1; a.y_cnt = TY8;
