@@ -127,3 +127,17 @@ def test_unmodified_reference_drivers_compile_against_the_b200_headers():
             if r.returncode != 0:
                 failures.append((d, r.stdout[-600:]))
     assert not failures, failures
+
+
+def test_c_abi_header_is_plain_c(tmp_path):
+    """include/qmg_b200.h is the drop-in boundary: it must be consumable from C (cgo / JNI / ctypes style bindings), i.e. parse
+    as strict C99 with no C++ or torch types, and a C translation unit using it must link against libqmg_b200.so."""
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include "qmg_b200.h"\n#include <stdio.h>\nint main(void) { printf("%d %d\\n", qmg_device_count(), qmg_comm_size()); return 0; }\n')
+    exe = tmp_path / "use_abi"
+    lib_dir = os.path.join(ROOT, "quantum-mg_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src),
+                        "-L" + lib_dir, "-lqmg_b200", "-Wl,-rpath," + lib_dir, "-o", str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0 and out.stdout.split()[1] == "1"
