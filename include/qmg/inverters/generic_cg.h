@@ -54,7 +54,7 @@ inline inversion_info minv_vector_cg_restart(complex<double>* phi, complex<doubl
                                              matrix_op_cplx matrix_vector, void* extra_info, inversion_verbose_struct* verb = 0)
 {
   return qmg_host::restarted("Restarted CG", phi0, size, max_iter, eps, restart_freq, verb,
-    [&](int burst, inversion_verbose_struct* quiet) { return minv_vector_cg(phi, phi0, size, burst, eps, matrix_vector, extra_info, quiet); });
+    [&](int burst, inversion_verbose_struct* quiet, qmg_host::SolveHints*) { return minv_vector_cg(phi, phi0, size, burst, eps, matrix_vector, extra_info, quiet); });
 }
 
 #endif

@@ -13,24 +13,47 @@
 
 namespace qmg_host {
 
-// Shared body of GCR and flexible (variably preconditioned) GCR.
+// A preconditioner that overwrites its whole output (the K-cycle registers StatefulMultigridMG::mg_preconditioner here)
+// needs no zeroed output vector; any other callback still gets one, as quantum-linalg's callers expect.
+inline precond_op_cplx& overwriting_precond() { static precond_op_cplx f = 0; return f; }
+
+// Shared body of GCR and flexible (variably preconditioned) GCR.  `hints` (inverter_struct.h) as in minres_core: from a
+// zero start r0 = b without applying A to zero, x is written by the first step instead of being zeroed and read, |b|^2
+// can come from the caller, and a solve that ends converged skips the true-residual apply nobody reads.
 inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps,
                                matrix_op_cplx matrix_vector, void* extra_info,
-                               precond_op_cplx precond, void* precond_info, inversion_verbose_struct* verb)
+                               precond_op_cplx precond, void* precond_info, inversion_verbose_struct* verb, SolveHints* hints = 0)
 {
   inversion_info invif;
   invif.name = name;
   inversion_verbose_struct verb_prec = precond_view(verb);
+  const int flags = (hints != 0 && eps < 1.0 && max_iter > 0) ? hints->flags : 0;
+  const bool zero_start = (flags & SOLVE_ZERO_START) != 0;
+  const bool zero_for_precond = (precond != 0 && precond != overwriting_precond());
+  int executed = 0;
   complex<double>* r = allocate_vector<complex<double> >(size);
   complex<double>* z = precond ? allocate_vector<complex<double> >(size) : 0;
-  complex<double>* scratch = allocate_vector<complex<double> >(size);
+  complex<double>* scratch = 0;
   std::vector<complex<double>*> p, Ap;
   std::vector<double> ApNormSq;
-  const double bsqrt = sqrt(norm2sq(phi0, size));
+  double bsq = (hints != 0 && hints->bnorm2 >= 0.0) ? hints->bnorm2 : norm2sq(phi0, size);
+  const double bsqrt = sqrt(bsq);
+  complex<double>* r_in = r;
+  double rsq;
 
-  matrix_vector(scratch, phi, extra_info); invif.ops_count++;
-  caxpbyz(1.0, phi0, -1.0, scratch, r, size);
-  double rsq = norm2sq(r, size);
+  if (zero_start)
+  {
+    invif.ops_count++;           // the reference's A.0
+    r_in = phi0; rsq = bsq;
+  }
+  else
+  {
+    if (hints != 0 && (hints->flags & SOLVE_ZERO_START)) zero_vector(phi, size);
+    scratch = allocate_vector<complex<double> >(size);
+    matrix_vector(scratch, phi, extra_info); invif.ops_count++; executed++;
+    caxpbyz(1.0, phi0, -1.0, scratch, r, size);
+    rsq = norm2sq(r, size);
+  }
 
   int k = 0;
   bool converged = sqrt(rsq) < eps * bsqrt;
@@ -38,15 +61,16 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
   {
     p.push_back(allocate_vector<complex<double> >(size));
     Ap.push_back(allocate_vector<complex<double> >(size));
-    if (precond) { zero_vector(p[0], size); precond(p[0], r, size, precond_info, &verb_prec); }
-    else copy_vector(p[0], r, size);
-    matrix_vector(Ap[0], p[0], extra_info); invif.ops_count++;
+    if (precond) { if (zero_for_precond) zero_vector(p[0], size); precond(p[0], r_in, size, precond_info, &verb_prec); }
+    else copy_vector(p[0], r_in, size);
+    matrix_vector(Ap[0], p[0], extra_info); invif.ops_count++; executed++;
     for (k = 1; k <= max_iter; k++)
     {
       const int c = k - 1;
       // alpha = <Ap|r> / <Ap|Ap> formed on the device; x += alpha p ; r -= alpha Ap ; |r|^2 : one host wait per step
-      double step[4];
-      QMG_CHK(qmg_step_xr_norm(1.0, P(p[c]), P(Ap[c]), P(phi), P(r), size, step));
+      double step[5];
+      QMG_CHK(qmg_krylov_step(1.0, P(p[c]), P(Ap[c]), (zero_start && k == 1) ? 0 : P(phi), P(phi), P(r_in), P(r), 0, size, 0, step));
+      r_in = r;
       rsq = step[0];
       ApNormSq.push_back(step[3]);
       say(verb, VERB_DETAIL, name, "", false, false, k, invif.ops_count, sqrt(rsq) / bsqrt);
@@ -57,8 +81,8 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
       p.push_back(allocate_vector<complex<double> >(size));
       Ap.push_back(allocate_vector<complex<double> >(size));
       complex<double>* dir = r;
-      if (precond) { zero_vector(z, size); precond(z, r, size, precond_info, &verb_prec); dir = z; }
-      matrix_vector(Ap[k], dir, extra_info); invif.ops_count++;
+      if (precond) { if (zero_for_precond) zero_vector(z, size); precond(z, r, size, precond_info, &verb_prec); dir = z; }
+      matrix_vector(Ap[k], dir, extra_info); invif.ops_count++; executed++;
       std::vector<double> beta(2 * k);
       std::vector<const qmg_cplx*> ptrs(k);
       for (int i = 0; i < k; i++) ptrs[i] = P(Ap[i]);
@@ -70,33 +94,46 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
     }
   }
   if (k > max_iter) k = max_iter;
+  // a zero start that took no step (b = 0, or no iterations allowed) still owes the caller its x = 0
+  if (zero_start && ApNormSq.empty()) zero_vector(phi, size);
 
-  matrix_vector(scratch, phi, extra_info); invif.ops_count++;
-  invif.resSq = diffnorm2sq(scratch, phi0, size);
+  invif.ops_count++;
+  if ((flags & SOLVE_NO_FINAL_RESIDUAL) && converged) invif.resSq = rsq;     // converged: nothing downstream reads the true residual
+  else
+  {
+    if (scratch == 0) scratch = allocate_vector<complex<double> >(size);
+    matrix_vector(scratch, phi, extra_info); executed++;
+    invif.resSq = diffnorm2sq(scratch, phi0, size);
+  }
   invif.iter = k;
   invif.success = converged;
   say(verb, VERB_SUMMARY, name, "", true, invif.success, invif.iter, invif.ops_count, sqrt(invif.resSq) / bsqrt);
+  if (hints != 0) hints->executed += executed;
 
   for (size_t i = 0; i < p.size(); i++) { deallocate_vector(&p[i]); deallocate_vector(&Ap[i]); }
   deallocate_vector(&r);
-  deallocate_vector(&scratch);
+  if (scratch != 0) deallocate_vector(&scratch);
   if (z != 0) deallocate_vector(&z);
   return invif;
 }
 
 // Bursts of restart_freq iterations of `one_burst` from the current iterate; tolerance stays relative to |b|.
+// hints: the zero start only holds for the first burst; |b|^2 is computed once for all of them.
 template <class Burst>
 inline inversion_info restarted(const char* name, complex<double>* phi0, int size, int max_iter, double eps, int restart_freq,
-                                inversion_verbose_struct* verb, Burst one_burst)
+                                inversion_verbose_struct* verb, Burst one_burst, SolveHints* hints = 0)
 {
   inversion_info invif, total;
   total.name = name;
-  const double bsqrt = sqrt(norm2sq(phi0, size));
+  SolveHints local((hints != 0) ? hints->flags : 0, (hints != 0) ? hints->bnorm2 : -1.0);
+  if (local.bnorm2 < 0.0) local.bnorm2 = norm2sq(phi0, size);
+  const double bsqrt = sqrt(local.bnorm2);
   inversion_verbose_struct quiet = burst_view(verb);
   do
   {
     const int left = max_iter - total.iter;
-    invif = one_burst(left < restart_freq ? left : restart_freq, &quiet);
+    invif = one_burst(left < restart_freq ? left : restart_freq, &quiet, &local);
+    local.flags &= ~SOLVE_ZERO_START;
     total.iter += invif.iter;
     total.ops_count += invif.ops_count;
     total.resSq = invif.resSq;
@@ -104,7 +141,20 @@ inline inversion_info restarted(const char* name, complex<double>* phi0, int siz
   } while (total.iter < max_iter && !invif.success && sqrt(invif.resSq) > eps * bsqrt);
   total.success = invif.success || sqrt(invif.resSq) <= eps * bsqrt;
   say(verb, VERB_SUMMARY, name, "", true, total.success, total.iter, total.ops_count, sqrt(total.resSq) / bsqrt);
+  if (hints != 0) hints->executed += local.executed;
   return total;
+}
+
+// GCR or flexible GCR, restarted or not (restart_freq == -1), with hints: what the K-cycle calls
+inline inversion_info gcr_solve(complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps, int restart_freq,
+                                matrix_op_cplx matrix_vector, void* extra_info, precond_op_cplx precond, void* precond_info,
+                                inversion_verbose_struct* verb, SolveHints* hints)
+{
+  const char* nm = precond ? "VPGCR" : "GCR";
+  if (restart_freq == -1) return gcr_core(nm, phi, phi0, size, max_iter, eps, matrix_vector, extra_info, precond, precond_info, verb, hints);
+  return restarted(precond ? "Restarted VPGCR" : "Restarted GCR", phi0, size, max_iter, eps, restart_freq, verb,
+    [&](int burst, inversion_verbose_struct* quiet, SolveHints* h) {
+      return gcr_core(nm, phi, phi0, size, burst, eps, matrix_vector, extra_info, precond, precond_info, quiet, h); }, hints);
 }
 
 } // namespace qmg_host
@@ -119,7 +169,8 @@ inline inversion_info minv_vector_gcr_restart(complex<double>* phi, complex<doub
                                               matrix_op_cplx matrix_vector, void* extra_info, inversion_verbose_struct* verb = 0)
 {
   return qmg_host::restarted("Restarted GCR", phi0, size, max_iter, eps, restart_freq, verb,
-    [&](int burst, inversion_verbose_struct* quiet) { return minv_vector_gcr(phi, phi0, size, burst, eps, matrix_vector, extra_info, quiet); });
+    [&](int burst, inversion_verbose_struct* quiet, qmg_host::SolveHints* h) {
+      return qmg_host::gcr_core("GCR", phi, phi0, size, burst, eps, matrix_vector, extra_info, 0, 0, quiet, h); });
 }
 
 #endif

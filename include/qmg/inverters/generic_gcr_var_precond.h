@@ -21,8 +21,8 @@ inline inversion_info minv_vector_gcr_var_precond_restart(complex<double>* phi, 
                                                           inversion_verbose_struct* verb = 0)
 {
   return qmg_host::restarted("Restarted VPGCR", phi0, size, max_iter, eps, restart_freq, verb,
-    [&](int burst, inversion_verbose_struct* quiet) {
-      return minv_vector_gcr_var_precond(phi, phi0, size, burst, eps, matrix_vector, extra_info, precond_matrix_vector, precond_info, quiet); });
+    [&](int burst, inversion_verbose_struct* quiet, qmg_host::SolveHints* h) {
+      return qmg_host::gcr_core("VPGCR", phi, phi0, size, burst, eps, matrix_vector, extra_info, precond_matrix_vector, precond_info, quiet, h); });
 }
 
 #endif

@@ -5,51 +5,104 @@
 // oracle states (oracle/qlinalg_shim/inverters/generic_minres.h) so that iteration counts compare:
 //   r = b - A x ; repeat { p = A r ; alpha = <p|r>/<p|p> ; x += w alpha r ; r -= w alpha p } ; true residual.
 // Per iteration: one operator apply, one fused (dot, norm) pass and one fused (x, r, |r|^2) update
-// -- 3 launches and 2 scalar read-backs instead of 1 + 5 BLAS sweeps.
+// -- 3 launches and 1 scalar read-back instead of 1 + 5 BLAS sweeps.
+//
+// The K-cycle calls the core below with SolveHints (inverter_struct.h): from a zero start the initial residual is the
+// right-hand side itself (no A.0 apply, no copy, no zeroing of x: the first step WRITES x), the final true-residual
+// apply whose result the K-cycle never reads is skipped, and the last permitted iteration updates x only.  Every value
+// that is still computed is formed by the same kernels in the same order, so x is bit-identical to the unhinted call;
+// ops_count keeps reporting what the reference would have counted, hints->executed what was launched.
 #ifndef QMG_B200_MINRES
 #define QMG_B200_MINRES
 
+#include <limits>
 #include "../blas/generic_vector.h"
 #include "inverter_struct.h"
 
-inline inversion_info minv_vector_minres(complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps, double omega,
-                                         matrix_op_cplx matrix_vector, void* extra_info, inversion_verbose_struct* verb = 0)
+namespace qmg_host {
+
+inline inversion_info minres_core(complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps, double omega,
+                                  matrix_op_cplx matrix_vector, void* extra_info, inversion_verbose_struct* verb, SolveHints* hints)
 {
   inversion_info invif;
   invif.name = "MR";
+  // the shortcuts assume the solve cannot stop before its first step (a relative tolerance below one) and takes one
+  const int flags = (hints != 0 && eps < 1.0 && max_iter > 0) ? hints->flags : 0;
+  const bool zero_start = (flags & SOLVE_ZERO_START) != 0;
+  int executed = 0;
   complex<double>* r = allocate_vector<complex<double> >(size);
   complex<double>* p = allocate_vector<complex<double> >(size);
-  const double bsqrt = sqrt(norm2sq(phi0, size));
+  double bsq = (hints != 0 && hints->bnorm2 >= 0.0) ? hints->bnorm2 : -1.0;
+  const complex<double>* r_in = r;
+  double rsq;
 
-  matrix_vector(p, phi, extra_info); invif.ops_count++;
-  caxpbyz(1.0, phi0, -1.0, p, r, size);
-  double rsq = norm2sq(r, size);
+  if (zero_start)
+  {
+    // r = b - A 0 = b exactly; the reference still counts the apply
+    invif.ops_count++;
+    r_in = phi0;
+    rsq = bsq;       // unknown (< 0) until the first step returns |b|^2; the entry test below cannot fire for eps < 1
+  }
+  else
+  {
+    // a caller that promised a zero start did not have to zero x: do it here when the shortcut does not apply
+    if (hints != 0 && (hints->flags & SOLVE_ZERO_START)) zero_vector(phi, size);
+    if (bsq < 0.0) bsq = norm2sq(phi0, size);
+    matrix_vector(p, phi, extra_info); invif.ops_count++; executed++;
+    caxpbyz(1.0, phi0, -1.0, p, r, size);
+    rsq = norm2sq(r, size);
+  }
+  double bsqrt = bsq >= 0.0 ? sqrt(bsq) : std::numeric_limits<double>::quiet_NaN();
 
   int k = 0;
   bool converged = false;
-  if (max_iter <= 0 || sqrt(rsq) < eps * bsqrt) converged = (sqrt(rsq) < eps * bsqrt);
+  bool acc_done = false;
+  complex<double>* acc = (hints != 0) ? hints->accumulate_into : 0;
+  if (!zero_start && (max_iter <= 0 || sqrt(rsq) < eps * bsqrt)) converged = (sqrt(rsq) < eps * bsqrt);
   else for (k = 1; k <= max_iter; k++)
   {
-    matrix_vector(p, r, extra_info); invif.ops_count++;
+    matrix_vector(p, const_cast<complex<double>*>(r_in), extra_info); invif.ops_count++; executed++;
     // alpha = omega <Ar|r> / <Ar|Ar> ; x += alpha r ; r -= alpha A r ; |r|^2 -- alpha is formed on the device, one host wait
     // (x is updated from the old r inside the same thread)
-    double step[4];
-    QMG_CHK(qmg_step_xr_norm(omega, qmg_host::P(r), qmg_host::P(p), qmg_host::P(phi), qmg_host::P(r), size, step));
+    const bool first = zero_start && k == 1;
+    const bool x_only = (flags & SOLVE_LAST_X_ONLY) && k == max_iter;
+    const bool want_b = first && bsq < 0.0 && !x_only;
+    double step[5];
+    QMG_CHK(qmg_krylov_step(omega, P(r_in), P(p), first ? 0 : P(phi), P(x_only && acc != 0 ? acc : phi), P(r_in), P(r),
+                            x_only && acc != 0 ? P(acc) : 0, size, (want_b ? QMG_STEP_WANT_RNORM : 0) | (x_only ? QMG_STEP_X_ONLY : 0), step));
+    r_in = r;
+    if (x_only) { acc_done = (acc != 0); break; }     // nobody reads this residual: no reduction, no host wait
+    if (want_b) { bsq = step[4]; bsqrt = sqrt(bsq); }
     rsq = step[0];
-    qmg_host::say(verb, VERB_DETAIL, "MR", "", false, false, k, invif.ops_count, sqrt(rsq) / bsqrt);
+    say(verb, VERB_DETAIL, "MR", "", false, false, k, invif.ops_count, sqrt(rsq) / bsqrt);
     if (sqrt(rsq) < eps * bsqrt) { converged = true; break; }
   }
   if (k > max_iter) k = max_iter;
+  if (acc != 0 && !acc_done) cxpy(phi, acc, size);
 
-  matrix_vector(p, phi, extra_info); invif.ops_count++;
-  invif.resSq = diffnorm2sq(p, phi0, size);
+  invif.ops_count++;
+  if (flags & SOLVE_NO_FINAL_RESIDUAL) invif.resSq = rsq;      // the recursive residual (of the last step that formed one)
+  else
+  {
+    matrix_vector(p, phi, extra_info); executed++;
+    invif.resSq = diffnorm2sq(p, phi0, size);
+  }
   invif.iter = k;
   invif.success = converged;
-  qmg_host::say(verb, VERB_SUMMARY, "MR", "", true, invif.success, invif.iter, invif.ops_count, sqrt(invif.resSq) / bsqrt);
+  say(verb, VERB_SUMMARY, "MR", "", true, invif.success, invif.iter, invif.ops_count, sqrt(invif.resSq) / bsqrt);
+  if (hints != 0) hints->executed += executed;
 
   deallocate_vector(&r);
   deallocate_vector(&p);
   return invif;
+}
+
+} // namespace qmg_host
+
+inline inversion_info minv_vector_minres(complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps, double omega,
+                                         matrix_op_cplx matrix_vector, void* extra_info, inversion_verbose_struct* verb = 0)
+{
+  return qmg_host::minres_core(phi, phi0, size, max_iter, eps, omega, matrix_vector, extra_info, verb, 0);
 }
 
 #endif

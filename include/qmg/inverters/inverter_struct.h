@@ -18,6 +18,26 @@ struct inversion_info
   inversion_info() : resSq(0.0), iter(0), success(false), ops_count(0) { }
 };
 
+// B200 extension (not in quantum-linalg): what a caller that knows more than the solver signature can say tells the
+// device solvers, so that work whose result is known or never read is not launched.  Used by the K-cycle
+// (multigrid/stateful_multigrid.h); the public minv_vector_* entry points pass none and behave as before.
+namespace qmg_host {
+enum
+{
+  SOLVE_ZERO_START = 1,          // x is zero by contract and its content is NOT read: r0 = b without applying A to zero
+  SOLVE_NO_FINAL_RESIDUAL = 2,   // do not recompute |b - A x| at exit (resSq then holds the recursive value)
+  SOLVE_LAST_X_ONLY = 4,         // smoother: the last permitted iteration updates x only (its residual is never read)
+};
+struct SolveHints
+{
+  int flags;
+  double bnorm2;                            // |b|^2 when the caller has just computed it, else < 0
+  std::complex<double>* accumulate_into;    // MR: add the solution to this vector as well (folded into the last step)
+  int executed;                             // out: operator applications actually launched (ops_count keeps the reference's count)
+  SolveHints(int f = 0, double b2 = -1.0) : flags(f), bnorm2(b2), accumulate_into(0), executed(0) { }
+};
+}
+
 #ifndef QLINALG_FCN_POINTER
 #define QLINALG_FCN_POINTER
 typedef void (*matrix_op_real)(double*, double*, void*);

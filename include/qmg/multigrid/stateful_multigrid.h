@@ -7,6 +7,7 @@
 #ifndef QMG_B200_STATEFUL_MULTIGRID
 #define QMG_B200_STATEFUL_MULTIGRID
 
+#include <cstdlib>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -57,9 +58,12 @@ public:
     int counts[4];
     int iterations;
     int total;
+    long executed;     // B200 extension: operator applications actually launched (the K-cycle skips applies whose result is known or unread)
   public:
     DslashTrackerMG() { reset_tracker(); }
     void add_tracker_count(QMGDslashType type, int accum) { counts[type] += accum; total += accum; }
+    void add_executed_count(int accum) { executed += accum; }
+    long get_executed_count() { return executed; }
     void add_iterations_count(int accum) { iterations += accum; }
     void shift_all_to_nullvec()
     {
@@ -70,7 +74,7 @@ public:
     int get_tracker_count(QMGDslashType type) { return counts[type]; }
     int get_total_count() { return total; }
     int get_iterations_count() { return iterations; }
-    void reset_tracker() { counts[0] = counts[1] = counts[2] = counts[3] = 0; total = 0; iterations = 0; }
+    void reset_tracker() { counts[0] = counts[1] = counts[2] = counts[3] = 0; total = 0; iterations = 0; executed = 0; }
   };
 
   // the coarsest solve (stateful_multigrid.h:204-241)
@@ -92,6 +96,7 @@ protected:
   int coarsest_deflated;
   complex<double>* coarsest_evals;
   complex<double>** coarsest_evecs;
+  bool fused_cycle;
 
   static void check_level_solve(LevelSolveMG* s, const char* where)
   {
@@ -109,7 +114,12 @@ protected:
 public:
   StatefulMultigridMG(Lattice2D* in_lat, Stencil2D* in_stencil, CoarsestSolveMG* in_coarsest_solve)
     : MultigridMG(in_lat, in_stencil), current_level(0), coarsest_solve(in_coarsest_solve), coarsest_deflated(0), coarsest_evals(0), coarsest_evecs(0)
-  { dslash_tracker_list.push_back(new DslashTrackerMG()); }
+  {
+    dslash_tracker_list.push_back(new DslashTrackerMG());
+    const char* e = getenv("QMG_FUSED_CYCLE");
+    fused_cycle = !(e != 0 && e[0] == '0');
+    qmg_host::overwriting_precond() = mg_preconditioner;    // writes every element of its output: the solvers need not zero it
+  }
   ~StatefulMultigridMG()
   {
     for (size_t i = 0; i < dslash_tracker_list.size(); i++) delete dslash_tracker_list[i];
@@ -255,6 +265,13 @@ public:
   // ---- counters (stateful_multigrid.h:500-609)
   void add_tracker_count(QMGDslashType type, int accum, int i) { if (tracker_ok(i, "update tracker")) dslash_tracker_list[i]->add_tracker_count(type, accum); }
   void add_iterations_count(int accum, int i) { if (tracker_ok(i, "update tracker")) dslash_tracker_list[i]->add_iterations_count(accum); }
+  // B200 extension: applications launched, beside the reference's counts (which include the skipped A.0 and unread residual applies)
+  void add_executed_count(int accum, int i) { if (tracker_ok(i, "update tracker")) dslash_tracker_list[i]->add_executed_count(accum); }
+  long get_executed_count(int i) { return tracker_ok(i, "query tracker") ? dslash_tracker_list[i]->get_executed_count() : -1; }
+  // 1 (default): zero-start / unread-residual shortcuts and one-pass residual, restrict and prolong-correct steps;
+  // 0: the reference's sequence of separate sweeps, launch for launch (what round 1 ran).  Results are bit-identical.
+  void set_fused_cycle(bool on) { fused_cycle = on; }
+  bool get_fused_cycle() { return fused_cycle; }
   void shift_all_to_nullvec(int i) { if (tracker_ok(i, "shift to null vectors")) dslash_tracker_list[i]->shift_all_to_nullvec(); }
   int get_tracker_count(QMGDslashType type, int i) { return tracker_ok(i, "query tracker") ? dslash_tracker_list[i]->get_tracker_count(type) : -1; }
   int get_total_count(int i) { return tracker_ok(i, "query tracker") ? dslash_tracker_list[i]->get_total_count() : -1; }
@@ -283,34 +300,52 @@ protected:
     caxpy(s->extra_shift, in, out, s->length);
   }
 
-  // z = MR_smooth(A_type, b) from a zero start; with cgne the smoother runs on A A^dag and z = A^dag z'.  Returns the operator applications spent.
+  // z = MR_smooth(A_type, b) from a zero start; with cgne the smoother runs on A A^dag and z = A^dag z'.  Returns the operator
+  // applications the reference counts; `executed` receives those launched.  hints == 0: z must be zero on entry.
   static int smooth(Stencil2D* op, ArrayStorageMG<complex<double> >* pool, QMGStencilType type, bool cgne, int iters, double tol,
-                    complex<double>* z, complex<double>* b, int n_solve, long n_full)
+                    complex<double>* z, complex<double>* b, int n_solve, long n_full, qmg_host::SolveHints* hints, int& executed)
   {
     if (cgne && (type == QMG_MATVEC_ORIGINAL || type == QMG_MATVEC_RIGHT_JACOBI))
     {
       const bool orig = (type == QMG_MATVEC_ORIGINAL);
       complex<double>* zp = pool->check_out();
-      zero_vector(zp, n_full);
-      inversion_info inv = minv_vector_minres(zp, b, n_solve, iters, tol, 0.85,
-                                              Stencil2D::get_apply_function(orig ? QMG_MATVEC_M_MDAGGER : QMG_MATVEC_RBJ_M_MDAGGER), (void*)op);
+      qmg_host::SolveHints h2(hints != 0 ? (hints->flags & ~qmg_host::SOLVE_LAST_X_ONLY) : 0);
+      if (hints == 0) zero_vector(zp, n_full);
+      inversion_info inv = qmg_host::minres_core(zp, b, n_solve, iters, tol, 0.85,
+                                                 Stencil2D::get_apply_function(orig ? QMG_MATVEC_M_MDAGGER : QMG_MATVEC_RBJ_M_MDAGGER), (void*)op, 0, hints != 0 ? &h2 : 0);
+      if (hints != 0) zero_vector(z, n_full);      // apply_M accumulates
       op->apply_M(z, zp, orig ? QMG_MATVEC_DAGGER : QMG_MATVEC_RBJ_DAGGER);
+      if (hints != 0 && hints->accumulate_into != 0) cxpy(z, hints->accumulate_into, n_solve);
       pool->check_in(zp);
+      executed += (hints != 0) ? 2 * h2.executed + 1 : 2 * inv.ops_count + 1;
       return 2 * inv.ops_count + 1;
     }
-    inversion_info inv = minv_vector_minres(z, b, n_solve, iters, tol, 0.85, Stencil2D::get_apply_function(type), (void*)op);
+    inversion_info inv = qmg_host::minres_core(z, b, n_solve, iters, tol, 0.85, Stencil2D::get_apply_function(type), (void*)op, 0, hints);
+    executed += (hints != 0) ? hints->executed : inv.ops_count;
     return inv.ops_count;
   }
 
 public:
   // One K-cycle application at the current level: lhs ~ A^-1 rhs.  Signature of a quantum-linalg preconditioner;
   // extra_data is the StatefulMultigridMG (stateful_multigrid.h:734).
+  //
+  // The steps and their order are the reference's (:840-1051).  With fused_cycle (default) the work whose result is
+  // known or never read is not launched -- the smoothers and coarse solves start from a zero vector, so their initial
+  // residual is the right-hand side and A.0 is not applied (:860, :915-990); the true-residual apply at the end of each
+  // of them feeds only inversion_info::resSq, which this function never reads (:854,:861,:996 use ops_count and iter) --
+  // and steps the reference spells as several sweeps run as one: r = b - A z (:863-866, :1023-1029), zero + restrict
+  // (:876-878), zero + prolong + z1 + z2 (:1005-1019), lhs += z3 (:1050).  Every number that IS computed is formed by
+  // the same kernel arithmetic in the same order: lhs is bit-identical with fused_cycle on and off.  The trackers keep
+  // the reference's operator counts; add_executed_count records what was launched.
   static void mg_preconditioner(complex<double>* lhs, complex<double>* rhs, int size, void* extra_data, inversion_verbose_struct* verb)
   {
     (void)size;
     StatefulMultigridMG* mg = (StatefulMultigridMG*)extra_data;
     const int level = mg->get_multigrid_level();
     const int nlev = mg->get_num_levels();
+    const bool fuse = mg->fused_cycle;
+    using qmg_host::SolveHints;
+    using qmg_host::SOLVE_ZERO_START; using qmg_host::SOLVE_NO_FINAL_RESIDUAL; using qmg_host::SOLVE_LAST_X_ONLY;
 
     LevelSolveMG* ls = mg->get_level_solve();
     if (ls == 0) { std::cout << "[QMG-MG-SOLVE-ERROR]: Level solve for level " << level << " does not exist.\n"; return; }
@@ -348,20 +383,29 @@ public:
     }
     matrix_op_cplx coarse_op = Stencil2D::get_apply_function(ctype);
     const int nc_solve = (int)(ctype == QMG_MATVEC_RIGHT_SCHUR ? nc / 2 : nc);
+    // the smoother shortcuts: zero start, no unread residual; its last step may skip r only when the tolerance cannot stop it earlier anyway
+    const int smooth_flags = SOLVE_ZERO_START | SOLVE_NO_FINAL_RESIDUAL | SOLVE_LAST_X_ONLY;
 
     // 1. pre-smooth: z1 ~ A^-1 rhs, r1 = rhs - A z1
     complex<double>* z1 = fpool->check_out();
     complex<double>* r1 = fpool->check_out();
-    zero_vector(z1, nf);
+    if (!fuse) zero_vector(z1, nf);
+    else if (nf_solve != nf) zero_vector(z1 + nf_solve, nf - nf_solve);     // Schur: the odd half is read as zero further down
     if (ls->pre_iters > 0)
     {
-      const int ops = smooth(fine, fpool, ftype, ls->pre_cgne, ls->pre_iters, ls->pre_tol, z1, rhs, nf_solve, nf);
+      SolveHints hints(smooth_flags);
+      int executed = 0;
+      const int ops = smooth(fine, fpool, ftype, ls->pre_cgne, ls->pre_iters, ls->pre_tol, z1, rhs, nf_solve, nf, fuse ? &hints : 0, executed);
       mg->add_tracker_count(QMG_DSLASH_TYPE_PRESMOOTH, ops, level);
-      complex<double>* Az = fpool->check_out();
-      fine_op(Az, z1, (void*)fine);
+      if (!(fuse && fine->apply_residual(r1, rhs, z1, ftype)))
+      {
+        complex<double>* Az = fpool->check_out();
+        fine_op(Az, z1, (void*)fine);
+        caxpbyz(1.0, rhs, -1.0, Az, r1, nf_solve);
+        fpool->check_in(Az);
+      }
       mg->add_tracker_count(QMG_DSLASH_TYPE_PRESMOOTH, 1, level);
-      caxpbyz(1.0, rhs, -1.0, Az, r1, nf_solve);
-      fpool->check_in(Az);
+      mg->add_executed_count(executed + 1, level);
     }
     else
     {
@@ -371,23 +415,37 @@ public:
 
     // 2. restrict the residual and bring it to the form the coarse system is solved in
     complex<double>* r_c = cpool->check_out();
-    zero_vector(r_c, nc);
-    transfer->restrict_f2c(r1, r_c);
+    if (fuse) transfer->restrict_f2c_overwrite(r1, r_c);
+    else { zero_vector(r_c, nc); transfer->restrict_f2c(r1, r_c); }
     fpool->check_in(r1);
-    const double rnorm = sqrt(norm2sq(r_c, nc));
-    complex<double>* r_c_prep = cpool->check_out();
-    zero_vector(r_c_prep, nc);
-    coarse->prepare_M(r_c_prep, r_c, ctype);
-    const double rnorm_prep = sqrt(norm2sq(r_c_prep, nc));
+    const double rsq_c = norm2sq(r_c, nc);
+    const double rnorm = sqrt(rsq_c);
+    // prepare_M is a copy for every operator flavour except Schur and the M^dag M normal equations (stencil_2d.h:2455-2489)
+    const bool prep_is_copy = !(ctype == QMG_MATVEC_RIGHT_SCHUR || ctype == QMG_MATVEC_MDAGGER_M || ctype == QMG_MATVEC_RBJ_MDAGGER_M);
+    complex<double>* r_c_prep = r_c;
+    double rsq_prep = rsq_c;
+    if (!(fuse && prep_is_copy))
+    {
+      r_c_prep = cpool->check_out();
+      zero_vector(r_c_prep, nc);
+      coarse->prepare_M(r_c_prep, r_c, ctype);
+      rsq_prep = norm2sq(r_c_prep, nc);
+    }
+    const double rnorm_prep = sqrt(rsq_prep);
     const double tol = c_tol * rnorm / rnorm_prep;
 
     // 3. coarse solve from a zero start
     complex<double>* e_c = cpool->check_out();
-    zero_vector(e_c, nc);
     inversion_info inv;
+    int coarse_executed = -1;
+    const bool normal = coarsest && (ctype == QMG_MATVEC_M_MDAGGER || ctype == QMG_MATVEC_MDAGGER_M || ctype == QMG_MATVEC_RBJ_M_MDAGGER || ctype == QMG_MATVEC_RBJ_MDAGGER_M);
+    // zero-start hints for the GCR family; |b|^2 is the norm just taken when it ran over the same elements
+    SolveHints chints(SOLVE_ZERO_START | SOLVE_NO_FINAL_RESIDUAL, nc_solve == nc ? rsq_prep : -1.0);
+    const bool hinted = fuse && !normal;
+    if (!hinted) zero_vector(e_c, nc);
+    else if (nc_solve != nc) zero_vector(e_c + nc_solve, nc - nc_solve);
     if (coarsest)
     {
-      const bool normal = (ctype == QMG_MATVEC_M_MDAGGER || ctype == QMG_MATVEC_MDAGGER_M || ctype == QMG_MATVEC_RBJ_M_MDAGGER || ctype == QMG_MATVEC_RBJ_MDAGGER_M);
       ShiftedFunctionStruct shifted;
       matrix_op_cplx op = coarse_op; void* op_data = (void*)coarse;
       if (normal && mg->get_coarsest_solve()->normal_shift != 0.0)
@@ -409,8 +467,11 @@ public:
         }
       }
       if (!normal)
-        inv = (c_restart == -1) ? minv_vector_gcr(e_c, r_c_prep, nc_solve, c_iters, tol, op, op_data, &verb2)
-                                : minv_vector_gcr_restart(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, op, op_data, &verb2);
+      {
+        if (hinted) { inv = qmg_host::gcr_solve(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, op, op_data, 0, 0, &verb2, &chints); coarse_executed = chints.executed; }
+        else inv = (c_restart == -1) ? minv_vector_gcr(e_c, r_c_prep, nc_solve, c_iters, tol, op, op_data, &verb2)
+                                     : minv_vector_gcr_restart(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, op, op_data, &verb2);
+      }
       else
         inv = (c_restart == -1) ? minv_vector_cg(e_c, r_c_prep, nc_solve, c_iters, tol, op, op_data, &verb2)
                                 : minv_vector_cg_restart(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, op, op_data, &verb2);
@@ -418,42 +479,62 @@ public:
     else
     {
       mg->go_coarser();
-      inv = (c_restart == -1) ? minv_vector_gcr_var_precond(e_c, r_c_prep, nc_solve, c_iters, tol, coarse_op, (void*)coarse, mg_preconditioner, (void*)mg, &verb2)
-                              : minv_vector_gcr_var_precond_restart(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, coarse_op, (void*)coarse, mg_preconditioner, (void*)mg, &verb2);
+      if (hinted) { inv = qmg_host::gcr_solve(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, coarse_op, (void*)coarse, mg_preconditioner, (void*)mg, &verb2, &chints); coarse_executed = chints.executed; }
+      else inv = (c_restart == -1) ? minv_vector_gcr_var_precond(e_c, r_c_prep, nc_solve, c_iters, tol, coarse_op, (void*)coarse, mg_preconditioner, (void*)mg, &verb2)
+                                   : minv_vector_gcr_var_precond_restart(e_c, r_c_prep, nc_solve, c_iters, tol, c_restart, coarse_op, (void*)coarse, mg_preconditioner, (void*)mg, &verb2);
       mg->go_finer();
     }
     mg->add_tracker_count(QMG_DSLASH_TYPE_KRYLOV, inv.ops_count, level + 1);
+    mg->add_executed_count(coarse_executed >= 0 ? coarse_executed : inv.ops_count, level + 1);
     mg->add_iterations_count(inv.iter, level + 1);
-    cpool->check_in(r_c_prep);
+    if (r_c_prep != r_c) cpool->check_in(r_c_prep);
 
     // 4. undo the preparation, prolong, correct: lhs = z1 + P e
-    complex<double>* e_full = cpool->check_out();
-    zero_vector(e_full, nc);
-    coarse->reconstruct_M(e_full, e_c, r_c, ctype);
+    // reconstruct_M is a copy for the flavours whose solution IS the unknown (stencil_2d.h:2492-2527)
+    const bool recon_is_copy = (ctype == QMG_MATVEC_ORIGINAL || ctype == QMG_MATVEC_DAGGER || ctype == QMG_MATVEC_MDAGGER_M || ctype == QMG_MATVEC_RBJ_DAGGER);
+    complex<double>* e_full = e_c;
+    if (!(fuse && recon_is_copy))
+    {
+      e_full = cpool->check_out();
+      zero_vector(e_full, nc);
+      coarse->reconstruct_M(e_full, e_c, r_c, ctype);
+    }
     cpool->check_in(r_c);
-    cpool->check_in(e_c);
-    complex<double>* z2 = fpool->check_out();
-    zero_vector(z2, nf);
-    transfer->prolong_c2f(e_full, z2);
-    if (ctype == QMG_MATVEC_RIGHT_SCHUR) zero_vector(z2 + nf / 2, nf / 2);   // stateful_multigrid.h:1012
+    if (e_full != e_c) cpool->check_in(e_c);
+    if (fuse && ftype != QMG_MATVEC_RIGHT_SCHUR && transfer->can_fuse_prolong())
+      transfer->prolong_c2f_add(e_full, z1, lhs);
+    else
+    {
+      complex<double>* z2 = fpool->check_out();
+      zero_vector(z2, nf);
+      transfer->prolong_c2f(e_full, z2);
+      if (ctype == QMG_MATVEC_RIGHT_SCHUR) zero_vector(z2 + nf / 2, nf / 2);   // stateful_multigrid.h:1012
+      cxpyz(z1, z2, lhs, nf_solve);
+      fpool->check_in(z2);
+    }
     cpool->check_in(e_full);
-    cxpyz(z1, z2, lhs, nf_solve);
     fpool->check_in(z1);
-    fpool->check_in(z2);
 
     // 5. post-smooth on the new residual
     if (ls->post_iters > 0)
     {
-      complex<double>* Ax = fpool->check_out();
       complex<double>* r2 = fpool->check_out();
-      fine_op(Ax, lhs, (void*)fine);
-      caxpbyz(1.0, rhs, -1.0, Ax, r2, nf_solve);
-      fpool->check_in(Ax);
+      if (!(fuse && fine->apply_residual(r2, rhs, lhs, ftype)))
+      {
+        complex<double>* Ax = fpool->check_out();
+        fine_op(Ax, lhs, (void*)fine);
+        caxpbyz(1.0, rhs, -1.0, Ax, r2, nf_solve);
+        fpool->check_in(Ax);
+      }
       complex<double>* z3 = fpool->check_out();
-      zero_vector(z3, nf);
-      const int ops = smooth(fine, fpool, ftype, ls->post_cgne, ls->post_iters, ls->post_tol, z3, r2, nf_solve, nf);
+      SolveHints hints(smooth_flags);
+      hints.accumulate_into = lhs;        // lhs += z3 rides on the smoother's last step
+      int executed = 0;
+      if (!fuse) zero_vector(z3, nf);
+      const int ops = smooth(fine, fpool, ftype, ls->post_cgne, ls->post_iters, ls->post_tol, z3, r2, nf_solve, nf, fuse ? &hints : 0, executed);
       mg->add_tracker_count(QMG_DSLASH_TYPE_POSTSMOOTH, ops, level);
-      cxpy(z3, lhs, nf_solve);
+      mg->add_executed_count(executed + 1, level);
+      if (!fuse) cxpy(z3, lhs, nf_solve);
       fpool->check_in(r2);
       fpool->check_in(z3);
     }

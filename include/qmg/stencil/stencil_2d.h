@@ -346,6 +346,30 @@ public:
   // lhs = M rhs in one pass, nothing read from lhs (what the apply_stencil_2D_* wrappers need)
   void apply_M_overwrite(complex<double>* lhs, complex<double>* rhs) { launch(QMG_APPLY_ALL, 15, lhs, rhs); }
 
+  // B200 extension used by the K-cycle: lhs = b - M_type rhs in ONE launch for the single-launch operator flavours
+  // (original, right block Jacobi); returns false -- nothing done -- for the others, whose callers apply and subtract.
+  bool apply_residual(complex<double>* lhs, complex<double>* b, complex<double>* rhs, QMGStencilType type)
+  {
+    if (type == QMG_MATVEC_ORIGINAL)
+    {
+      qmg_stencil_desc d = describe();
+      int pieces = QMG_APPLY_ALL;
+      if (clover == 0) pieces &= ~QMG_APPLY_CLOVER;
+      if (hopping == 0) pieces &= ~(QMG_APPLY_HOP_TO_EVEN | QMG_APPLY_HOP_TO_ODD);
+      QMG_CHK(qmg_stencil_apply_residual(&d, pieces, 15, qmg_host::P(lhs), qmg_host::P(rhs), qmg_host::P(b)));
+      return true;
+    }
+    if (type == QMG_MATVEC_RIGHT_JACOBI && built_rbjacobi)
+    {
+      qmg_stencil_desc d = describe(0, rbjacobi_hopping, 0.0, 0.0, 0.0);
+      int pieces = QMG_APPLY_IDENTITY_CLOVER;
+      if (rbjacobi_hopping != 0) pieces |= QMG_APPLY_HOP_TO_EVEN | QMG_APPLY_HOP_TO_ODD;
+      QMG_CHK(qmg_stencil_apply_residual(&d, pieces, 15, qmg_host::P(lhs), qmg_host::P(rhs), qmg_host::P(b)));
+      return true;
+    }
+    return false;
+  }
+
   // ---- chirality (overridden by the operators)
   static int get_dof(int i = 0) { (void)i; return -1; }
   static chirality_state has_chirality() { return QMG_CHIRAL_UNKNOWN; }

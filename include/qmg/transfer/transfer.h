@@ -203,6 +203,20 @@ public:
   // coarse += R fine (accumulates, transfer.h:487)
   void restrict_f2c(complex<double>* fine_cv, complex<double>* coarse_cv)
   { restrict_f2c(fine_cv, coarse_cv, restrict_null_vectors == 0 ? null_vectors : restrict_null_vectors, num_null_vec); }
+  // B200 extensions used by the K-cycle: the same sums in one pass each.
+  // coarse = R fine, written outright (zero_vector + restrict_f2c)
+  void restrict_f2c_overwrite(complex<double>* fine_cv, complex<double>* coarse_cv)
+  {
+    complex<double>** vecs = restrict_null_vectors == 0 ? null_vectors : restrict_null_vectors;
+    QMG_CHK(qmg_restrict_overwrite(&desc, reinterpret_cast<const qmg_cplx* const*>(vecs), num_null_vec, qmg_host::P(fine_cv), qmg_host::P(coarse_cv)));
+  }
+  // fine_out = base + P coarse (zero_vector + prolong_c2f + cxpyz); at most 8 null vectors, see can_fuse_prolong
+  bool can_fuse_prolong() const { return num_null_vec <= 8; }
+  void prolong_c2f_add(complex<double>* coarse_cv, complex<double>* base_cv, complex<double>* fine_out)
+  {
+    QMG_CHK(qmg_prolong_add(&desc, reinterpret_cast<const qmg_cplx* const*>(null_vectors), num_null_vec, qmg_host::P(coarse_cv),
+                            qmg_host::P(base_cv), qmg_host::P(fine_out)));
+  }
   bool is_symmetric() { return restrict_null_vectors == 0; }
   bool has_decompositions() { return is_symmetric() ? (block_cholesky != 0) : (block_L != 0 && block_U != 0); }
   void copy_cholesky(complex<double>* save_cholesky)

@@ -139,6 +139,11 @@ int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
 int qmg_stencil_apply_host(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs_host, const qmg_cplx* rhs_host,
                            qmg_cplx* dev_lhs, qmg_cplx* dev_rhs, int rows_per_chunk);
 
+/* lhs = b - A rhs in the same single pass (the residual every smoother and K-cycle stage forms as apply + caxpbyz,
+ * multigrid/stateful_multigrid.h:863-866,1023-1029): b is read once, A rhs never touches memory.  lhs may alias b, not rhs;
+ * QMG_APPLY_ACCUMULATE is not allowed.  Bit-identical to qmg_stencil_apply followed by qmg_caxpbyz(1, b, -1, A rhs, lhs). */
+int qmg_stencil_apply_residual(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs, const qmg_cplx* b);
+
 /* result2 = { sum |hopping_{-mu}(x) - s s conj(hopping_{+mu}(x-mu))^T|^2 over sites and mu, sum |hopping|^2 }: how far the
  * stored backward blocks are from the gamma5-hermitian relation (see qmg_stencil_desc.gamma5_hermitian). */
 int qmg_stencil_gamma5_deviation(const qmg_stencil_desc* st, double* result2);
@@ -216,6 +221,17 @@ int qmg_update_xr_norm(double ar, double ai, const qmg_cplx* p, const qmg_cplx* 
 /* One MR / GCR step with a single host wait: alpha = omega <q|r>/<q|q> formed on the device, x += alpha p, r -= alpha q;
  * result4 = { |r|^2, Re<q|r>, Im<q|r>, <q|q> }.  Bit-identical to qmg_dot_norm(q, r) + qmg_update_xr_norm(alpha, p, q, x, r). */
 int qmg_step_xr_norm(double omega, const qmg_cplx* p, const qmg_cplx* q, qmg_cplx* x, qmg_cplx* r, long n, double* result4);
+/* The general MR / GCR step (qmg_step_xr_norm with the first and last steps of a solve folded in):
+ *   alpha = omega <q|r_in>/<q|q> ;  t = (x_in ? x_in : 0) + alpha p ;  x_out = acc ? acc + t : t ;
+ *   r_out = r_in - alpha q ;  |r_out|^2.
+ * x_in NULL: first step from a zero start (x_out is written, never read).  r_in != r_out: the same first step reading the
+ * right-hand side itself.  acc: folds the "lhs += z" after a smoother (stateful_multigrid.h:1050) into its last step.
+ * flags: QMG_STEP_WANT_RNORM also returns |r_in|^2 (read anyway); QMG_STEP_X_ONLY skips r_out and every reduction
+ * read-back (the last step of a smoother whose residual nobody reads) -- result5 is then untouched.
+ * result5 = { |r_out|^2, Re<q|r_in>, Im<q|r_in>, <q|q>, |r_in|^2 }.  Without flags bit-identical to qmg_step_xr_norm. */
+enum { QMG_STEP_WANT_RNORM = 1, QMG_STEP_X_ONLY = 2 };
+int qmg_krylov_step(double omega, const qmg_cplx* p, const qmg_cplx* q, const qmg_cplx* x_in, qmg_cplx* x_out,
+                    const qmg_cplx* r_in, qmg_cplx* r_out, const qmg_cplx* acc, long n, int flags, double* result5);
 /* y += sum_j a_j xs[j]   (GCR: p_k += sum beta_i p_i) ; a: HOST 2k doubles; xs: HOST array of k device pointers */
 int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y, long n);
 /* y = x0 + sum_j a_j xs[j]   (GCR: p_k = r + sum beta_i p_i without a separate copy); x0 == y allowed */
@@ -258,6 +274,13 @@ int qmg_prolong(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host
                 const qmg_cplx* coarse, qmg_cplx* fine);     /* fine += P coarse  (transfer.h:455-480) */
 int qmg_restrict(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec,
                  const qmg_cplx* fine, qmg_cplx* coarse);    /* coarse += P^dag fine (transfer.h:487-511) */
+/* coarse = P^dag fine, written outright (zero_vector + restrict_f2c, stateful_multigrid.h:876-878, in one pass); nvec == ncc */
+int qmg_restrict_overwrite(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec,
+                           const qmg_cplx* fine, qmg_cplx* coarse);
+/* fine_out = base + P coarse (base NULL: P coarse): zero_vector + prolong_c2f + cxpyz (stateful_multigrid.h:1005-1019) in
+ * one pass, the sum formed from zero first so the result is bit-identical; nvec <= 8; fine_out may alias base */
+int qmg_prolong_add(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec,
+                    const qmg_cplx* coarse, const qmg_cplx* base, qmg_cplx* fine_out);
 /* one pass of per-aggregate Gram-Schmidt, in place (transfer.h:514-607);
  * cholesky: optional V_c*ncc*ncc output of the triangular factor (:555-594) or NULL */
 int qmg_block_orthonormalize(const qmg_transfer_desc* t, qmg_cplx* const* nullvecs_host, int nvec, qmg_cplx* cholesky);

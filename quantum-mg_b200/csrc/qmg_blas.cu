@@ -428,6 +428,81 @@ int qmg_step_xr_norm(double omega, const qmg_cplx* p_, const qmg_cplx* q_, qmg_c
   return 0;
 }
 
+// The general Krylov step behind the K-cycle's smoothers and (flexible) GCR solves: the same two kernels as
+// qmg_step_xr_norm -- so every sum is formed in the same order and a step without flags is bit-identical to it -- with
+// the start-up and wind-down work of a solve folded in:
+//   alpha = omega <q|r_in> / <q|q>
+//   t = (x_in ? x_in : 0) + alpha p ;  x_out = (acc ? acc + t : t)
+//   r_out = r_in - alpha q ;  |r_out|^2                       (skipped with QMG_STEP_X_ONLY: no reduction, no host wait)
+// x_in == NULL is the first step of a solve from a zero start (x is written, never read, so nobody has to zero it);
+// r_in != r_out is the same first step reading the right-hand side in place of a copied residual; acc folds the
+// "lhs += z" that follows a smoother into its last step.  QMG_STEP_WANT_RNORM adds |r_in|^2 (the |b|^2 every solver
+// needs) to the dot-product pass, which reads r_in anyway.
+// result5 = { |r_out|^2, Re<q|r_in>, Im<q|r_in>, <q|q>, |r_in|^2 }; with QMG_STEP_X_ONLY nothing is returned.
+int qmg_krylov_step(double omega, const qmg_cplx* p_, const qmg_cplx* q_, const qmg_cplx* x_in_, qmg_cplx* x_out_,
+                    const qmg_cplx* r_in_, qmg_cplx* r_out_, const qmg_cplx* acc_, long n, int flags, double* result5)
+{
+  QMG_REQUIRE_INIT();
+  if (n <= 0) return fail_msg("qmg_krylov_step: empty vector");
+  Runtime& rtm = rt();
+  const cd* p = CCD(p_); const cd* q = CCD(q_); const cd* xin = CCD(x_in_); cd* x = CD(x_out_);
+  const cd* rin = CCD(r_in_); cd* r = CD(r_out_); const cd* accv = CCD(acc_);
+  double* dres = rtm.d_result + 64;                    // device slot of the dot products
+  double* aux = rtm.h_result + 256;                    // mapped host slot the second kernel copies them to
+  const bool want_rnorm = (flags & QMG_STEP_WANT_RNORM) != 0;
+  int rc;
+  if (want_rnorm)
+    rc = launch_reduce_keep<4>(n, [=] __device__(long i, double (&acc)[4]) {
+      cd a = q[i], b = rin[i];
+      acc[0] += a.x * b.x + a.y * b.y;
+      acc[1] += a.x * b.y - a.y * b.x;
+      acc[2] += a.x * a.x + a.y * a.y;
+      acc[3] += b.x * b.x + b.y * b.y;
+    }, dres);
+  else
+    rc = launch_reduce_keep<3>(n, [=] __device__(long i, double (&acc)[3]) {
+      cd a = q[i], b = rin[i];
+      acc[0] += a.x * b.x + a.y * b.y;
+      acc[1] += a.x * b.y - a.y * b.x;
+      acc[2] += a.x * a.x + a.y * a.y;
+    }, dres);
+  if (rc) return rc;
+  if (flags & QMG_STEP_X_ONLY)
+    return launch_ew(n, [=] __device__(long i) {
+      const double d0 = dres[0], d1 = dres[1], d2 = dres[2];
+      const cd a = cmake(__ddiv_rn(__dmul_rn(omega, d0), d2), __ddiv_rn(__dmul_rn(omega, d1), d2));
+      cd xi = (xin != nullptr) ? xin[i] : cmake(0.0, 0.0);
+      cfma(xi, a, p[i]);
+      if (accv != nullptr) xi = cadd(accv[i], xi);
+      x[i] = xi;
+    });
+  double out[1];
+  rc = launch_reduce<1>(n, [=] __device__(long i, double (&acc)[1]) {
+    const double d0 = dres[0], d1 = dres[1], d2 = dres[2];
+    const cd a = cmake(__ddiv_rn(__dmul_rn(omega, d0), d2), __ddiv_rn(__dmul_rn(omega, d1), d2));
+    const cd ma = cmake(-a.x, -a.y);
+    if (i == 0) { aux[0] = d0; aux[1] = d1; aux[2] = d2; if (want_rnorm) aux[3] = dres[3]; __threadfence_system(); }
+    cd pi = p[i];
+    cd ri = rin[i];
+    cd xi = (xin != nullptr) ? xin[i] : cmake(0.0, 0.0);
+    cfma(xi, a, pi);
+    if (accv != nullptr) xi = cadd(accv[i], xi);
+    x[i] = xi;
+    cfma(ri, ma, q[i]); r[i] = ri;
+    acc[0] += ri.x * ri.x + ri.y * ri.y;
+  }, out);
+  if (rc) return rc;
+  result5[0] = out[0];
+  if (rtm.publish_now) { result5[1] = aux[0]; result5[2] = aux[1]; result5[3] = aux[2]; result5[4] = want_rnorm ? aux[3] : 0.0; }
+  else
+  {
+    // copy-and-synchronise mode: the stream has been synchronised by the fetch above
+    QMG_CUDA(cudaMemcpy(result5 + 1, dres, sizeof(double) * (want_rnorm ? 4 : 3), cudaMemcpyDeviceToHost));
+    if (!want_rnorm) result5[4] = 0.0;
+  }
+  return 0;
+}
+
 } // extern "C"
 
 // ------------------------------------------------------- time-slice reductions --

@@ -114,7 +114,7 @@ int ring_exchange(const cd* lo, const cd* hi, cd* ym, cd* yp, size_t first, size
 __global__ void __launch_bounds__(256) halo_p2p_kernel(const cd* __restrict__ field, int rowlen, long half_elems, int Y, int parity_mask,
                                                        cd* up_ym, cd* down_yp, unsigned long long* up_flag, unsigned long long* down_flag,
                                                        const unsigned long long* my_flags, unsigned long long seq, unsigned int* counter, int rank,
-                                                       long long watchdog_cycles)
+                                                       long long watchdog_cycles, unsigned long long* host_err)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 2 * rowlen)
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) halo_p2p_kernel(const cd* __restrict__ fi
   {
     const long long t0 = clock64();
     while (ld_sys_u64(my_flags + threadIdx.x) < seq)
-      if (clock64() - t0 > watchdog_cycles) { printf("[QMG-ERROR]: rank %d gave up waiting for a halo row (exchange %llu, side %d)\n", rank, seq, (int)threadIdx.x); __trap(); }
+      if (clock64() - t0 > watchdog_cycles) { st_sys_u64(host_err, 257ull + threadIdx.x); break; }   // no trap: the host turns this into an error code (peer_timeout_error)
   }
 }
 
@@ -169,7 +169,7 @@ int exchange_on(cudaStream_t s, const cd* field, int X, int Y, int dof, int pari
     {
       halo_p2p_kernel<<<(2 * rowlen + 255) / 256, 256, 0, s>>>(field, rowlen, (long)rowlen * Y, Y, parity_mask,
           halo_slot(c.mail[up], slot, 0), halo_slot(c.mail[down], slot, 1), halo_flags(c.mail[up], slot) + 0, halo_flags(c.mail[down], slot) + 1,
-          halo_flags(c.mail[c.rank], slot), seq, c.d_halo_counter, c.rank, p2p_watchdog_cycles());
+          halo_flags(c.mail[c.rank], slot), seq, c.d_halo_counter, c.rank, p2p_watchdog_cycles(), rt().h_err);
       QMG_LAUNCH_CHECK();
       c.halo_exchanges++; c.p2p_halo_exchanges++;
       if (out_ym != nullptr) QMG_CUDA(cudaMemcpyAsync(out_ym + first, my_ym + first, sizeof(cd) * count, cudaMemcpyDeviceToDevice, s));
@@ -227,27 +227,32 @@ int allreduce_result(double* d_buf, int count, int op_max)
 // Peer mailboxes for the in-kernel all-reduce: every rank allocates one block, the IPC handles go round with one
 // ncclAllGather, and each rank maps the other ranks' blocks (NVLink peer memory).  All ranks switch together: if any
 // rank cannot map a peer, everybody stays on ncclAllReduce.
-static int setup_mailboxes()
+static int setup_mailboxes(bool want)
 {
+  // Every rank runs the SAME collectives whatever happens locally (QMG_P2P=0 on this rank only, an allocation or a
+  // mapping that fails): a local problem votes "no" in the unanimity all-reduce instead of leaving the peers waiting.
   Comm& c = comm();
   NcclApi& a = api();
   cudaStream_t s = rt().stream;
-  int ok = 1;
-  if (cudaMalloc(&c.mail_local, kPeerBlockBytes) != cudaSuccess) { cudaGetLastError(); c.mail_local = nullptr; ok = 0; }
+  int ok = want ? 1 : 0;
+  if (ok && cudaMalloc(&c.mail_local, kPeerBlockBytes) != cudaSuccess) { cudaGetLastError(); c.mail_local = nullptr; ok = 0; }
   if (ok && cudaMalloc(&c.d_halo_counter, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); c.d_halo_counter = nullptr; ok = 0; }
-  if (ok) QMG_CUDA(cudaMemset(c.d_halo_counter, 0, sizeof(unsigned int)));
+  if (ok && cudaMemset(c.d_halo_counter, 0, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); ok = 0; }
   cudaIpcMemHandle_t mine;
   memset(&mine, 0, sizeof(mine));
-  if (ok) { QMG_CUDA(cudaMemset(c.mail_local, 0, kHaloDataOffset)); if (cudaIpcGetMemHandle(&mine, c.mail_local) != cudaSuccess) { cudaGetLastError(); ok = 0; } }
+  if (ok && cudaMemset(c.mail_local, 0, kHaloDataOffset) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  if (ok && cudaIpcGetMemHandle(&mine, c.mail_local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  // the handles and the vote travel in device scratch; without it this rank cannot take part in any collective at all
   char* d_handles = nullptr;
-  QMG_CUDA(cudaMalloc(&d_handles, sizeof(mine) * (c.nranks + 1)));
-  QMG_CUDA(cudaMemcpy(d_handles + sizeof(mine) * c.nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice));
-  QMG_NCCL(a.AllGather(d_handles + sizeof(mine) * c.nranks, d_handles, sizeof(mine), kNcclChar, c.nccl, s));
-  QMG_CUDA(cudaStreamSynchronize(s));
+  QMG_CUDA(cudaMalloc(&d_handles, sizeof(mine) * (c.nranks + 1) + sizeof(double)));
+  double* d_ok = reinterpret_cast<double*>(d_handles + sizeof(mine) * (c.nranks + 1));
   std::vector<cudaIpcMemHandle_t> all(c.nranks);
-  QMG_CUDA(cudaMemcpy(all.data(), d_handles, sizeof(mine) * c.nranks, cudaMemcpyDeviceToHost));
-  cudaFree(d_handles);
-  for (int r = 0; r < c.nranks && ok; r++)
+  bool comm_failed = false;
+  if (cudaMemcpy(d_handles + sizeof(mine) * c.nranks, &mine, sizeof(mine), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  if (a.AllGather(d_handles + sizeof(mine) * c.nranks, d_handles, sizeof(mine), kNcclChar, c.nccl, s) != 0) comm_failed = true;
+  if (!comm_failed && cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); comm_failed = true; }
+  if (!comm_failed && cudaMemcpy(all.data(), d_handles, sizeof(mine) * c.nranks, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  for (int r = 0; r < c.nranks && ok && !comm_failed; r++)
   {
     if (r == c.rank) { c.mail[r] = c.mail_local; continue; }
     void* p = nullptr;
@@ -255,15 +260,14 @@ static int setup_mailboxes()
     c.mail[r] = reinterpret_cast<double*>(p);
   }
   // unanimous?
-  double* d_ok = nullptr;
-  QMG_CUDA(cudaMalloc(&d_ok, sizeof(double)));
   const double mine_ok = ok;
-  QMG_CUDA(cudaMemcpy(d_ok, &mine_ok, sizeof(double), cudaMemcpyHostToDevice));
-  QMG_NCCL(a.AllReduce(d_ok, d_ok, 1, kNcclDouble, kNcclSum, c.nccl, s));
-  QMG_CUDA(cudaStreamSynchronize(s));
   double total = 0.0;
-  QMG_CUDA(cudaMemcpy(&total, d_ok, sizeof(double), cudaMemcpyDeviceToHost));
-  cudaFree(d_ok);
+  if (!comm_failed && cudaMemcpy(d_ok, &mine_ok, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); comm_failed = true; }
+  if (!comm_failed && a.AllReduce(d_ok, d_ok, 1, kNcclDouble, kNcclSum, c.nccl, s) != 0) comm_failed = true;
+  if (!comm_failed && cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); comm_failed = true; }
+  if (!comm_failed && cudaMemcpy(&total, d_ok, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); comm_failed = true; }
+  cudaFree(d_handles);
+  if (comm_failed) return fail_msg("qmg_comm_init: the NCCL rendezvous of the peer mailboxes failed");
   c.p2p = ((int)(total + 0.5) == c.nranks);
   return 0;
 }
@@ -338,7 +342,7 @@ int qmg_comm_init(int nranks, int rank, const void* unique_id128)
   c.active = true;
   // in-kernel all-reduce over NVLink peer memory unless QMG_P2P=0 (then every reduction calls ncclAllReduce)
   const char* env = getenv("QMG_P2P");
-  if (!(env != nullptr && env[0] == '0') && nranks <= kMaxRanks) { rc = setup_mailboxes(); if (rc) return rc; }
+  rc = setup_mailboxes(!(env != nullptr && env[0] == '0') && nranks <= kMaxRanks); if (rc) return rc;
   if (!c.p2p) release_mailboxes();
   return upload_red_state(nranks, rank, c.p2p ? 1 : 0, c.mail);
 }

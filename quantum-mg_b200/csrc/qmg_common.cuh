@@ -25,6 +25,7 @@ struct Runtime
   double* d_result = nullptr;       // kMaxRedWidth doubles
   double* h_result = nullptr;       // pinned, mapped: the last block of every reduction writes its result here
   unsigned long long* h_flag = nullptr;   // pinned, mapped: number of reductions published so far
+  unsigned long long* h_err = nullptr;    // pinned, mapped: non-zero once a kernel gave up waiting for a peer (1 + the peer's rank; +256 for a halo row)
   unsigned long long red_seq = 0;   // host mirror of that number (reductions launched)
   int publish = 1;                  // 1: results arrive through h_result / h_flag; 0 (QMG_PUBLISH=0): copy + stream synchronise
   int tile_kernel = 1;              // gamma5-hermitian applies use the shared-memory tile kernel (QMG_TILE=0: streaming HERM kernel)
@@ -54,11 +55,15 @@ constexpr int kMailWidth = 2 * kMaxPtrs;   // doubles one rank can publish per r
 struct RedState
 {
   unsigned int counter; unsigned int pad;
-  unsigned long long seq;
+  unsigned long long seq;           // reductions published by THIS process so far (host handshake; private to the process)
+  unsigned long long coll_seq;      // reductions all-reduced through the mailboxes since qmg_comm_init: the SAME on every rank, it
+                                    // picks the mailbox slot and is the flag value (ranks may have reduced different numbers of
+                                    // times before they joined the communicator)
   int nranks, rank, p2p, publish;
   double* mail[kMaxRanks];          // mail[r]: rank r's mailbox (own: local pointer; others: IPC-mapped peer memory)
   double* host_out;
   unsigned long long* host_flag;
+  unsigned long long* host_err;
   long long watchdog_cycles;        // how long a last block waits for its peers before it gives up (QMG_P2P_TIMEOUT_S, default 120 s)
 };
 // mailbox layout: data[2][kMaxRanks][kMailWidth] doubles, then flags[2][kMaxRanks] (unsigned long long)
@@ -173,7 +178,8 @@ __device__ __forceinline__ void publish_result(unsigned int* counter, double* re
   const unsigned long long seq = st->seq + 1;
   if (st->p2p)
   {
-    const int nr = st->nranks, me = st->rank, buf = (int)(seq & 1);
+    const unsigned long long cseq = st->coll_seq + 1;
+    const int nr = st->nranks, me = st->rank, buf = (int)(cseq & 1);
     for (int i = tid; i < W * nr; i += nthreads)
     {
       const int r = i / W, w = i - r * W;
@@ -184,11 +190,17 @@ __device__ __forceinline__ void publish_result(unsigned int* counter, double* re
     if (tid < nr)
     {
       unsigned long long* peer_flags = reinterpret_cast<unsigned long long*>(st->mail[tid] + kMailDataDoubles);
-      st_sys_u64(peer_flags + buf * kMaxRanks + me, seq);
+      st_sys_u64(peer_flags + buf * kMaxRanks + me, cseq);
       const unsigned long long* my_flags = reinterpret_cast<const unsigned long long*>(st->mail[me] + kMailDataDoubles);
       const long long t0 = clock64();
-      while (ld_sys_u64(my_flags + buf * kMaxRanks + tid) < seq)
-        if (clock64() - t0 > st->watchdog_cycles) { printf("[QMG-ERROR]: rank %d gave up waiting for rank %d in reduction %llu\n", me, tid, seq); __trap(); }
+      while (ld_sys_u64(my_flags + buf * kMaxRanks + tid) < cseq)
+        if (clock64() - t0 > st->watchdog_cycles)
+        {
+          // a peer is gone: no trap (that would poison the context) -- flag the error for the host, which turns it into an
+          // error code at the next fetch, and let the kernel retire with whatever arrived
+          st_sys_u64(st->host_err, 1ull + (unsigned long long)tid);
+          break;
+        }
     }
     __syncthreads();
     for (int w = tid; w < W; w += nthreads)
@@ -199,6 +211,7 @@ __device__ __forceinline__ void publish_result(unsigned int* counter, double* re
       result[w] = acc;
     }
     __syncthreads();
+    if (tid == 0) st->coll_seq = cseq;
   }
   if (st->publish)
   {

@@ -77,6 +77,17 @@ int fail_msg(const char* msg)
 
 int allreduce_result(double* d_buf, int count, int op_max);   // qmg_comm.cu
 
+// A kernel that waits for a peer (in-kernel all-reduce, halo rows stored by the neighbours) gives up after the watchdog
+// time and records who was missing in mapped host memory; the host reports it as an ordinary error code.
+int peer_timeout_error()
+{
+  const unsigned long long e = *rt().h_err;
+  char buf[160];
+  if (e > 256) snprintf(buf, sizeof(buf), "rank %d gave up waiting for a halo row from its %s neighbour (peer lost?)", qmg_comm_rank(), (e - 257) ? "upper" : "lower");
+  else snprintf(buf, sizeof(buf), "rank %d gave up waiting for rank %d in an all-reduce (peer lost?)", qmg_comm_rank(), (int)(e - 1));
+  return fail_msg(buf);
+}
+
 int fetch_result(double* host_out, int count, int op_max)
 {
   Runtime& r = rt();
@@ -97,6 +108,7 @@ int fetch_result(double* host_out, int count, int op_max)
       }
     }
     __sync_synchronize();
+    if (*r.h_err != 0) return peer_timeout_error();
     for (int i = 0; i < count; i++) host_out[i] = r.h_result[i];
     return 0;
   }
@@ -136,7 +148,8 @@ int upload_red_state(int nranks, int rank, int p2p, double* const* mail)
   r.publish_now = (r.publish && (nranks == 1 || p2p)) ? 1 : 0;
   st.nranks = nranks; st.rank = rank; st.p2p = p2p; st.publish = r.publish_now;
   for (int i = 0; i < kMaxRanks; i++) st.mail[i] = (mail != nullptr && i < nranks) ? mail[i] : nullptr;
-  st.host_out = r.h_result; st.host_flag = r.h_flag;
+  st.host_out = r.h_result; st.host_flag = r.h_flag; st.host_err = r.h_err;
+  st.coll_seq = 0;     // a new communicator starts with fresh (zeroed) mailboxes on every rank
   st.watchdog_cycles = p2p_watchdog_cycles();
   QMG_CUDA(cudaMemcpy(r.d_counter, &st, sizeof(st), cudaMemcpyHostToDevice));
   return 0;
@@ -192,9 +205,10 @@ int qmg_init(int device)
   if (ensure_partials((size_t)kMaxRedBlocks * kMaxRedWidth) == nullptr) return 1;
   QMG_CUDA(cudaMalloc(&r.d_counter, sizeof(RedState)));
   QMG_CUDA(cudaMalloc(&r.d_result, sizeof(double) * 2 * kMaxPtrs));
-  QMG_CUDA(cudaHostAlloc(&r.h_result, sizeof(double) * 2 * kMaxPtrs + sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+  QMG_CUDA(cudaHostAlloc(&r.h_result, sizeof(double) * 2 * kMaxPtrs + 2 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
   r.h_flag = reinterpret_cast<unsigned long long*>(r.h_result + 2 * kMaxPtrs);
-  *r.h_flag = 0; r.red_seq = 0;
+  r.h_err = r.h_flag + 1;
+  *r.h_flag = 0; *r.h_err = 0; r.red_seq = 0;
   {
     const char* pe = getenv("QMG_PUBLISH");
     r.publish = (pe != nullptr && pe[0] == '0') ? 0 : 1;
@@ -230,7 +244,7 @@ int qmg_finalize(void)
 
 int qmg_set_stream(void* cuda_stream) { QMG_REQUIRE_INIT(); rt().stream = (cudaStream_t)cuda_stream; return 0; }
 void* qmg_get_stream(void) { return (void*)rt().stream; }
-int qmg_sync(void) { QMG_REQUIRE_INIT(); QMG_CUDA(cudaStreamSynchronize(rt().stream)); return 0; }
+int qmg_sync(void) { QMG_REQUIRE_INIT(); QMG_CUDA(cudaStreamSynchronize(rt().stream)); if (*rt().h_err != 0) return peer_timeout_error(); return 0; }
 const char* qmg_last_error(void) { return rt().error.c_str(); }
 int qmg_sm_count(void) { return rt().sm_count; }
 long qmg_kernel_launches(void) { return rt().launches; }
@@ -322,7 +336,15 @@ double qmg_profile_report(void)
   fflush(stdout);
   return total;
 }
-int qmg_set_alloc_mode(int managed) { QMG_REQUIRE_INIT(); rt().managed = managed ? 1 : 0; return 0; }
+int qmg_set_alloc_mode(int managed)
+{
+  QMG_REQUIRE_INIT();
+  const int want = managed ? 1 : 0;
+  // parked blocks are keyed by size only: hand them back to the driver so that the next qmg_malloc really is of the new kind
+  if (want != rt().managed) { int rc = cache_trim(); if (rc) return rc; }
+  rt().managed = want;
+  return 0;
+}
 int qmg_get_alloc_mode(void) { return rt().managed; }
 int qmg_malloc_host(void** hptr, size_t bytes) { QMG_REQUIRE_INIT(); QMG_CUDA(cudaMallocHost(hptr, bytes ? bytes : 16)); return 0; }
 int qmg_free_host(void* hptr) { if (hptr) { QMG_CUDA(cudaFreeHost(hptr)); } return 0; }

@@ -28,6 +28,7 @@ struct StencilKArgs
   const cd* in;
   cd* out;
   const cd* dotw;       // fused <out|dotw> or nullptr
+  const cd* resid;      // residual epilogue: out = resid - A in (nullptr: out = A in)
   const cd* halo_ym;    // input row y=-1 from the lower rank, or nullptr (periodic)
   const cd* halo_yp;    // input row y=Y from the upper rank, or nullptr
   Geom g;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
   const cd V3 = m3 ? ld_keep(s3) : zero;
   const cd VC = (has_cl || has_dg) ? ld_keep(a.in + site * NC + c2) : zero;
   const cd OLD = (writer && a.accumulate) ? a.out[idx] : zero;
+  const cd RB = (writer && a.resid != nullptr) ? ld_stream(a.resid + idx) : zero;
   const cd DG = has_dg ? a.diag[p][(2 * c2 >= NC && NC > 1) ? 1 : 0] : zero;
 
   cd acc = zero;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
   if (writer)
   {
     acc = cadd(acc, OLD);
+    if (a.resid != nullptr) acc = csub(RB, acc);
     a.out[idx] = acc;
     if (REDUCE)
     {
@@ -374,6 +377,7 @@ template <int NC, int TK, int TY, int SPLIT = 1> struct Tile
         const size_t site = (size_t)p * a.g.half + (size_t)y * a.g.xh + (k0 + tk);
         cd res = acc[0];
         if (a.accumulate) res = cadd(res, a.out[site * NC + row]);
+        if (a.resid != nullptr) res = csub(ld_stream(a.resid + site * NC + row), res);
         a.out[site * NC + row] = res;
       }
     }
@@ -422,9 +426,10 @@ template <int TK, int TY> static bool tile_applicable(const StencilKArgs& a, int
 
 template <int NC, int TK, int TY, int SPLIT = 1> static int launch_tile(const StencilKArgs& a)
 {
-  static bool configured = false;
+  static bool configured[64] = { false };      // the attribute is per device (qmg_init may move to another one)
   const size_t smem = tile_smem_bytes<NC, TK, TY>();
-  if (!configured) { QMG_CUDA(cudaFuncSetAttribute(stencil_tile_kernel<NC, TK, TY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+  const int dev = rt().device & 63;
+  if (!configured[dev]) { QMG_CUDA(cudaFuncSetAttribute(stencil_tile_kernel<NC, TK, TY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[dev] = true; }
   dim3 grid(a.g.xh / TK, a.y_cnt / TY, 1);       // rows [y_off, y_off + y_cnt): whole patches
   if (grid.y > 65535) return fail_msg("qmg_stencil_apply: Y too large for the launch grid");
   stencil_tile_kernel<NC, TK, TY, SPLIT><<<grid, TileDims<NC, TK, TY, SPLIT>::THREADS, smem, rt().stream>>>(a);
@@ -469,6 +474,7 @@ __global__ void __launch_bounds__(256) stencil_kernel_generic(const StencilKArgs
     }
     const size_t idx = site * nc + c1;
     if (a.accumulate) acc = cadd(acc, a.out[idx]);
+    if (a.resid != nullptr) acc = csub(a.resid[idx], acc);
     a.out[idx] = acc;
   }
 }
@@ -487,6 +493,7 @@ static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   a.in = reinterpret_cast<const cd*>(rhs);
   a.out = reinterpret_cast<cd*>(lhs);
   a.dotw = nullptr;
+  a.resid = nullptr;
   a.halo_ym = reinterpret_cast<const cd*>(st->halo_ym);
   a.halo_yp = reinterpret_cast<const cd*>(st->halo_yp);
   a.herm = (st->gamma5_hermitian != 0 && st->nc % 2 == 0 && st->nc <= 32) ? 1 : 0;
@@ -777,6 +784,30 @@ int qmg_stencil_apply(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   StencilKArgs a; int n_par;
   int rc = build_args(st, pieces, dir_mask, lhs, rhs, a, n_par);
   if (rc) return rc;
+  if ((const void*)lhs == (const void*)rhs && n_par == 2)
+  {
+    // in-place hopping into BOTH parities: one launch would read rows of parity 1 - p while other blocks rewrite them.
+    // The reference is sequential -- apply_M_eo, then apply_M_oe on the updated even rows (stencil_2d.h:843-850) -- so
+    // the in-place case is two ordered launches with exactly that meaning.
+    rc = qmg_stencil_apply(st, (pieces & ~QMG_APPLY_ODD_ROWS_ONLY & ~QMG_APPLY_HOP_TO_ODD) | QMG_APPLY_EVEN_ROWS_ONLY, dir_mask, lhs, rhs);
+    if (rc) return rc;
+    return qmg_stencil_apply(st, (pieces & ~QMG_APPLY_EVEN_ROWS_ONLY & ~QMG_APPLY_HOP_TO_EVEN) | QMG_APPLY_ODD_ROWS_ONLY, dir_mask, lhs, rhs);
+  }
+  if (needs_exchange(a)) return apply_sharded(a, st->nc, n_par);
+  return dispatch_stencil(a, st->nc, n_par, false);
+}
+
+int qmg_stencil_apply_residual(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs, const qmg_cplx* b)
+{
+  QMG_REQUIRE_INIT();
+  if (st != nullptr) prof_scope__.detail(st->nc, st->X, st->Y);
+  if (b == nullptr) return fail_msg("qmg_stencil_apply_residual: null right-hand side");
+  if (pieces & QMG_APPLY_ACCUMULATE) return fail_msg("qmg_stencil_apply_residual: the residual epilogue is out-of-place (no QMG_APPLY_ACCUMULATE)");
+  if ((const void*)lhs == (const void*)rhs) return fail_msg("qmg_stencil_apply_residual: lhs must not alias rhs (it may alias b)");
+  StencilKArgs a; int n_par;
+  int rc = build_args(st, pieces, dir_mask, lhs, rhs, a, n_par);
+  if (rc) return rc;
+  a.resid = reinterpret_cast<const cd*>(b);
   if (needs_exchange(a)) return apply_sharded(a, st->nc, n_par);
   return dispatch_stencil(a, st->nc, n_par, false);
 }

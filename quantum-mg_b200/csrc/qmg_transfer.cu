@@ -80,7 +80,8 @@ template <int NV> struct VecPackRW { cd* p[NV]; };
 // NV values over 32 lanes cost NV - 1 + (5 - log2 NV) shuffles instead of 5 NV.
 template <int NV>
 __global__ void __launch_bounds__(256) restrict_kernel(const TGeom g, const VecPack<NV> nv, const int nv_count, const int v0,
-                                                       const cd* __restrict__ fine, cd* __restrict__ coarse, const int G, const int logG)
+                                                       const cd* __restrict__ fine, cd* __restrict__ coarse, const int G, const int logG,
+                                                       const int overwrite)
 {
   const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long agg = gt >> logG;             // aggregates are enumerated row-major in (yc, xc): neighbours in memory are neighbours in the grid
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) restrict_kernel(const TGeom g, const VecP
       if (i < left && vbase + i < nv_count)
       {
         cd* dst = coarse + ci * g.ncc + v0 + vbase + i;
-        *dst = cadd(*dst, acc[i]);
+        *dst = overwrite ? acc[i] : cadd(*dst, acc[i]);
       }
   }
 }
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(256) restrict_kernel(const TGeom g, const VecP
 // fine vector; the NV coarse values of the aggregate come through L1.
 template <int NV>
 __global__ void __launch_bounds__(256) prolong_kernel(const TGeom g, const VecPack<NV> nv, const int nv_count, const int v0,
-                                                      const cd* __restrict__ coarse, cd* __restrict__ fine)
+                                                      const cd* __restrict__ coarse, cd* __restrict__ fine,
+                                                      const cd* __restrict__ base, const int use_base)
 {
   const int rowlen = g.xhf * g.ncf;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,16 +161,19 @@ __global__ void __launch_bounds__(256) prolong_kernel(const TGeom g, const VecPa
   const int x = 2 * k + ((y + p) & 1);
   const long ci = coarse_index(g, x / g.bx, y / g.by);
   const long idx = ((long)(y + p * g.Yf) * g.xhf) * g.ncf + col;
-  cd acc = fine[idx];
+  // use_base: fine = base + P coarse with the sum formed from zero first (what zero + prolong + cxpyz produce, in one
+  // pass); base == nullptr then means a zero base
+  cd acc = use_base ? cmake(0.0, 0.0) : fine[idx];
   const cd* cv = coarse + ci * g.ncc + v0;
 #pragma unroll
   for (int v = 0; v < NV; v++)
     if (v < nv_count) cfma(acc, ld_stream(nv.p[v] + idx), __ldg(cv + v));
+  if (use_base && base != nullptr) acc = cadd(base[idx], acc);
   fine[idx] = acc;
 }
 
 template <int NV>
-static int launch_restrict(const TGeom& g, const qmg_cplx* const* vecs, int count, int v0, const qmg_cplx* fine, qmg_cplx* coarse)
+static int launch_restrict(const TGeom& g, const qmg_cplx* const* vecs, int count, int v0, const qmg_cplx* fine, qmg_cplx* coarse, int overwrite = 0)
 {
   VecPack<NV> pk;
   for (int v = 0; v < NV; v++) pk.p[v] = reinterpret_cast<const cd*>(vecs[v < count ? v : 0]);
@@ -183,20 +188,22 @@ static int launch_restrict(const TGeom& g, const qmg_cplx* const* vecs, int coun
   const long threads = g.Vc * G;
   const long blocks = (threads + 255) / 256;
   if (blocks > 0x7fffffffL) return fail_msg("restrict: lattice too large for the launch grid");
-  restrict_kernel<NV><<<(unsigned)blocks, 256, 0, rt().stream>>>(g, pk, count, v0, reinterpret_cast<const cd*>(fine), reinterpret_cast<cd*>(coarse), G, logG);
+  restrict_kernel<NV><<<(unsigned)blocks, 256, 0, rt().stream>>>(g, pk, count, v0, reinterpret_cast<const cd*>(fine), reinterpret_cast<cd*>(coarse), G, logG, overwrite);
   QMG_LAUNCH_CHECK();
   return 0;
 }
 
 template <int NV>
-static int launch_prolong(const TGeom& g, const qmg_cplx* const* vecs, int count, int v0, const qmg_cplx* coarse, qmg_cplx* fine)
+static int launch_prolong(const TGeom& g, const qmg_cplx* const* vecs, int count, int v0, const qmg_cplx* coarse, qmg_cplx* fine,
+                          const qmg_cplx* base = nullptr, int use_base = 0)
 {
   VecPack<NV> pk;
   for (int v = 0; v < NV; v++) pk.p[v] = reinterpret_cast<const cd*>(vecs[v < count ? v : 0]);
   const int rowlen = g.xhf * g.ncf;
   if (g.Yf > 65535) return fail_msg("prolong: Y too large for the launch grid");
   dim3 grid((rowlen + 255) / 256, g.Yf, 2);
-  prolong_kernel<NV><<<grid, 256, 0, rt().stream>>>(g, pk, count, v0, reinterpret_cast<const cd*>(coarse), reinterpret_cast<cd*>(fine));
+  prolong_kernel<NV><<<grid, 256, 0, rt().stream>>>(g, pk, count, v0, reinterpret_cast<const cd*>(coarse), reinterpret_cast<cd*>(fine),
+                                                         reinterpret_cast<const cd*>(base), use_base);
   QMG_LAUNCH_CHECK();
   return 0;
 }
@@ -412,6 +419,44 @@ int qmg_prolong(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host
     done += take;
   }
   return 0;
+}
+
+// coarse = P^dag fine, every coarse dof of the nvec vectors written outright (restrict_f2c after zero_vector, in one pass)
+int qmg_restrict_overwrite(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec, const qmg_cplx* fine, qmg_cplx* coarse)
+{
+  QMG_REQUIRE_INIT();
+  TGeom g; int rc = make_geom(t, g, "qmg_restrict_overwrite"); if (rc) return rc;
+  if (nvec != g.ncc) return fail_msg("qmg_restrict_overwrite: needs all coarse dof (nvec == coarse nc); the partial flavour is qmg_restrict");
+  int done = 0;
+  while (done < nvec)
+  {
+    const int left = nvec - done;
+    int take;
+    if (left >= 8) { take = 8; rc = launch_restrict<8>(g, nullvecs_host + done, take, done, fine, coarse, 1); }
+    else if (left > 4) { take = left; rc = launch_restrict<8>(g, nullvecs_host + done, take, done, fine, coarse, 1); }
+    else if (left > 2) { take = left; rc = launch_restrict<4>(g, nullvecs_host + done, take, done, fine, coarse, 1); }
+    else if (left == 2) { take = 2; rc = launch_restrict<2>(g, nullvecs_host + done, take, done, fine, coarse, 1); }
+    else { take = 1; rc = launch_restrict<1>(g, nullvecs_host + done, take, done, fine, coarse, 1); }
+    if (rc) return rc;
+    done += take;
+  }
+  return 0;
+}
+
+// fine_out = base + P coarse (base NULL: fine_out = P coarse): zero_vector + prolong_c2f + cxpyz of the K-cycle's
+// correction step (stateful_multigrid.h:1005-1019) in one pass; fine_out may alias base
+int qmg_prolong_add(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec, const qmg_cplx* coarse,
+                    const qmg_cplx* base, qmg_cplx* fine_out)
+{
+  QMG_REQUIRE_INIT();
+  TGeom g; int rc = make_geom(t, g, "qmg_prolong_add"); if (rc) return rc;
+  if (nvec < 1 || nvec > g.ncc) return fail_msg("qmg_prolong_add: nvec must be in [1, coarse nc]");
+  // one pass holds 8 vectors; callers with more (none on the K-cycle path: coarse_dof = 8) use zero + qmg_prolong + cxpyz
+  if (nvec > 8) return fail_msg("qmg_prolong_add: at most 8 vectors per fused pass");
+  if (nvec > 4) return launch_prolong<8>(g, nullvecs_host, nvec, 0, coarse, fine_out, base, 1);
+  if (nvec > 2) return launch_prolong<4>(g, nullvecs_host, nvec, 0, coarse, fine_out, base, 1);
+  if (nvec == 2) return launch_prolong<2>(g, nullvecs_host, nvec, 0, coarse, fine_out, base, 1);
+  return launch_prolong<1>(g, nullvecs_host, nvec, 0, coarse, fine_out, base, 1);
 }
 
 int qmg_block_orthonormalize(const qmg_transfer_desc* t, qmg_cplx* const* nullvecs_host, int nvec, qmg_cplx* cholesky)

@@ -642,6 +642,28 @@ void CAPI(mg_tracker)(void* h_, int level, int* out)
   out[5] = mg->get_iterations_count(level);
 }
 void CAPI(mg_reset_tracker)(void* h_) { ((capi::MgH*)h_)->mg->reset_tracker(); }
+// B200 extension: operator applications actually LAUNCHED at `level` (the trackers above keep the reference's counts, which
+// include the A.0 and unread true-residual applies the fused K-cycle skips).  Reference build: the reference's total.
+long CAPI(mg_executed)(void* h_, int level)
+{
+#ifdef QMG_B200_HOST
+  return ((capi::MgH*)h_)->mg->get_executed_count(level);
+#else
+  return ((capi::MgH*)h_)->mg->get_total_count(level);
+#endif
+}
+// B200 extension: 1 = fused K-cycle (default), 0 = the reference's sequence of separate sweeps; bit-identical results.  Returns the previous setting.
+int CAPI(mg_set_fused)(void* h_, int on)
+{
+#ifdef QMG_B200_HOST
+  StatefulMultigridMG* mg = ((capi::MgH*)h_)->mg;
+  const int was = mg->get_fused_cycle() ? 1 : 0;
+  mg->set_fused_cycle(on != 0);
+  return was;
+#else
+  (void)h_; (void)on; return 0;
+#endif
+}
 // emulated/explicit level operator (multigrid.h:465), prolong / restrict through the MG object
 void CAPI(mg_apply_stencil)(void* h_, int level, int type, capi_cd* lhs, const capi_cd* rhs)
 {

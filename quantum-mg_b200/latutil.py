@@ -1,10 +1,10 @@
-"""TEST INFRASTRUCTURE: numpy helpers for the reference's even-odd layout
-(/root/reference/lattice/lattice.h:75-81) and the U(1) fixtures under tests/golden/."""
+"""numpy helpers for the reference's even-odd layout (/root/reference/lattice/lattice.h:75-81), the reference's
+thermalised U(1) configs (re-encoded under tests/golden/) and the synthetic large-lattice gauge fields bench.py runs on."""
 import os
 
 import numpy as np
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 
 def site_index(x, y, X, Y):

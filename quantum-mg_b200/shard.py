@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE: y-slab re-indexing of eo-ordered fields.
+"""y-slab re-indexing of eo-ordered fields: what a caller uses to cut a global field into the per-rank slabs.
 
 A slab of rows [y0, y0+Yl) of an (X, Y) lattice is itself an (X, Yl) even-odd lattice when y0 is
 even (parity is preserved), and every field is two contiguous chunks of the global array, one per

@@ -353,6 +353,64 @@ def test_n13_kcycle_parity(ref, gpu, L, levels):
     mg_r.free(); mg_g.free()
 
 
+def test_n13_kcycle_parity_256(ref, gpu):
+    """BASELINE config 2 at its stated size: tests/n13_wilson_kcycle on the reference's own l256t256b60 config
+    (wilson_kcycle.cpp:148-194), 2 levels, 4x4 blocks, 8 coarse dof, MR(2,2), coarsest GCR(32) tol 0.2, outer VPGCR(32) to
+    1e-10, whole flow native on both back ends (kcycle_new draws the same mt19937 stream).  Mass -0.05: at the usage string's
+    -0.075 the CPU reference itself stalls on this config (profiles/r03_oracle_mass_m0075_nonconvergence.log).
+    Gates: iteration count +-1, explicit residual, solution to 1e-8."""
+    L = 256
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L * 2, 256)
+    res = {}
+    for name, be in (("ref", ref), ("gpu", gpu)):
+        kc = capi.KCycle(be, L, -0.05, g, n_refine=1)
+        x, info = kc.solve(b=b, tol=1e-10, restart=32, want_x=True)
+        res[name] = (x, info, [kc.tracker(l) for l in range(2)])
+        kc.free()
+    (xr, ir, tr_), (xg, ig, tg_) = res["ref"], res["gpu"]
+    assert ir["success"] and ig["success"], (ir, ig)
+    assert abs(ir["iter"] - ig["iter"]) <= 1, (ir, ig)
+    assert ig["check_relres"] < 2e-10 and ir["check_relres"] < 2e-10
+    assert latutil.rel_l2(xg, xr) < 1e-8
+    for lev in range(2):
+        assert abs(tr_[lev]["total"] - tg_[lev]["total"]) <= 0.1 * tr_[lev]["total"] + 8, (lev, tr_[lev], tg_[lev])
+
+
+@pytest.mark.parametrize("level_app,coarsest_app", [(0, 0), (2, 2), (3, 3)])
+def test_fused_kcycle_is_bit_identical(gpu, level_app, coarsest_app):
+    """The fused K-cycle (zero-start smoothers and coarse solves without A.0, no unread true-residual applies, one-pass
+    residual / restrict / prolong-correct, lhs += z3 folded into the smoother's last step) against the reference's
+    sweep-for-sweep sequence on the same hierarchy: same iteration counts, same reference operator counts, the SAME BITS in
+    one preconditioner application and in the solution -- and a third fewer operator launches on every level."""
+    L = 64
+    g = latutil.load_gauge(L)
+    kc = capi.KCycle(gpu, L, -0.05, g, n_refine=2, level_app=level_app, coarsest_app=coarsest_app)
+    mg = capi.Multigrid.__new__(capi.Multigrid)
+    mg.be, mg.h = gpu, kc._mg
+    b = latutil.gaussian_cv(L * L * 2, 77)
+    out = {}
+    for fused in (0, 1):
+        kc.set_fused(fused)
+        z = mg.precond(b)
+        mg.reset_tracker()
+        x, info = kc.solve(b=b, tol=1e-10, restart=32, want_x=True, outer_type=level_app)
+        out[fused] = (z, x, info, [kc.tracker(l) for l in range(3)], [kc.executed(l) for l in range(3)])
+    (z0, x0, i0, t0, e0), (z1, x1, i1, t1, e1) = out[0], out[1]
+    assert i0["success"] and i1["success"]
+    assert np.array_equal(z0, z1)
+    assert np.array_equal(x0, x1)
+    assert i0["iter"] == i1["iter"] and t0 == t1, (i0, i1, t0, t1)
+    # unfused: everything the reference counts is launched (+ the post-smooth residual apply it does not count)
+    for lev in range(3):
+        assert e0[lev] >= t0[lev]["total"] - t0[lev]["nullvec"], (lev, e0, t0)
+    # fused: levels 0 and 1 launch 3 + 3 applies per K-cycle application instead of 5 + 5
+    for lev in range(2):
+        assert e1[lev] < 0.7 * e0[lev], (lev, e0, e1)
+    assert e1[2] < e0[2]
+    kc.free()
+
+
 def test_n19_schur_kcycle_parity(ref, gpu):
     """tests/n19_wilson_kcycle_precond: every level solved as the Schur system of the right-block-Jacobi operator,
     coarse stencils built from the rbjacobi fine stencil, outer tolerance 1e-8."""

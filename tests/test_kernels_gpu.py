@@ -364,6 +364,113 @@ def test_fused_krylov_step(qmg_gpu):
             assert out[0] == want[2] and (out[1], out[2], out[3]) == want[3], (n, alias)
 
 
+def test_krylov_step_flavours(qmg_gpu):
+    """qmg_krylov_step: without flags bit-identical to qmg_step_xr_norm; the zero-start first step (x_in NULL, r_in = b != r_out,
+    |b|^2 on the side), the x-only last step and the accumulate-into flavour reproduce the separate sweeps bit for bit."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    NULL = C.c_void_p(0)
+    for n in (5, 4096, 100003):
+        p0, q0, x0, r0, a0 = (latutil.gaussian_cv(n, s) for s in (1, 2, 3, 4, 5))
+        omega = 0.85
+        # (a) no flags, MR aliasing p == r
+        q, x, r = dev(qmg, q0), dev(qmg, x0), dev(qmg, r0)
+        want4 = (C.c_double * 4)()
+        qmg.check(lib.qmg_step_xr_norm(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(r), C.c_long(n), want4))
+        wx, wr = host(x), host(r)
+        q, x, r = dev(qmg, q0), dev(qmg, x0), dev(qmg, r0)
+        out = (C.c_double * 5)()
+        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(x), qmg.ptr(r), qmg.ptr(r), NULL, C.c_long(n), 0, out))
+        assert np.array_equal(host(x), wx) and np.array_equal(host(r), wr) and tuple(out)[:4] == tuple(want4), n
+        # (b) first step from a zero start: x written, b read in place of r, |b|^2 returned == qmg_norm2sq(b)
+        q, b = dev(qmg, q0), dev(qmg, r0)
+        x, r = qmg.cvec(n), dev(qmg, r0)
+        qmg.check(lib.qmg_step_xr_norm(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(r), C.c_long(n), want4))
+        wx, wr = host(x), host(r)
+        x2 = dev(qmg, x0)          # garbage on entry: must not be read
+        r2 = dev(qmg, a0)
+        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(b), qmg.ptr(q), NULL, qmg.ptr(x2), qmg.ptr(b), qmg.ptr(r2), NULL, C.c_long(n), 1, out))
+        assert np.array_equal(host(x2), wx) and np.array_equal(host(r2), wr) and tuple(out)[:4] == tuple(want4), n
+        assert out[4] == qmg.norm2sq(b) and np.array_equal(host(b), r0), n
+        # (c) x-only last step with lhs += z folded in: lhs + (x + alpha p)
+        q, x, r, lhs = dev(qmg, q0), dev(qmg, x0), dev(qmg, r0), dev(qmg, a0)
+        qmg.check(lib.qmg_step_xr_norm(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(r), C.c_long(n), want4))
+        qmg.check(lib.qmg_caxpy(C.c_double(1.0), C.c_double(0.0), qmg.ptr(x), qmg.ptr(lhs), C.c_long(n)))
+        wl = host(lhs)
+        q, x, r, lhs = dev(qmg, q0), dev(qmg, x0), dev(qmg, r0), dev(qmg, a0)
+        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(lhs), qmg.ptr(r), qmg.ptr(r), qmg.ptr(lhs), C.c_long(n), 2, out))
+        assert np.array_equal(host(lhs), wl) and np.array_equal(host(r), r0), n
+
+
+@pytest.mark.parametrize("nc,herm", [(2, False), (8, False), (8, True), (1, False), (6, False)])
+def test_apply_residual_epilogue(qmg_gpu, nc, herm):
+    """qmg_stencil_apply_residual == qmg_stencil_apply + qmg_caxpbyz(1, b, -1, A x), bit for bit, on the streaming, tile
+    (gamma5-hermitian nc = 8) and generic kernels; lhs may alias b."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    L = 32
+    n = L * L * nc
+    if herm:
+        # a gamma5-hermitian nc = 8 link set: forward blocks random, backward blocks from the relation
+        rng = np.random.default_rng(5)
+        V = L * L
+        hop = (rng.normal(size=(4, V, nc, nc)) + 1j * rng.normal(size=(4, V, nc, nc)))
+        s = np.where(np.arange(nc) < nc // 2, 1.0, -1.0)
+        import latutil as lu
+        idx = np.arange(V)
+        X = Y = L
+        xh = X // 2
+        p_, rem = np.divmod(idx, xh * Y)
+        y_, k_ = np.divmod(rem, xh)
+        x_ = 2 * k_ + ((y_ + p_) & 1)
+        def site(x, y):
+            x %= X; y %= Y
+            par = (x + y) & 1
+            return (y + par * Y) * xh + x // 2
+        for mu, (dx, dy) in ((2, (-1, 0)), (3, (0, -1))):
+            nb = site(x_ + dx, y_ + dy)
+            hop[mu] = (s[None, :, None] * s[None, None, :]) * np.conj(np.swapaxes(hop[mu - 2][nb], 1, 2))
+        cl = rng.normal(size=(V, nc, nc)) + 1j * rng.normal(size=(V, nc, nc))
+        clover, hopping = dev(qmg, cl.reshape(-1)), dev(qmg, hop.reshape(-1))
+        d = qmg.stencil_desc(L, L, nc, clover, hopping, shift=0.3, gamma5_hermitian=True)
+        assert qmg.stencil_gamma5_deviation(d) < 1e-14
+    else:
+        cl, hp = random_stencil(L, nc, 3)
+        clover, hopping = dev(qmg, cl), dev(qmg, hp)
+        d = qmg.stencil_desc(L, L, nc, clover, hopping, shift=0.3 + 0.1j, eo_shift=0.05, dof_shift=(0.02 if nc % 2 == 0 else 0.0))
+    x, b = dev(qmg, latutil.gaussian_cv(n, 8)), dev(qmg, latutil.gaussian_cv(n, 9))
+    Ax, want = qmg.cvec(n), qmg.cvec(n)
+    qmg.stencil_apply(d, Ax, x)
+    qmg.check(lib.qmg_caxpbyz(C.c_double(1.0), C.c_double(0.0), qmg.ptr(b), C.c_double(-1.0), C.c_double(0.0), qmg.ptr(Ax), qmg.ptr(want), C.c_long(n)))
+    got = qmg.cvec(n)
+    qmg.check(lib.qmg_stencil_apply_residual(C.byref(d), C.c_int(15), C.c_int(15), qmg.ptr(got), qmg.ptr(x), qmg.ptr(b)))
+    assert np.array_equal(host(got), host(want))
+    b2 = b.clone()
+    qmg.check(lib.qmg_stencil_apply_residual(C.byref(d), C.c_int(15), C.c_int(15), qmg.ptr(b2), qmg.ptr(x), qmg.ptr(b2)))
+    assert np.array_equal(host(b2), host(want))
+    assert lib.qmg_stencil_apply_residual(C.byref(d), C.c_int(15), C.c_int(15), qmg.ptr(x), qmg.ptr(x), qmg.ptr(b)) != 0   # lhs == rhs refused
+
+
+def test_in_place_hopping_is_sequential(ref, qmg_gpu):
+    """apply_M_hopping(x, x): the reference runs apply_M_eo, then apply_M_oe on the UPDATED even rows
+    (stencil/stencil_2d.h:843-850); the in-place both-parity request is two ordered launches with that meaning."""
+    qmg = qmg_gpu
+    L, nc = 16, 2
+    cl, hp = random_stencil(L, nc, 11)
+    lat = ref.lattice(L, L, nc)
+    op = lat.generic(cl, hp)
+    x0 = latutil.gaussian_cv(L * L * nc, 12)
+    y = op.apply_piece(2, x0, lhs=x0)             # apply_M_eo: even rows += H x_odd
+    want = op.apply_piece(3, y, lhs=y)            # apply_M_oe on the updated vector: odd rows += H y_even
+    op.free()
+    d = qmg.stencil_desc(L, L, nc, dev(qmg, cl), dev(qmg, hp))
+    x = dev(qmg, x0)
+    qmg.stencil_apply(d, x, x, pieces=qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_HOP_TO_ODD | qmg.APPLY_ACCUMULATE)
+    assert latutil.rel_l2(host(x), want) < TOL
+
+
 def test_fused_apply_dot(ref, qmg_gpu):
     qmg = qmg_gpu
     L = 64
