@@ -11,7 +11,9 @@ operands resident in HBM; `e2e` is the same apply through the C ABI with HOST so
 N > 1: y-slab weak scaling, every rank owns an L x L slab of an L x (N L) lattice; the library
 (qmg_comm_init) exchanges one boundary row with the two ring neighbours per apply, overlapped with
 the interior rows.  The second half of the metric, the 3-level Wilson K-cycle solve, runs on the
-same slabs (`kcycle` in the JSON line).
+same slabs (`kcycle` in the JSON line).  N > 1 adds two records the driver's SCALE file then carries: `shard_parity`
+(a 512 x 512 K-cycle on N slabs against the same solve on one GPU: iteration counts, per-level operator counts, slab error)
+and `kcycle_strong` (the SAME 8192 x 8192 lattice cut into N slabs: strong scaling of the solve).
 
 --impl reference: the reference's own CPU implementation (oracle/_ref: the unmodified reference
 headers, single thread -- the reference has no threading) on a bounded sample of the same workload.
@@ -82,7 +84,7 @@ class ClockSampler(threading.Thread):
 
 def cpu_reference_apply(L, reps, warm=1):
     """Time the reference's CPU apply (oracle/_ref) on an L x L Wilson lattice; returns (GB/s, seconds per apply)."""
-    import capi
+    import capi          # tests/capi.py: the oracle binding (CPU baseline legs only)
     import latutil
     if not capi.have_ref():
         raise RuntimeError("oracle/_ref/libqmg_ref.so missing: run __graft_entry__.build() in the build container")
@@ -100,12 +102,19 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
     vectors, MR(2,2) smoothing, inner tol 0.2), gaussian right-hand side; returns the solve record.
     world > 1 (after qmg.comm_init): this rank owns an L x L y-slab of the L x (world L) lattice (weak scaling); the
     hierarchy, the solvers and the K-cycle are the same host code, the library exchanges halo rows and all-reduces dots."""
-    import capi
     import latutil
-    be = capi.Backend(backend)
+    if backend == "gpu":
+        import driver                     # quantum-mg_b200/driver.py: the product's own driver API (libqmg_host.so)
+        be = driver.Backend("gpu")
+        KC = driver.KCycle
+    else:
+        import capi                       # tests/capi.py: the oracle binding (CPU baseline legs only)
+        be = capi.Backend(backend)
+        KC = capi.KCycle
     # Mass -0.05 everywhere: n13's usage string suggests -0.075, but that is beyond the critical mass of some of the shipped
     # configs (l128t128b60 and l256t256b60 stall there on the CPU reference too: "eigenvalues go negative around -0.075",
-    # tests/n13_wilson_kcycle/wilson_kcycle.cpp:81), and the chance of an exceptional mode grows with the volume.
+    # tests/n13_wilson_kcycle/wilson_kcycle.cpp:81; the oracle's own run is committed as
+    # profiles/r03_oracle_mass_m0075_nonconvergence.log), and the chance of an exceptional mode grows with the volume.
     # Iteration caps (inner 100, coarsest 400, outer 100; n13 uses 1000) only bind if a solve stalls.
     mass = -0.05
     if gauge is None:
@@ -124,7 +133,7 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
         import torch.distributed as dist
         dist.barrier()
     t0 = time.perf_counter()
-    kc = capi.KCycle(be, L, mass, gauge, n_refine=n_refine, seed=seed, inner_iters=100, coarsest_iters=400, Y=Yl)
+    kc = KC(be, L, mass, gauge, n_refine=n_refine, seed=seed, inner_iters=100, coarsest_iters=400, Y=Yl)
     del gauge
     out = kc.solve(tol=tol, restart=restart, max_iter=100)
     if backend == "gpu":
@@ -153,11 +162,60 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
         out["hbm_in_use_gb"] = (total - free) / 1e9
     out["config"] = cfg
     out["per_level_ops"] = [kc.tracker(l)["total"] for l in range(n_refine + 1)]
+    if backend == "gpu":
+        # the trackers count what the reference counts; the fused K-cycle launches fewer (no A.0, no unread true residuals)
+        out["per_level_ops_executed"] = [kc.executed(l) for l in range(n_refine + 1)]
     out["per_level_iters"] = [kc.tracker(l)["iters"] for l in range(n_refine + 1)]
     out["precond_apply_s"] = kc.time_precond(1, 2)
     out["wall_s_incl_setup"] = time.perf_counter() - t0
     kc.free()
     return out
+
+
+def shard_parity_one_gpu(L, levels=3, mass=-0.03, tol=1e-10):
+    """Phase A of the multi-rank equivalence check (tests/shard_worker.py in bench form), called BEFORE qmg.comm_init: this
+    rank solves the whole L x L lattice alone on its GPU.  Returns what phase B compares against."""
+    import driver
+    import latutil
+    be = driver.Backend("gpu")
+    g = latutil.synthetic_gauge(L, L, 6.0, 11)
+    b = latutil.gaussian_cv(L * L * 2, 21)
+    kc = driver.KCycle(be, L, mass, g, n_refine=levels - 1, block=4, coarse_dof=8, seed=5)
+    x, info = kc.solve(b, tol=tol, want_x=True)
+    ops = [kc.tracker(l)["total"] for l in range(levels)]
+    kc.free()
+    return dict(L=L, levels=levels, mass=mass, tol=tol, g=g, b=b, x=x, info=info, ops=ops)
+
+
+def shard_parity_slabs(one, world, rank):
+    """Phase B, after qmg.comm_init: the same gauge field and right-hand side cut into `world` y-slabs, same host code.
+    Gates (tests/shard_worker.py): outer iterations +-1, per-level operator counts within 5 %, this rank's slab of the
+    one-GPU solution to 1e-8.  Returns the record for the JSON line (max / min over ranks)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import driver
+    import latutil
+    import shard
+    L, levels = one["L"], one["levels"]
+    be = driver.Backend("gpu")
+    sl = shard.Slab(L, L, world, rank)
+    V = L * L
+    g_loc = np.concatenate([sl.take(one["g"][:V], 1), sl.take(one["g"][V:], 1)])
+    kc = driver.KCycle(be, L, one["mass"], g_loc, Y=sl.Yl, n_refine=levels - 1, block=4, coarse_dof=8, seed=5)
+    x_loc, info = kc.solve(sl.take(one["b"], 2), tol=one["tol"], want_x=True)
+    ops = [kc.tracker(l)["total"] for l in range(levels)]
+    kc.free()
+    err = float(latutil.rel_l2(x_loc, sl.take(one["x"], 2)))
+    ok = bool(abs(info["iter"] - one["info"]["iter"]) <= 1 and err < 1e-8 and info["success"]
+              and all(abs(p - q) <= max(2, 0.05 * q) for p, q in zip(ops, one["ops"])))
+    t = torch.tensor([err, 0.0 if ok else 1.0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"lattice": [L, L], "slabs": world, "levels": levels, "mass": one["mass"],
+            "one_gpu": {"iter": one["info"]["iter"], "per_level_ops": one["ops"], "check_relres": one["info"]["check_relres"]},
+            "slabs_result": {"iter": info["iter"], "per_level_ops": ops, "check_relres": info["check_relres"]},
+            "max_slab_rel_error": float(t[0].item()), "ok_on_every_rank": bool(t[1].item() == 0.0),
+            "gates": "outer iterations +-1, per-level operator counts within 5 %, slab of the one-GPU solution to 1e-8 (tests/shard_worker.py)"}
 
 
 def run_reference(args):
@@ -198,9 +256,16 @@ def run_gpu(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    qmg.init(local)
     if world > 1:
+        os.environ["QMG_DEVICE_RNG"] = "1"      # gaussian fills keyed by the GLOBAL element index: N slabs draw what one GPU draws
+    qmg.init(local)
+    shard_parity = None
+    if world > 1:
+        one = shard_parity_one_gpu(args.parity_L) if args.parity_L > 0 else None
         qmg.comm_init()          # from here on every lattice handed to the library is this rank's y-slab
+        if one is not None:
+            shard_parity = shard_parity_slabs(one, world, rank)
+            del one
     lib = qmg.lib()
     L = args.L
     strong = args.scaling == "strong"
@@ -273,6 +338,20 @@ def run_gpu(args):
     qmg.check(lib.qmg_memcpy_d2h(hout, qmg.ptr(lhs), C.c_size_t(16 * n)))
     t2 = time.perf_counter()
     pcie = {"h2d_GBps": 16 * n / (t1 - t0) / 1e9, "d2h_GBps": 16 * n / (t2 - t1) / 1e9}
+    lib.qmg_device_numa_node.restype = C.c_int
+    numa = int(lib.qmg_device_numa_node())
+    if world > 1:
+        # every rank copies at the same time: report the slowest GPU's rates and where each rank's staging memory lives
+        import torch.distributed as dist
+        t = torch.tensor([pcie["h2d_GBps"], pcie["d2h_GBps"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        pcie = {"h2d_GBps_slowest_gpu": float(t[0].item()), "d2h_GBps_slowest_gpu": float(t[1].item()), "all_gpus_copying_at_once": True}
+        nodes = [None] * world
+        dist.all_gather_object(nodes, numa)
+        pcie["numa_node_of_each_gpu"] = nodes
+    else:
+        pcie["numa_node_of_gpu"] = numa
+    pcie["pinned_staging"] = "allocated and first touched on the GPU's NUMA node (qmg_malloc_host)"
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -305,6 +384,21 @@ def run_gpu(args):
             kcycle["comm"] = qmg.comm_counters()
         if world == 1 and args.cpu_kcycle_L > 0 and not args.no_cpu:
             kcycle_same = kcycle_run("gpu", args.cpu_kcycle_L)
+    # strong scaling of the solve: the SAME kcycle_L x kcycle_L lattice (a stack of N independently drawn slabs) on N GPUs;
+    # its N = 1 point is the `kcycle` leg above
+    kcycle_strong = None
+    if world > 1 and not strong and args.kcycle_L > 0 and not args.no_strong and args.kcycle_L % (32 * world) == 0:
+        import torch.distributed as dist
+        torch.cuda.empty_cache()
+        lib.qmg_trim()
+        kcycle_strong = kcycle_run("gpu", args.kcycle_L, restart=args.kcycle_restart, world=world, rank=rank, Yl=args.kcycle_L // world,
+                                   link_compressed=not args.kcycle_stored_blocks)
+        t = torch.tensor([kcycle_strong["seconds"], kcycle_strong["setup_seconds"], kcycle_strong["precond_apply_s"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kcycle_strong["seconds"], kcycle_strong["setup_seconds"], kcycle_strong["precond_apply_s"] = (float(v) for v in t.tolist())
+        kcycle_strong["lattice"] = [args.kcycle_L, args.kcycle_L]
+        kcycle_strong["per_gpu_lattice"] = [args.kcycle_L, args.kcycle_L // world]
+        kcycle_strong["note"] = "same global lattice size as the N = 1 `kcycle` leg, cut into %d y-slabs; time is the max over ranks" % world
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -320,12 +414,32 @@ def run_gpu(args):
                 if args.cpu_kcycle_L > 0:
                     cpu["kcycle"] = kcycle_run("ref", args.cpu_kcycle_L)
                     cpu["kcycle_gpu_same_config"] = kcycle_same
+                    if kcycle is not None and cpu["kcycle"].get("iter"):
+                        # explicit extrapolation of the CPU reference to the GPU leg's lattice: cost per site per outer iteration is
+                        # size-independent on paper (it only grows on a CPU once the working set leaves the caches), so
+                        #   t_cpu(L) ~ t_cpu(L0) x (L / L0)^2 x iterations(L) / iterations(L0)      -- a LOWER bound for the CPU
+                        kc_cpu = cpu["kcycle"]
+                        vol = (args.kcycle_L / float(args.cpu_kcycle_L)) ** 2
+                        itr = kcycle["iter"] / float(kc_cpu["iter"])
+                        ext = {"to_lattice": [args.kcycle_L, args.kcycle_L], "from_lattice": [args.cpu_kcycle_L, args.cpu_kcycle_L],
+                               "solve_seconds": kc_cpu["seconds"] * vol * itr, "setup_seconds": kc_cpu["setup_seconds"] * vol,
+                               "formula": "t_cpu(%d^2) x (%d/%d)^2 x iter_gpu(%d^2)/iter_cpu(%d^2) = %.2f s x %.0f x %d/%d; set-up: %.2f s x %.0f"
+                                          % (args.cpu_kcycle_L, args.kcycle_L, args.cpu_kcycle_L, args.kcycle_L, args.cpu_kcycle_L,
+                                             kc_cpu["seconds"], vol, kcycle["iter"], kc_cpu["iter"], kc_cpu["setup_seconds"], vol),
+                               "gpu_solve_seconds_measured": kcycle["seconds"], "gpu_setup_seconds_measured": kcycle["setup_seconds"]}
+                        ext["solve_speedup_vs_extrapolated_cpu"] = ext["solve_seconds"] / kcycle["seconds"]
+                        cpu["kcycle_extrapolated"] = ext
+                        sys.stderr.write("[bench] CPU reference K-cycle extrapolated to %dx%d: solve %.0f s (%.1f h), set-up %.0f s; GPU measured: solve %.2f s, set-up %.2f s\n"
+                                         % (args.kcycle_L, args.kcycle_L, ext["solve_seconds"], ext["solve_seconds"] / 3600.0, ext["setup_seconds"],
+                                            kcycle["seconds"], kcycle["setup_seconds"]))
             except Exception as e:  # the baseline is a report, never the product path
                 cpu = {"value": None, "unit": "GB/s", "cores": 1, "kind": "reference", "sample": "unavailable: %s" % e}
         emit(json.dumps({
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "wilson_stencil_apply_%dx%d_u1" % (X, Y * world), "per_gpu_lattice": [X, Y], "beta": beta, "mass": -0.075,
+            "config": {"workload": "wilson_stencil_apply_%dx%d_u1" % (X, Y * world), "per_gpu_lattice": [X, Y], "beta": beta,
+                       "mass": {"stencil_apply": -0.075, "kcycle": -0.05,
+                                "why": "the apply only adds the mass to the diagonal; the K-cycle legs use -0.05 because n13's -0.075 is beyond critical on the reference's own 128^2 / 256^2 configs (profiles/r03_oracle_mass_m0075_nonconvergence.log)"},
                        "bytes_per_site": BYTES_PER_SITE, "l2": "operands (%.1f GB per apply) far larger than the 126 MB L2; no flush needed" % (BYTES_PER_SITE * V / 1e9),
                        "parallelism": "y-slabs x%d, 1-row halo ring" % world},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (traffic or {}).get("bytes"), "traffic_unit": "DRAM bytes per launch (ncu --set full)",
@@ -337,6 +451,8 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "kcycle": kcycle,
+            "kcycle_strong": kcycle_strong,
+            "shard_parity": shard_parity,
         }))
     if world > 1:
         import torch.distributed as dist
@@ -375,7 +491,10 @@ def main():
     ap.add_argument("--kcycle-L", type=int, default=8192, dest="kcycle_L", help="3-level K-cycle solve on L x L per GPU after the stencil run (0 = skip)")
     ap.add_argument("--kcycle-restart", type=int, default=8, dest="kcycle_restart",
                     help="restart length of the outer flexible GCR (n13 uses 32; at 8192^2 per GPU 2 x 32 stored 2.1 GB vectors do not fit beside the hierarchy; 8, 16 and 32 need the same 22 iterations at 4096^2)")
-    ap.add_argument("--cpu-kcycle-L", type=int, default=128, dest="cpu_kcycle_L", help="K-cycle size for the CPU reference leg (a bounded sample: the reference needs ~10 s at 128x128; 0 = skip)")
+    ap.add_argument("--cpu-kcycle-L", type=int, default=256, dest="cpu_kcycle_L",
+                    help="K-cycle size for the CPU reference leg: BASELINE config 2's 256 x 256 on the reference's own l256t256b60 config (~35 s of CPU: set-up + solve; 0 = skip)")
+    ap.add_argument("--parity-L", type=int, default=512, dest="parity_L", help="N > 1: lattice of the N-slabs-against-one-GPU K-cycle equivalence check (0 = skip)")
+    ap.add_argument("--no-strong", action="store_true", dest="no_strong", help="N > 1: skip the strong-scaling K-cycle leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -391,6 +391,10 @@ public:
     complex<double>* r1 = fpool->check_out();
     if (!fuse) zero_vector(z1, nf);
     else if (nf_solve != nf) zero_vector(z1 + nf_solve, nf - nf_solve);     // Schur: the odd half is read as zero further down
+    // Schur: the residual lives on the even sites, but the restriction below reads the whole vector.  The reference leaves
+    // the odd half of r1 as whatever the pool vector last held (stateful_multigrid.h:843 "gets initialized in the next code
+    // block" -- only its first fine_size_solve elements are); here it is zero, so that the K-cycle is a function of its input.
+    if (nf_solve != nf) zero_vector(r1 + nf_solve, nf - nf_solve);
     if (ls->pre_iters > 0)
     {
       SolveHints hints(smooth_flags);

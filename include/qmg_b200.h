@@ -60,7 +60,8 @@ int qmg_memcpy_d2d(void* dst, const void* src, size_t bytes);
  * variable QMG_MANAGED=1 read at qmg_init. */
 int qmg_set_alloc_mode(int managed);
 int qmg_get_alloc_mode(void);
-int qmg_malloc_host(void** hptr, size_t bytes);   /* pinned host staging */
+int qmg_malloc_host(void** hptr, size_t bytes);   /* pinned host staging, allocated and first touched on the GPU's NUMA node (QMG_NUMA=0: wherever the caller runs) */
+int qmg_device_numa_node(void);                   /* NUMA node of the active GPU (sysfs numa_node of its PCI function), -1 if unknown */
 int qmg_free_host(void* hptr);
 
 /* --------------------------------------------------------------- sharding -- */

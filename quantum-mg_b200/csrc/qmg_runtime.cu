@@ -3,6 +3,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <time.h>
+#include <sched.h>
 #include <algorithm>
 #include <map>
 #include <unordered_map>
@@ -346,7 +347,63 @@ int qmg_set_alloc_mode(int managed)
   return 0;
 }
 int qmg_get_alloc_mode(void) { return rt().managed; }
-int qmg_malloc_host(void** hptr, size_t bytes) { QMG_REQUIRE_INIT(); QMG_CUDA(cudaMallocHost(hptr, bytes ? bytes : 16)); return 0; }
+// NUMA node the active GPU hangs off (sysfs), or -1 when the platform does not say
+int qmg_device_numa_node(void)
+{
+  if (!rt().ready) return -1;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), rt().device) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (f == nullptr) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+
+// Pinned host staging on the GPU's own NUMA node: with one process per GPU, every rank's host vectors otherwise land on
+// whichever node the launcher started it on (node 0 for all eight ranks of a torchrun job), and eight PCIe streams then
+// cross the socket interconnect into one memory controller.  The calling thread is moved onto the GPU's node for the
+// allocation and the first touch (default "local" policy), then gets its affinity back.
+int qmg_malloc_host(void** hptr, size_t bytes)
+{
+  QMG_REQUIRE_INIT();
+  if (bytes == 0) bytes = 16;
+  cpu_set_t old_set, node_set;
+  bool moved = false;
+  const int node = qmg_device_numa_node();
+  const char* off = getenv("QMG_NUMA");
+  if (node >= 0 && !(off != nullptr && off[0] == '0') && sched_getaffinity(0, sizeof(old_set), &old_set) == 0)
+  {
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE* f = fopen(path, "r");
+    if (f != nullptr)
+    {
+      CPU_ZERO(&node_set);
+      int a, b, any = 0;
+      // "0-31,64-95": ranges separated by commas
+      while (fscanf(f, "%d", &a) == 1)
+      {
+        b = a;
+        int ch = fgetc(f);
+        if (ch == '-') { if (fscanf(f, "%d", &b) != 1) b = a; ch = fgetc(f); }
+        for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; cpu++) if (CPU_ISSET(cpu, &old_set)) { CPU_SET(cpu, &node_set); any = 1; }   // never leave the cpuset we were given
+        if (ch != ',') break;
+      }
+      fclose(f);
+      if (any && sched_setaffinity(0, sizeof(node_set), &node_set) == 0) moved = true;
+    }
+  }
+  cudaError_t e = cudaHostAlloc(hptr, bytes, cudaHostAllocPortable);
+  if (e == cudaSuccess) memset(*hptr, 0, bytes);        // first touch from the GPU's node
+  if (moved) sched_setaffinity(0, sizeof(old_set), &old_set);
+  if (e != cudaSuccess) return qmg::fail("pinned host allocation", e, __FILE__, __LINE__);
+  return 0;
+}
 int qmg_free_host(void* hptr) { if (hptr) { QMG_CUDA(cudaFreeHost(hptr)); } return 0; }
 
 } // extern "C"

@@ -282,7 +282,9 @@ template <int NC, int TK, int TY, int SPLIT = 1> struct Tile
   }
 
   // clover column c2 of this thread's site(s), straight from global memory while a tile is in flight
-  __device__ static __forceinline__ void clover(const StencilKArgs& a, int k0, int y0, int tid, cd (&CLc)[PASSES][R])
+  // (also the element of the residual epilogue's right-hand side this thread will need at the very end: fetched here, while
+  // the tile is in flight, instead of as a dependent load after the butterfly)
+  __device__ static __forceinline__ void clover(const StencilKArgs& a, int k0, int y0, int tid, cd (&CLc)[PASSES][R], cd (&RBc)[PASSES])
   {
     const int c2 = tid % NC, hf = (tid / NC) % SPLIT;
     const cd zero = cmake(0.0, 0.0);
@@ -294,6 +296,7 @@ template <int NC, int TK, int TY, int SPLIT = 1> struct Tile
       const size_t site = (size_t)p * a.g.half + (size_t)(y0 + ty) * a.g.xh + (k0 + tk);
 #pragma unroll
       for (int i = 0; i < R; i++) CLc[ps][i] = (a.clover != nullptr) ? ld_stream(a.clover + site * LPS + (hf * R + i) * NC + c2) : zero;
+      RBc[ps] = (a.resid != nullptr && (SPLIT == 1 || (c2 % SPLIT) == 0)) ? ld_stream(a.resid + site * NC + hf * R + c2 / SPLIT) : zero;
     }
   }
 
@@ -302,7 +305,7 @@ template <int NC, int TK, int TY, int SPLIT = 1> struct Tile
   // (NC - 1 complex shuffles) that leaves row t on thread t.  Per block a thread reads NC matrix elements and ONE spinor
   // element from shared memory (an element-per-lane mapping reads one of each per element: twice the shared-memory
   // traffic, which is what bounds this kernel).
-  __device__ static __forceinline__ void compute(const StencilKArgs& a, const cd* buf, int k0, int y0, int tid, const cd (&CLc)[PASSES][R])
+  __device__ static __forceinline__ void compute(const StencilKArgs& a, const cd* buf, int k0, int y0, int tid, const cd (&CLc)[PASSES][R], const cd (&RBc)[PASSES])
   {
     const cd* sHx = buf; const cd* sHy = sHx + (size_t)NHX * BS; const cd* sV = sHy + (size_t)NHY * BS;
     const int c2 = tid % NC, hf = (tid / NC) % SPLIT;
@@ -377,7 +380,7 @@ template <int NC, int TK, int TY, int SPLIT = 1> struct Tile
         const size_t site = (size_t)p * a.g.half + (size_t)y * a.g.xh + (k0 + tk);
         cd res = acc[0];
         if (a.accumulate) res = cadd(res, a.out[site * NC + row]);
-        if (a.resid != nullptr) res = csub(ld_stream(a.resid + site * NC + row), res);
+        if (a.resid != nullptr) res = csub(RBc[ps], res);
         a.out[site * NC + row] = res;
       }
     }
@@ -394,10 +397,11 @@ __global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT >
   const int k0 = blockIdx.x * TK, y0 = a.y_off + blockIdx.y * TY;
   T::stage(a, tile_smem, k0, y0, tid);
   cd CLc[T::PASSES][T::R];
-  T::clover(a, k0, y0, tid, CLc);
+  cd RBc[T::PASSES];
+  T::clover(a, k0, y0, tid, CLc, RBc);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  T::compute(a, tile_smem, k0, y0, tid, CLc);
+  T::compute(a, tile_smem, k0, y0, tid, CLc, RBc);
 }
 
 // (A persistent, double-buffered flavour -- a CTA walking over patches, the next patch's cp.async traffic filling a second
@@ -435,6 +439,237 @@ template <int NC, int TK, int TY, int SPLIT = 1> static int launch_tile(const St
   stencil_tile_kernel<NC, TK, TY, SPLIT><<<grid, TileDims<NC, TK, TY, SPLIT>::THREADS, smem, rt().stream>>>(a);
   QMG_LAUNCH_CHECK();
   return 0;
+}
+
+// ---- the same patch staged by the TMA engine ---------------------------------------------------------------------------
+// The cp.async flavour above spends ~10 LDGSTS plus their index arithmetic per thread on staging (64 % issue utilisation,
+// profiles/r03a_ncu_tile_kernel_cp_async.txt).  Here the patch arrives by BULK asynchronous copies -- cp.async.bulk
+// global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP / SYNCS) -- issued by the lanes of ONE warp:
+// the forward blocks of the TK sites of one (row, parity) are TK nc^2 contiguous complex numbers in the reference's layout
+// (4 KB at nc = 8), so a patch is 2 TY + TY copies for +x (rows + left halo column), 2 TY + 2 for +y (rows + the halo row
+// below), and the spinor rows with their 1-site ring; no thread computes a staging address in the hot loop and nothing
+// passes through registers.  Bulk copies cannot pad, so the blocks sit UNPADDED (row stride nc) and the backward products
+// are re-mapped to stay conflict-free: the thread of output row a walks DOWN column a of the neighbour's block --
+// consecutive lanes read consecutive elements -- against broadcast spinor elements, and hands its complete row sum to the
+// lane that owns row a in the forward butterfly.  Forward products keep the column mapping of the cp.async kernel.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned), completing on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int NC, int TK, int TY, int SPLIT> struct TmaTile
+{
+  static const int S = TileDims<NC, TK, TY, SPLIT>::S, NT = TileDims<NC, TK, TY, SPLIT>::THREADS, PASSES = TileDims<NC, TK, TY, SPLIT>::PASSES;
+  static const int R = NC / SPLIT;
+  static const int LPS = NC * NC;              // elements per block, unpadded
+  static const int NHX = S + TY, NHY = S + 2 * TK, VK = TK + 2;
+  static const int NV = (TY + 2) * 2 * VK * NC;
+  static const unsigned BYTES = (unsigned)(sizeof(cd) * ((size_t)(NHX + NHY) * LPS + NV));
+  static const size_t SMEM = 128 + BYTES;      // mbarrier in the first 128 bytes
+  // copies: +x rows 2 TY, +x halo column TY, +y rows 2 TY, +y halo row 2, spinor (row, parity) pairs 2 (TY + 2)
+  static const int NCOPY = 2 * TY + TY + 2 * TY + 2 + 2 * (TY + 2);
+
+  // issued by ONE warp: lane l takes copies l, l + 32, ...
+  __device__ static __forceinline__ void stage(const StencilKArgs& a, cd* buf, unsigned long long* bar, int k0, int y0, int lane)
+  {
+    cd* sHx = buf; cd* sHy = sHx + (size_t)NHX * LPS; cd* sV = sHy + (size_t)NHY * LPS;
+    const int xh = a.g.xh, Y = a.g.Y;
+    const size_t half = a.g.half;
+    const cd* hopx = a.hop;
+    const cd* hopy = a.hop + a.size_cm;
+    for (int c = lane; c < NCOPY; c += 32)
+    {
+      int j = c;
+      if (j < 2 * TY)
+      {
+        const int ty = j >> 1, p = j & 1;        // the TK sites of (row ty, parity p): one contiguous run of TK blocks
+        bulk_g2s(sHx + (size_t)(j * TK) * LPS, hopx + ((size_t)p * half + (size_t)(y0 + ty) * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
+        continue;
+      }
+      j -= 2 * TY;
+      if (j < TY)
+      {
+        const int ty = j, p = 1 - ((y0 + ty) & 1), k = (k0 == 0) ? xh - 1 : k0 - 1;     // left neighbour of the sft = 0 site of this row
+        bulk_g2s(sHx + (size_t)(S + ty) * LPS, hopx + ((size_t)p * half + (size_t)(y0 + ty) * xh + k) * LPS, LPS * sizeof(cd), bar);
+        continue;
+      }
+      j -= TY;
+      if (j < 2 * TY)
+      {
+        const int ty = j >> 1, p = j & 1;
+        bulk_g2s(sHy + (size_t)(j * TK) * LPS, hopy + ((size_t)p * half + (size_t)(y0 + ty) * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
+        continue;
+      }
+      j -= 2 * TY;
+      if (j < 2)
+      {
+        const int p = j, y = (y0 == 0) ? Y - 1 : y0 - 1;       // the row below the patch
+        bulk_g2s(sHy + (size_t)(S + p * TK) * LPS, hopy + ((size_t)p * half + (size_t)y * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
+        continue;
+      }
+      j -= 2;
+      {
+        // spinor row ry - 1 of the patch (ry = 0 .. TY + 1), parity p, sites k0 - 1 .. k0 + TK: contiguous except across the x wrap
+        const int ry = j >> 1, p = j & 1;
+        int y = y0 + ry - 1; y = (y < 0) ? Y - 1 : ((y >= Y) ? 0 : y);
+        const cd* row = a.in + ((size_t)p * half + (size_t)y * xh) * NC;
+        cd* dst = sV + (size_t)((ry * 2 + p) * VK) * NC;
+        const bool wl = (k0 == 0), wr = (k0 + TK == xh);
+        const int kk0 = wl ? 1 : 0, kk1 = wr ? VK - 1 : VK;     // [kk0, kk1): the run that does not wrap
+        bulk_g2s(dst + kk0 * NC, row + (size_t)(k0 - 1 + kk0) * NC, (unsigned)((kk1 - kk0) * NC * sizeof(cd)), bar);
+        if (wl) bulk_g2s(dst, row + (size_t)(xh - 1) * NC, NC * sizeof(cd), bar);
+        if (wr) bulk_g2s(dst + (size_t)(VK - 1) * NC, row, NC * sizeof(cd), bar);
+      }
+    }
+  }
+
+  __device__ static __forceinline__ void compute(const StencilKArgs& a, const cd* buf, int k0, int y0, int tid, const cd (&CLc)[PASSES][R], const cd (&RBc)[PASSES])
+  {
+    const cd* sHx = buf; const cd* sHy = sHx + (size_t)NHX * LPS; const cd* sV = sHy + (size_t)NHY * LPS;
+    const int c2 = tid % NC, hf = (tid / NC) % SPLIT;
+    const cd zero = cmake(0.0, 0.0);
+    const bool top = (2 * c2 < NC);
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ps++)
+    {
+      const int slot = ps * (NT / (NC * SPLIT)) + tid / (NC * SPLIT);
+      const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; const int p = r / TK, tk = r - p * TK;
+      const int q = 1 - p, y = y0 + ty, sft = (y + p) & 1;
+      const int nx = sft ? (ty * 2 + q) * TK + tk : (tk > 0 ? (ty * 2 + q) * TK + tk - 1 : S + ty);
+      const int ny = (ty > 0) ? ((ty - 1) * 2 + q) * TK + tk : S + q * TK + tk;
+      const cd* vrow = sV + ((size_t)((ty + 1) * 2) * VK) * NC;            // row ty of the patch, parity 0, kk = 0
+      const cd VC = vrow[((size_t)p * VK + tk + 1) * NC + c2];
+      const cd V0 = vrow[((size_t)q * VK + tk + 1 + sft) * NC + c2];
+      const cd V1 = vrow[((size_t)(2 + q) * VK + tk + 1) * NC + c2];
+      const cd* v2 = vrow + ((size_t)q * VK + tk + sft) * NC + hf * R;                      // in(x - x^)[rows of this thread]: broadcast reads
+      const cd* v3 = vrow + ((ptrdiff_t)q * VK + tk + 1 - 2 * VK) * NC + hf * R;            // in(x - y^)
+      const cd* hx = sHx + (size_t)slot * LPS + (hf * R) * NC + c2;    // forward: column c2, rows of this thread: [c1][c2] at + i NC
+      const cd* hy = sHy + (size_t)slot * LPS + (hf * R) * NC + c2;
+      const cd* bx = sHx + (size_t)nx * LPS + (hf * R) * NC + c2;      // backward: column a = c2 of the neighbour's block, rows b of this thread
+      const cd* by = sHy + (size_t)ny * LPS + (hf * R) * NC + c2;
+      cd acc[R];
+      cd back = zero;
+#pragma unroll
+      for (int i = 0; i < R; i++)
+      {
+        cd t = zero;
+        cfma(t, CLc[ps][i], VC);
+        cfma(t, hx[i * NC], V0);
+        cfma(t, hy[i * NC], V1);
+        acc[i] = t;
+        // s_a s_b conj(B[b][a]) in(x - mu)[b], b = hf R + i: the sign is applied once below
+        cfma_conj(back, bx[i * NC], v2[i]);
+        cfma_conj(back, by[i * NC], v3[i]);
+      }
+      // rows b of this thread all lie in one half of the dof when R divides NC / 2: one sign per thread
+      static_assert((NC / 2) % R == 0, "TmaTile: the rows of a thread must not straddle the two chiral halves");
+      const double sg = (top == (2 * hf * R < NC)) ? 1.0 : -1.0;
+      back = cmake(sg * back.x, sg * back.y);
+      // complete the sum over b across the SPLIT threads of (site, a)
+#pragma unroll
+      for (int off = NC * (SPLIT / 2); off >= NC; off >>= 1) back = cadd(back, shfl_xor_c(back, off));
+      // row a = c2 of the forward partial sums lives on the thread with hf = c2 / R, as acc[c2 % R]: add the backward row sum there
+#pragma unroll
+      for (int i = 0; i < R; i++) if (hf * R + i == c2) acc[i] = cadd(acc[i], back);
+      if (a.use_diag)
+      {
+        const cd dg = a.diag[p][top ? 0 : 1];
+#pragma unroll
+        for (int i = 0; i < R; i++) if (hf * R + i == c2) cfma(acc[i], dg, VC);
+      }
+      int left = R;
+#pragma unroll
+      for (int off = NC / 2; off > 0; off >>= 1)
+      {
+        if (left > 1)
+        {
+          const int hl = left / 2;
+          const bool upper = (c2 & off) != 0;
+#pragma unroll
+          for (int i = 0; i < R / 2; i++)
+            if (i < hl)
+            {
+              const cd send = upper ? acc[i] : acc[i + hl];
+              const cd keep = upper ? acc[i + hl] : acc[i];
+              acc[i] = cadd(keep, shfl_xor_c(send, off));
+            }
+          left = hl;
+        }
+        else acc[0] = cadd(acc[0], shfl_xor_c(acc[0], off));
+      }
+      if (SPLIT == 1 || (c2 % SPLIT) == 0)
+      {
+        const int row = hf * R + c2 / SPLIT;
+        const size_t site = (size_t)p * a.g.half + (size_t)y * a.g.xh + (k0 + tk);
+        cd res = acc[0];
+        if (a.accumulate) res = cadd(res, a.out[site * NC + row]);
+        if (a.resid != nullptr) res = csub(RBc[ps], res);
+        a.out[site * NC + row] = res;
+      }
+    }
+  }
+};
+
+template <int NC, int TK, int TY, int SPLIT>
+__global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT > 1 ? 2 : 1)) stencil_tma_kernel(const StencilKArgs a)
+{
+  typedef TmaTile<NC, TK, TY, SPLIT> T;
+  typedef Tile<NC, TK, TY, SPLIT> T0;          // the clover / residual register prefetch is shared with the cp.async kernel
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(tma_smem);
+  cd* buf = reinterpret_cast<cd*>(tma_smem + 128);
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * TK, y0 = a.y_off + blockIdx.y * TY;
+  if (tid == 0)
+  {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32)
+  {
+    if (tid == 0) mbar_expect_tx(bar, T::BYTES);
+    __syncwarp();
+    T::stage(a, buf, bar, k0, y0, tid);
+  }
+  cd CLc[T::PASSES][T::R];
+  cd RBc[T::PASSES];
+  T0::clover(a, k0, y0, tid, CLc, RBc);
+  mbar_wait(bar, 0);
+  T::compute(a, buf, k0, y0, tid, CLc, RBc);
+}
+
+template <int NC, int TK, int TY, int SPLIT = 1> static int launch_tma(const StencilKArgs& a)
+{
+  static bool configured[64] = { false };
+  const size_t smem = TmaTile<NC, TK, TY, SPLIT>::SMEM;
+  const int dev = rt().device & 63;
+  if (!configured[dev]) { QMG_CUDA(cudaFuncSetAttribute(stencil_tma_kernel<NC, TK, TY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured[dev] = true; }
+  dim3 grid(a.g.xh / TK, a.y_cnt / TY, 1);
+  if (grid.y > 65535) return fail_msg("qmg_stencil_apply: Y too large for the launch grid");
+  stencil_tma_kernel<NC, TK, TY, SPLIT><<<grid, TileDims<NC, TK, TY, SPLIT>::THREADS, smem, rt().stream>>>(a);
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+
+// nc = 8 patches: the TMA-staged kernel (QMG_TILE=3: the cp.async-staged one; 2: cp.async with one thread per column)
+static int launch_tile8(const StencilKArgs& a)
+{
+  if (rt().tile_kernel == 2) return launch_tile<8, 4, 4, 1>(a);
+  if (rt().tile_kernel == 3) return launch_tile<8, 4, 4, 2>(a);
+  return launch_tma<8, 4, 4, 2>(a);
 }
 
 // Any nc (DWF Ls = 6, 12, 24, 32 give nc = 12, 24, 48, 64): one thread per
@@ -563,8 +798,7 @@ static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduc
     // column-wise clover loads waste half of every sector): the fine level keeps the streaming kernel.
     // nc = 8: two threads per (site, column), four rows each -- 32 instead of 16 warps per SM on the same staged bytes:
     // 3.00 -> 2.51 ms sustained on 2048^2 (profiles/r02w_tile_split.txt; QMG_TILE=2 selects the one-thread flavour)
-    if (nc == 8 && rt().tile_kernel == 2 && tile_applicable<4, 4>(a, n_par)) return launch_tile<8, 4, 4, 1>(a);
-    if (nc == 8 && tile_applicable<4, 4>(a, n_par)) return launch_tile<8, 4, 4, 2>(a);
+    if (nc == 8 && tile_applicable<4, 4>(a, n_par)) return launch_tile8(a);
     if (nc == 4 && tile_applicable<8, 8>(a, n_par)) return launch_tile<4, 8, 8>(a);
   }
   switch (nc)
@@ -615,7 +849,7 @@ static int apply_sharded(StencilKArgs& a, int nc, int n_par)
   {
     StencilKArgs in = a;
     in.hop_ym = nullptr; in.y_off = TY8; in.y_stride = 1; in.y_cnt = a.g.Y - 2 * TY8;
-    rc = launch_tile<8, TK8, TY8, 2>(in); if (rc) return rc;
+    rc = launch_tile8(in); if (rc) return rc;
     rc = halo_exchange_end(); if (rc) return rc;
     a.halo_ym = rows.ym; a.halo_yp = rows.yp;
     a.y_off = 0; a.y_stride = 1; a.y_cnt = TY8;

@@ -93,7 +93,21 @@ __global__ void __launch_bounds__(256) restrict_kernel(const TGeom g, const VecP
 #pragma unroll
   for (int v = 0; v < NV; v++) acc[v] = cmake(0.0, 0.0);
   if (live)
-    for (int e = lane_in; e < g.fspc; e += G)
+  {
+    // two elements per trip: 2 (NV + 1) independent 16-byte loads in flight per lane (one element per trip left the
+    // kernel latency-bound: 62 % of DRAM peak at 17 % issue utilisation, profiles/r03a_ncu_restrict_reduce_tile.txt)
+    int e = lane_in;
+    for (; e + G < g.fspc; e += 2 * G)
+    {
+      const long i0 = agg_elem_index(g, xc, yc, e), i1 = agg_elem_index(g, xc, yc, e + G);
+      const cd f0 = __ldg(fine + i0), f1 = __ldg(fine + i1);
+      cd n0[NV], n1[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) if (v < nv_count) { n0[v] = ld_stream(nv.p[v] + i0); n1[v] = ld_stream(nv.p[v] + i1); }
+#pragma unroll
+      for (int v = 0; v < NV; v++) if (v < nv_count) { cfma_conj(acc[v], n0[v], f0); cfma_conj(acc[v], n1[v], f1); }
+    }
+    for (; e < g.fspc; e += G)
     {
       const long idx = agg_elem_index(g, xc, yc, e);
       const cd f = __ldg(fine + idx);
@@ -101,6 +115,7 @@ __global__ void __launch_bounds__(256) restrict_kernel(const TGeom g, const VecP
       for (int v = 0; v < NV; v++)
         if (v < nv_count) cfma_conj(acc[v], ld_stream(nv.p[v] + idx), f);
     }
+  }
 
   int vbase = 0;
 #pragma unroll

@@ -25,6 +25,8 @@ ap.add_argument("--null-iters", type=int, default=500)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--restart", type=int, default=32)
 ap.add_argument("--seed", type=int, default=1337)
+ap.add_argument("--hermitian", action="store_true", help="link-compressed (gamma5-hermitian) applies on every level that qualifies")
+ap.add_argument("--unfused", action="store_true", help="the reference's sweep-for-sweep K-cycle (round-1 behaviour) instead of the fused one")
 args = ap.parse_args()
 if args.backend == "gpu":
     import qmg
@@ -37,6 +39,11 @@ for L in args.sizes:
     kc = capi.KCycle(be, L, args.mass, g, n_refine=args.n_refine, inner_iters=args.inner_iters, coarsest_iters=args.coarsest_iters,
                      null_max_iter=args.null_iters, verbosity=args.verbosity)
     t2 = time.perf_counter()
+    if args.backend == "gpu":
+        if args.hermitian:
+            print("link-compressed levels:", kc.gamma5_hermitian(True), flush=True)
+        if args.unfused:
+            kc.set_fused(False)
     out = kc.solve(max_iter=args.max_iter, verbosity=args.verbosity, restart=args.restart)
     t3 = time.perf_counter()
     if args.profile and args.backend == "gpu":
@@ -49,6 +56,7 @@ for L in args.sizes:
         sys.stdout.flush(); qmg.lib().qmg_profile_report()
     out["second_solve_s"] = out2["seconds"]; out["second_solve_iter"] = out2["iter"]; out["second_solve_wall_s"] = time.perf_counter() - t4
     out.update(L=L, gauge_s=t1 - t0, setup_wall_s=t2 - t1, solve_wall_s=t3 - t2, per_level=[kc.tracker(l) for l in range(args.n_refine + 1)],
+               executed=[kc.executed(l) for l in range(args.n_refine + 1)],
                precond_s=kc.time_precond(1, 2))
     print(json.dumps(out), flush=True)
     kc.free()
