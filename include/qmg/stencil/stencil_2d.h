@@ -13,6 +13,7 @@
 #define QMG_B200_STENCIL_2D
 
 #include <complex>
+#include <cstdlib>
 #include <iostream>
 #include <utility>
 #include "../lattice/lattice.h"
@@ -179,6 +180,11 @@ public:
     gamma5_hermitian = false;
     const int nc = lat->get_nc();
     if (hopping == 0 || nc % 2 != 0 || nc > 32 || swap_dagger || swap_rbjacobi || swap_rbj_dagger) return false;
+    {
+      // QMG_HERM_MIN_NC: smallest dof count that switches (experiments: nc = 2 has no tile kernel and gains little)
+      const char* e = getenv("QMG_HERM_MIN_NC");
+      if (e != 0 && nc < atoi(e)) return false;
+    }
     qmg_stencil_desc d = describe();
     double dev[2] = {0.0, 0.0};
     QMG_CHK(qmg_stencil_gamma5_deviation(&d, dev));

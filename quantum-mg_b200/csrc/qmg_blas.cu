@@ -290,14 +290,18 @@ static int multi_dot_pass(const qmg_cplx* const* xs, int k, const cd* y, long n,
   PtrPack<K> pk;
   for (int j = 0; j < K; j++) pk.p[j] = CCD(xs[j < k ? j : 0]);
   double tmp[2 * K];
+  // all K + 1 loads of an element are issued before the first product (written as one loop they came out as load, use,
+  // load, use ... -- two loads in flight per thread and 0.56 of the copy peak at k = 8, profiles/r03a_kernel_probe_blas.txt)
   int rc = launch_reduce<2 * K>(n, [=] __device__(long i, double (&acc)[2 * K]) {
-    cd b = y[i];
+    const cd b = __ldg(y + i);
+    cd a[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) a[j] = ld_stream(pk.p[j] + i);
 #pragma unroll
     for (int j = 0; j < K; j++)
     {
-      cd a = pk.p[j][i];
-      acc[2 * j] += a.x * b.x + a.y * b.y;
-      acc[2 * j + 1] += a.x * b.y - a.y * b.x;
+      acc[2 * j] += a[j].x * b.x + a[j].y * b.y;
+      acc[2 * j + 1] += a[j].x * b.y - a[j].y * b.x;
     }
   }, tmp);
   if (rc) return rc;

@@ -560,7 +560,7 @@ template <int NC, int TK, int TY, int SPLIT> struct TmaTile
       const cd* bx = sHx + (size_t)nx * LPS + (hf * R) * NC + c2;      // backward: column a = c2 of the neighbour's block, rows b of this thread
       const cd* by = sHy + (size_t)ny * LPS + (hf * R) * NC + c2;
       cd acc[R];
-      cd back = zero;
+      cd backx = zero, backy = zero;      // two independent chains
 #pragma unroll
       for (int i = 0; i < R; i++)
       {
@@ -570,9 +570,10 @@ template <int NC, int TK, int TY, int SPLIT> struct TmaTile
         cfma(t, hy[i * NC], V1);
         acc[i] = t;
         // s_a s_b conj(B[b][a]) in(x - mu)[b], b = hf R + i: the sign is applied once below
-        cfma_conj(back, bx[i * NC], v2[i]);
-        cfma_conj(back, by[i * NC], v3[i]);
+        cfma_conj(backx, bx[i * NC], v2[i]);
+        cfma_conj(backy, by[i * NC], v3[i]);
       }
+      cd back = cadd(backx, backy);
       // rows b of this thread all lie in one half of the dof when R divides NC / 2: one sign per thread
       static_assert((NC / 2) % R == 0, "TmaTile: the rows of a thread must not straddle the two chiral halves");
       const double sg = (top == (2 * hf * R < NC)) ? 1.0 : -1.0;
@@ -632,21 +633,23 @@ __global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT >
   cd* buf = reinterpret_cast<cd*>(tma_smem + 128);
   const int tid = threadIdx.x;
   const int k0 = blockIdx.x * TK, y0 = a.y_off + blockIdx.y * TY;
-  if (tid == 0)
-  {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
+  // warp 0 sets the barrier up and issues the copies at once; the other warps only meet the barrier after their clover
+  // loads are in flight (the __syncthreads orders the initialisation before everybody's wait)
   if (tid < 32)
   {
-    if (tid == 0) mbar_expect_tx(bar, T::BYTES);
+    if (tid == 0)
+    {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, T::BYTES);
+    }
     __syncwarp();
     T::stage(a, buf, bar, k0, y0, tid);
   }
   cd CLc[T::PASSES][T::R];
   cd RBc[T::PASSES];
   T0::clover(a, k0, y0, tid, CLc, RBc);
+  __syncthreads();
   mbar_wait(bar, 0);
   T::compute(a, buf, k0, y0, tid, CLc, RBc);
 }
@@ -664,12 +667,16 @@ template <int NC, int TK, int TY, int SPLIT = 1> static int launch_tma(const Ste
   return 0;
 }
 
-// nc = 8 patches: the TMA-staged kernel (QMG_TILE=3: the cp.async-staged one; 2: cp.async with one thread per column)
+// nc = 8 patches.  Default: the cp.async-staged kernel.  QMG_TILE=4 selects the TMA-staged one: a third fewer instructions
+// (issue utilisation 64 % -> 35 %) and the same time inside a power-capped solve (8192^2 K-cycle 6.12 s vs 6.08 s), but
+// 7 % slower as a back-to-back burst (2.63 vs 2.44 ms on 2048^2): both flavours wait on their tile with two CTAs per SM
+// (registers and shared memory both stop at two), and that wait, not the staging instructions, is what bounds them
+// (profiles/r03d_ncu_tile_tma_vs_cp_async.txt).  QMG_TILE=2: cp.async with one thread per column.
 static int launch_tile8(const StencilKArgs& a)
 {
   if (rt().tile_kernel == 2) return launch_tile<8, 4, 4, 1>(a);
-  if (rt().tile_kernel == 3) return launch_tile<8, 4, 4, 2>(a);
-  return launch_tma<8, 4, 4, 2>(a);
+  if (rt().tile_kernel == 4) return launch_tma<8, 4, 4, 2>(a);
+  return launch_tile<8, 4, 4, 2>(a);
 }
 
 // Any nc (DWF Ls = 6, 12, 24, 32 give nc = 12, 24, 48, 64): one thread per

@@ -705,6 +705,19 @@ struct KCycleH
   int ip[15]; double dp[5]; int verbosity;
 };
 
+// B200 extension (see kcycle_setup_link_compressed below): switch every operator to its link-compressed apply as soon as it
+// exists, so that the null-vector solves of the set-up already run on clover / +x / +y blocks
+inline int& setup_link_compressed() { static int on = 0; return on; }
+inline void maybe_link_compress(Stencil2D* s)
+{
+#ifdef QMG_B200_HOST
+  // only where the shared-memory tile kernel exists (nc >= 4): at nc = 2 the link-compressed apply saves DRAM traffic but no time
+  if (setup_link_compressed() && s != 0 && s->get_lattice()->get_nc() >= 4) s->enable_gamma5_hermitian_apply();
+#else
+  (void)s;
+#endif
+}
+
 // null vectors -> TransferMG -> Galerkin coarse operator, level by level, on top of h->op (n13 :250-416, n16 :318-440)
 inline void kcycle_build_hierarchy(KCycleH* h)
 {
@@ -726,6 +739,7 @@ inline void kcycle_build_hierarchy(KCycleH* h)
     Lattice2D* fl = h->lats[i - 1];
     const long nf = fl->get_size_cv();
     Stencil2D* fop = h->mg->get_stencil(i - 1);
+    maybe_link_compress(fop);
     std::vector<capi_cd*> nv(coarse_dof);
     for (int j = 0; j < coarse_dof; j++) { nv[j] = capi_alloc(nf); zero_vector(nv[j], nf); }
     for (int j = 0; j < coarse_dof / 2; j++)
@@ -1040,6 +1054,15 @@ void CAPI(kcycle_solve)(void* h_, const capi_cd* b, capi_cd* x_out, int outer_ty
   info[6] = h->setup_seconds; info[7] = h->null_ops;
   if (x_out != 0) capi_get(x_out, xfull, n);
   h->mg->check_in(bd, 0); h->mg->check_in(x, 0); h->mg->check_in(bprep, 0); h->mg->check_in(xfull, 0);
+}
+// B200 extension: 1 = hierarchies built from now on switch each level's operator to the link-compressed apply the moment it is
+// built (checked per level, like kcycle_gamma5_hermitian), so the BiCGstab-L null-vector solves of the set-up use it too.
+// Reference build: no-op.  Returns the previous setting.
+int CAPI(kcycle_setup_link_compressed)(int on)
+{
+  const int was = capi::setup_link_compressed();
+  capi::setup_link_compressed() = on ? 1 : 0;
+  return was;
 }
 // B200 extension: link-compressed applies on every level of the hierarchy whose stored blocks obey the gamma5-hermitian
 // relation (checked per level); returns the number of levels switched.  Reference build: 0.

@@ -413,27 +413,8 @@ def test_apply_residual_epilogue(qmg_gpu, nc, herm):
     L = 32
     n = L * L * nc
     if herm:
-        # a gamma5-hermitian nc = 8 link set: forward blocks random, backward blocks from the relation
-        rng = np.random.default_rng(5)
-        V = L * L
-        hop = (rng.normal(size=(4, V, nc, nc)) + 1j * rng.normal(size=(4, V, nc, nc)))
-        s = np.where(np.arange(nc) < nc // 2, 1.0, -1.0)
-        import latutil as lu
-        idx = np.arange(V)
-        X = Y = L
-        xh = X // 2
-        p_, rem = np.divmod(idx, xh * Y)
-        y_, k_ = np.divmod(rem, xh)
-        x_ = 2 * k_ + ((y_ + p_) & 1)
-        def site(x, y):
-            x %= X; y %= Y
-            par = (x + y) & 1
-            return (y + par * Y) * xh + x // 2
-        for mu, (dx, dy) in ((2, (-1, 0)), (3, (0, -1))):
-            nb = site(x_ + dx, y_ + dy)
-            hop[mu] = (s[None, :, None] * s[None, None, :]) * np.conj(np.swapaxes(hop[mu - 2][nb], 1, 2))
-        cl = rng.normal(size=(V, nc, nc)) + 1j * rng.normal(size=(V, nc, nc))
-        clover, hopping = dev(qmg, cl.reshape(-1)), dev(qmg, hop.reshape(-1))
+        cl, hop = _herm_stencil(L, nc, 5)
+        clover, hopping = dev(qmg, cl), dev(qmg, hop)
         d = qmg.stencil_desc(L, L, nc, clover, hopping, shift=0.3, gamma5_hermitian=True)
         assert qmg.stencil_gamma5_deviation(d) < 1e-14
     else:
@@ -451,6 +432,59 @@ def test_apply_residual_epilogue(qmg_gpu, nc, herm):
     qmg.check(lib.qmg_stencil_apply_residual(C.byref(d), C.c_int(15), C.c_int(15), qmg.ptr(b2), qmg.ptr(x), qmg.ptr(b2)))
     assert np.array_equal(host(b2), host(want))
     assert lib.qmg_stencil_apply_residual(C.byref(d), C.c_int(15), C.c_int(15), qmg.ptr(x), qmg.ptr(x), qmg.ptr(b)) != 0   # lhs == rhs refused
+
+
+def _herm_stencil(L, nc, seed):
+    """A random gamma5-hermitian link set: forward blocks random, backward blocks s s conj(forward of the neighbour)^T."""
+    rng = np.random.default_rng(seed)
+    V = L * L
+    hop = rng.normal(size=(4, V, nc, nc)) + 1j * rng.normal(size=(4, V, nc, nc))
+    s = np.where(np.arange(nc) < nc // 2, 1.0, -1.0)
+    x_, y_ = latutil.site_coords(L, L)
+    for mu, (dx, dy) in ((2, (-1, 0)), (3, (0, -1))):
+        nb = latutil.site_index((x_ + dx) % L, (y_ + dy) % L, L, L)
+        hop[mu] = (s[None, :, None] * s[None, None, :]) * np.conj(np.swapaxes(hop[mu - 2][nb], 1, 2))
+    cl = rng.normal(size=(V, nc, nc)) + 1j * rng.normal(size=(V, nc, nc))
+    return cl.reshape(-1), hop.reshape(-1)
+
+
+@pytest.mark.parametrize("L", [16, 64])
+def test_tile_kernel_flavours_agree(qmg_gpu, L):
+    """nc = 8 link-compressed apply: streaming (0), cp.async patch kernel with two / one thread per column (1, 2) and the
+    TMA-staged patch kernel (4: cp.async.bulk + mbarrier) against the stored-block apply -- plain, accumulating and with
+    the residual epilogue; L = 16 makes every patch touch the periodic wrap in x."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    nc = 8
+    n = L * L * nc
+    cl, hop = _herm_stencil(L, nc, 31)
+    clover, hopping = dev(qmg, cl), dev(qmg, hop)
+    stored = qmg.stencil_desc(L, L, nc, clover, hopping, shift=0.2, dof_shift=0.03)
+    herm = qmg.stencil_desc(L, L, nc, clover, hopping, shift=0.2, dof_shift=0.03, gamma5_hermitian=True)
+    assert qmg.stencil_gamma5_deviation(stored) < 1e-14
+    x, b, acc0 = (dev(qmg, latutil.gaussian_cv(n, sd)) for sd in (1, 2, 3))
+    want = qmg.cvec(n)
+    qmg.stencil_apply(stored, want, x)
+    want_acc = acc0.clone()
+    qmg.stencil_apply(stored, want_acc, x, qmg.APPLY_ALL | qmg.APPLY_ACCUMULATE)
+    want_res = qmg.cvec(n)
+    qmg.check(lib.qmg_stencil_apply_residual(C.byref(stored), C.c_int(15), C.c_int(15), qmg.ptr(want_res), qmg.ptr(x), qmg.ptr(b)))
+    old = lib.qmg_get_tile_kernel()
+    try:
+        for mode in (0, 1, 2, 4):
+            qmg.check(lib.qmg_set_tile_kernel(mode))
+            got = qmg.cvec(n)
+            qmg.stencil_apply(herm, got, x)
+            assert latutil.rel_l2(host(got), host(want)) < 1e-14, mode
+            got = acc0.clone()
+            qmg.stencil_apply(herm, got, x, qmg.APPLY_ALL | qmg.APPLY_ACCUMULATE)
+            assert latutil.rel_l2(host(got), host(want_acc)) < 1e-14, mode
+            got = qmg.cvec(n)
+            qmg.check(lib.qmg_stencil_apply_residual(C.byref(herm), C.c_int(15), C.c_int(15), qmg.ptr(got), qmg.ptr(x), qmg.ptr(b)))
+            assert latutil.rel_l2(host(got), host(want_res)) < 1e-14, mode
+    finally:
+        qmg.check(lib.qmg_set_tile_kernel(old))
 
 
 def test_in_place_hopping_is_sequential(ref, qmg_gpu):
