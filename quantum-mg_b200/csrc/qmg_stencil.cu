@@ -53,7 +53,10 @@ struct StencilKArgs
 // so only clover, H_{+x}, H_{+y} are fetched from HBM (3 of the 5 blocks); the neighbour's forward block was read by the
 // neighbouring site moments ago (same row for -x, previous row for -y) and comes out of L2.  The lane that owns element
 // (c1, c2) reads element (c2, c1) of that block: the same 16 nc^2 bytes per site, permuted inside the block.
-template <int NC, bool REDUCE, bool HERM>
+// RESID: the residual epilogue out = resid - A in.  A template parameter, not a run-time test: the plain instantiation must stay
+// the straight-line body ptxas schedules with every load ahead of the first FMA (a run-time `if (a.resid)` in the epilogue made
+// it interleave load, use, load, use: 3.61 -> 4.07 ms on the 8192^2 Wilson apply, profiles/r03h_ncu_stencil_wilson8192_regression.txt)
+template <int NC, bool REDUCE, bool HERM, bool RESID>
 __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, double* partials, unsigned int* counter, double* result)
 {
   constexpr int LPS = NC * NC;   // lanes per site
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
   const cd V3 = m3 ? ld_keep(s3) : zero;
   const cd VC = (has_cl || has_dg) ? ld_keep(a.in + site * NC + c2) : zero;
   const cd OLD = (writer && a.accumulate) ? a.out[idx] : zero;
-  const cd RB = (writer && a.resid != nullptr) ? ld_stream(a.resid + idx) : zero;
+  const cd RB = (RESID && writer) ? ld_stream(a.resid + idx) : zero;
   const cd DG = has_dg ? a.diag[p][(2 * c2 >= NC && NC > 1) ? 1 : 0] : zero;
 
   cd acc = zero;
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const StencilKArgs a, doub
   if (writer)
   {
     acc = cadd(acc, OLD);
-    if (a.resid != nullptr) acc = csub(RB, acc);
+    if (RESID) acc = csub(RB, acc);
     a.out[idx] = acc;
     if (REDUCE)
     {
@@ -786,12 +789,17 @@ static int launch_stencil(const StencilKArgs& a, int n_par, bool reduce)
   {
     double* partials = ensure_partials((size_t)grid.x * grid.y * grid.z * 3);
     if (partials == nullptr) return 1;
-    stencil_kernel<NC, true, false><<<grid, block, 0, r.stream>>>(a, partials, r.d_counter, r.d_result);
+    stencil_kernel<NC, true, false, false><<<grid, block, 0, r.stream>>>(a, partials, r.d_counter, r.d_result);
   }
   else if (a.herm && NC > 1)
-    stencil_kernel<NC, false, (NC > 1)><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
+  {
+    if (a.resid != nullptr) stencil_kernel<NC, false, (NC > 1), true><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
+    else stencil_kernel<NC, false, (NC > 1), false><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
+  }
+  else if (a.resid != nullptr)
+    stencil_kernel<NC, false, false, true><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
   else
-    stencil_kernel<NC, false, false><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
+    stencil_kernel<NC, false, false, false><<<grid, block, 0, r.stream>>>(a, nullptr, nullptr, nullptr);
   QMG_LAUNCH_CHECK();
   return 0;
 }

@@ -141,3 +141,32 @@ def test_c_abi_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stdout
     out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True)
     assert out.returncode == 0 and out.stdout.split()[1] == "1"
+
+
+def test_ctypes_stencil_desc_matches_the_c_header(tmp_path):
+    """qmg.StencilDesc, and the copy a binder would paste from INTEGRATION.md section 3, mirror qmg_stencil_desc field for field
+    (a binder that omits the trailing gamma5_hermitian / hop_halo_ym hands the library 12 bytes of garbage)."""
+    import ctypes as C
+    import qmg
+    hdr = open(os.path.join(ROOT, "include", "qmg_b200.h")).read()
+    body = re.search(r"typedef struct qmg_stencil_desc\s*\{(.*?)\}\s*qmg_stencil_desc;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            names += [re.sub(r"\[.*\]", "", n).strip(" *") for n in decl.split(None, 1)[1].replace("qmg_cplx*", "").replace("const", "").split(",")]
+    names = [n.split()[-1] for n in names]
+    assert names == [f[0] for f in qmg.StencilDesc._fields_]
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    snippet = doc[doc.index("class StencilDesc(C.Structure)"):doc.index("desc = StencilDesc()")]
+    assert re.findall(r'\("(\w+)",', snippet) == names
+    # same size and offsets as the C compiler sees them
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "qmg_b200.h"\nint main(void) { printf("%zu", sizeof(qmg_stencil_desc));\n'
+                   + "".join('printf(" %%zu", offsetof(qmg_stencil_desc, %s));\n' % n for n in names) + "return 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
+    assert got[0] == C.sizeof(qmg.StencilDesc)
+    assert got[1:] == [getattr(qmg.StencilDesc, n).offset for n in names]
