@@ -155,6 +155,20 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
             stored = out
             n_sw = kc.gamma5_hermitian(True)
             out = kc.solve(tol=tol, restart=restart, max_iter=100)
+            if os.environ.get("QMG_BENCH_PROFILE") == "1":
+                # one more solve with the per-entry-point profile on (every call bracketed by stream synchronisations: the
+                # shares are what to read, the total is slower than the timed solve above); rank 0 prints the table to stderr
+                import ctypes as C
+                import qmg
+                lib = qmg.lib()
+                lib.qmg_profile_reset(); lib.qmg_profile_enable(1)
+                prof = kc.solve(tol=tol, restart=restart, max_iter=100)
+                lib.qmg_profile_enable(0)
+                if rank == 0:
+                    sys.stdout.flush()
+                    lib.qmg_profile_report.restype = C.c_double
+                    lib.qmg_profile_report()
+                    sys.stderr.write("[bench] profiled solve: %.3f s, %d iterations (timed solve %.3f s)\n" % (prof["seconds"], prof["iter"], out["seconds"]))
             out["first_solve_seconds"], out["first_solve_iter"] = first["seconds"], first["iter"]
             out["link_compressed_levels"] = n_sw
             out["seconds_stored_blocks"], out["iter_stored_blocks"] = stored["seconds"], stored["iter"]

@@ -2,8 +2,9 @@
 // /root/reference/multigrid/stateful_multigrid.h:915,947; tests/n18_rbjacobi_stencil_test/rbjacobi_stencil_test.cpp:154).
 // Iteration as stated by the oracle (oracle/qlinalg_shim/inverters/generic_gcr.h; quantum-linalg itself is
 // un-vendored): untruncated GCR, classical Gram-Schmidt of A r against every stored A p_i.
-// Device formulation: the k projections are ONE multi-dot pass over the stored A p_i, the two basis updates are
-// two multi-axpy passes, and (alpha, x, r, |r|^2) is one fused (dot, norm) pass plus one fused update.
+// Device formulation (qmg_gcr_orthogonalize + qmg_krylov_step): the k projections are ONE multi-dot pass over the stored
+// A p_i whose results stay on the device, the coefficients are formed there, both basis updates are ONE pass that also
+// forms <Ap_k|r> and |Ap_k|^2, and (alpha, x, r, |r|^2) is one fused update -- one host wait per iteration.
 #ifndef QMG_B200_GCR
 #define QMG_B200_GCR
 
@@ -35,7 +36,6 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
   complex<double>* z = precond ? allocate_vector<complex<double> >(size) : 0;
   complex<double>* scratch = 0;
   std::vector<complex<double>*> p, Ap;
-  std::vector<double> ApNormSq;
   double bsq = (hints != 0 && hints->bnorm2 >= 0.0) ? hints->bnorm2 : norm2sq(phi0, size);
   const double bsqrt = sqrt(bsq);
   complex<double>* r_in = r;
@@ -57,45 +57,59 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
 
   int k = 0;
   bool converged = sqrt(rsq) < eps * bsqrt;
+  bool stepped = false;
+  // device scratch of the orthogonalisation: <Ap_i|Ap_k> of the current step, |Ap_i|^2 of every step so far (the coefficients
+  // beta_i = -<Ap_i|Ap_k> / |Ap_i|^2 are formed on the device, qmg_gcr_orthogonalize: one host wait per iteration, not two)
+  double* dev_dots = 0; double* dev_apn = 0;
   if (!converged && max_iter > 0)
   {
+    long cap = max_iter < 64 ? max_iter + 1 : 64;          // grown on demand: an unrestarted solve may be allowed 10^8 iterations
+    dev_dots = allocate_vector<double>(2 * cap);
+    dev_apn = allocate_vector<double>(cap);
     p.push_back(allocate_vector<complex<double> >(size));
     Ap.push_back(allocate_vector<complex<double> >(size));
     if (precond) { if (zero_for_precond) zero_vector(p[0], size); precond(p[0], r_in, size, precond_info, &verb_prec); }
     else copy_vector(p[0], r_in, size);
     matrix_vector(Ap[0], p[0], extra_info); invif.ops_count++; executed++;
+    bool dots_ready = false;
     for (k = 1; k <= max_iter; k++)
     {
       const int c = k - 1;
-      // alpha = <Ap|r> / <Ap|Ap> formed on the device; x += alpha p ; r -= alpha Ap ; |r|^2 : one host wait per step
+      // alpha = <Ap|r> / <Ap|Ap> formed on the device; x += alpha p ; r -= alpha Ap ; |r|^2 : the one host wait of the step
       double step[5];
-      QMG_CHK(qmg_krylov_step(1.0, P(p[c]), P(Ap[c]), (zero_start && k == 1) ? 0 : P(phi), P(phi), P(r_in), P(r), 0, size, 0, step));
+      QMG_CHK(qmg_krylov_step(1.0, P(p[c]), P(Ap[c]), (zero_start && k == 1) ? 0 : P(phi), P(phi), P(r_in), P(r), 0, size,
+                              dots_ready ? QMG_STEP_DOTS_READY : 0, step, dev_apn + c));
       r_in = r;
+      stepped = true;
       rsq = step[0];
-      ApNormSq.push_back(step[3]);
       say(verb, VERB_DETAIL, name, "", false, false, k, invif.ops_count, sqrt(rsq) / bsqrt);
       if (sqrt(rsq) < eps * bsqrt) { converged = true; break; }
       if (k == max_iter) break;
 
-      // next direction: d = M^-1 r (or r), A d straight into its slot, then project out the stored set
+      // next direction: d = M^-1 r (or r), A d straight into its slot, then project out the stored set on the device
       p.push_back(allocate_vector<complex<double> >(size));
       Ap.push_back(allocate_vector<complex<double> >(size));
       complex<double>* dir = r;
       if (precond) { if (zero_for_precond) zero_vector(z, size); precond(z, r, size, precond_info, &verb_prec); dir = z; }
       matrix_vector(Ap[k], dir, extra_info); invif.ops_count++; executed++;
-      std::vector<double> beta(2 * k);
-      std::vector<const qmg_cplx*> ptrs(k);
-      for (int i = 0; i < k; i++) ptrs[i] = P(Ap[i]);
-      QMG_CHK(qmg_multi_dot(ptrs.data(), k, P(Ap[k]), size, beta.data()));
-      for (int i = 0; i < k; i++) { beta[2 * i] = -beta[2 * i] / ApNormSq[i]; beta[2 * i + 1] = -beta[2 * i + 1] / ApNormSq[i]; }
-      QMG_CHK(qmg_multi_axpyz(beta.data(), ptrs.data(), k, P(Ap[k]), P(Ap[k]), size));
-      for (int i = 0; i < k; i++) ptrs[i] = P(p[i]);
-      QMG_CHK(qmg_multi_axpyz(beta.data(), ptrs.data(), k, P(dir), P(p[k]), size));
+      if (k + 1 > cap)
+      {
+        double* grown = allocate_vector<double>(2 * cap);
+        copy_vector(grown, dev_apn, cap);
+        deallocate_vector(&dev_apn); deallocate_vector(&dev_dots);
+        cap *= 2;
+        dev_apn = grown;
+        dev_dots = allocate_vector<double>(2 * cap);
+      }
+      std::vector<const qmg_cplx*> aps(k), ps(k);
+      for (int i = 0; i < k; i++) { aps[i] = P(Ap[i]); ps[i] = P(p[i]); }
+      QMG_CHK(qmg_gcr_orthogonalize(aps.data(), ps.data(), k, P(Ap[k]), P(dir), P(p[k]), P(r), size, dev_dots, dev_apn));
+      dots_ready = true;
     }
   }
   if (k > max_iter) k = max_iter;
   // a zero start that took no step (b = 0, or no iterations allowed) still owes the caller its x = 0
-  if (zero_start && ApNormSq.empty()) zero_vector(phi, size);
+  if (zero_start && !stepped) zero_vector(phi, size);
 
   invif.ops_count++;
   if ((flags & SOLVE_NO_FINAL_RESIDUAL) && converged) invif.resSq = rsq;     // converged: nothing downstream reads the true residual
@@ -111,6 +125,8 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
   if (hints != 0) hints->executed += executed;
 
   for (size_t i = 0; i < p.size(); i++) { deallocate_vector(&p[i]); deallocate_vector(&Ap[i]); }
+  if (dev_dots != 0) deallocate_vector(&dev_dots);
+  if (dev_apn != 0) deallocate_vector(&dev_apn);
   deallocate_vector(&r);
   if (scratch != 0) deallocate_vector(&scratch);
   if (z != 0) deallocate_vector(&z);

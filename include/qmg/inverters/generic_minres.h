@@ -69,7 +69,7 @@ inline inversion_info minres_core(complex<double>* phi, complex<double>* phi0, i
     const bool want_b = first && bsq < 0.0 && !x_only;
     double step[5];
     QMG_CHK(qmg_krylov_step(omega, P(r_in), P(p), first ? 0 : P(phi), P(x_only && acc != 0 ? acc : phi), P(r_in), P(r),
-                            x_only && acc != 0 ? P(acc) : 0, size, (want_b ? QMG_STEP_WANT_RNORM : 0) | (x_only ? QMG_STEP_X_ONLY : 0), step));
+                            x_only && acc != 0 ? P(acc) : 0, size, (want_b ? QMG_STEP_WANT_RNORM : 0) | (x_only ? QMG_STEP_X_ONLY : 0), step, 0));
     r_in = r;
     if (x_only) { acc_done = (acc != 0); break; }     // nobody reads this residual: no reduction, no host wait
     if (want_b) { bsq = step[4]; bsqrt = sqrt(bsq); }

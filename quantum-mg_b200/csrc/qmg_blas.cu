@@ -187,12 +187,7 @@ int qmg_dot_norm(const qmg_cplx* x_, const qmg_cplx* y_, long n, double* result3
 {
   QMG_REQUIRE_INIT();
   const cd* x = CCD(x_); const cd* y = CCD(y_);
-  return launch_reduce<3>(n, [=] __device__(long i, double (&acc)[3]) {
-    cd a = x[i], b = y[i];
-    acc[0] += a.x * b.x + a.y * b.y;
-    acc[1] += a.x * b.y - a.y * b.x;
-    acc[2] += a.x * a.x + a.y * a.y;
-  }, result3);
+  return launch_reduce<3>(n, [=] __device__(long i, double (&acc)[3]) { dot_acc3(acc, x[i], y[i]); }, result3);
 }
 
 int qmg_norm2sq(const qmg_cplx* x_, long n, double* result)
@@ -403,12 +398,7 @@ int qmg_step_xr_norm(double omega, const qmg_cplx* p_, const qmg_cplx* q_, qmg_c
   const cd* p = CCD(p_); const cd* q = CCD(q_); cd* x = CD(x_); cd* r = CD(r_);
   double* dres = rtm.d_result + 64;                    // device slot of the dot products
   double* aux = rtm.h_result + 256;                    // mapped host slot the second kernel copies them to
-  int rc = launch_reduce_keep<3>(n, [=] __device__(long i, double (&acc)[3]) {
-    cd a = q[i], b = r[i];
-    acc[0] += a.x * b.x + a.y * b.y;
-    acc[1] += a.x * b.y - a.y * b.x;
-    acc[2] += a.x * a.x + a.y * a.y;
-  }, dres);
+  int rc = launch_reduce_keep<3>(n, [=] __device__(long i, double (&acc)[3]) { dot_acc3(acc, q[i], r[i]); }, dres);
   if (rc) return rc;
   double out[1];
   rc = launch_reduce<1>(n, [=] __device__(long i, double (&acc)[1]) {
@@ -432,6 +422,121 @@ int qmg_step_xr_norm(double omega, const qmg_cplx* p_, const qmg_cplx* q_, qmg_c
   return 0;
 }
 
+} // extern "C"
+
+namespace qmg {
+// GCR orthogonalisation with the coefficients formed ON THE DEVICE, the two basis updates in one pass, and the dot
+// products of the step that follows folded in:
+//   beta_j = -dots_j / apn_j                        (dots_j = <Ap_j|Ap_k> from the multi-dot pass, apn_j = |Ap_j|^2 of step j)
+//   Ap_k = (first ? Ap_k : Ap_k) + sum_j beta_j Ap_j ;  p_k = (first ? dir : p_k) + sum_j beta_j p_j
+//   last pass only: { <Ap_k|r>, |Ap_k|^2 } -> result (device)
+// One pass holds K vectors; the host chains passes of 8 in the order qmg_multi_axpyz uses, so the sums come out bit-identical.
+template <int K, bool DOTS>
+__global__ void __launch_bounds__(kEwBlock) gcr_ortho_kernel(long n, PtrPack<K> Ap, PtrPack<K> P, int k, cd* apk, const cd* dir,
+                                                             cd* pk, const cd* __restrict__ r, const double* __restrict__ dots,
+                                                             const double* __restrict__ apn, double* partials, unsigned int* counter, double* result)
+{
+  __shared__ double smem[(kEwBlock / 32) * 3];
+  cd beta[K];
+#pragma unroll
+  for (int j = 0; j < K; j++)
+  {
+    const double nr = (j < k) ? apn[j] : 1.0;
+    beta[j] = (j < k) ? cmake(__ddiv_rn(-dots[2 * j], nr), __ddiv_rn(-dots[2 * j + 1], nr)) : cmake(0.0, 0.0);
+  }
+  double acc[3] = {0.0, 0.0, 0.0};
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    cd a[K], b[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) { a[j] = ld_stream(Ap.p[j] + i); b[j] = ld_stream(P.p[j] + i); }
+    cd t = apk[i], u = dir[i];
+#pragma unroll
+    for (int j = 0; j < K; j++) { cfma(t, beta[j], a[j]); cfma(u, beta[j], b[j]); }
+    apk[i] = t; pk[i] = u;
+    if (DOTS) dot_acc3(acc, t, r[i]);
+  }
+  if (DOTS) grid_reduce_finish<3>(acc, smem, partials, counter, result);
+}
+
+template <int K>
+static int gcr_ortho_pass(long n, const qmg_cplx* const* Ap, const qmg_cplx* const* P, int k, cd* apk, const cd* dir, cd* pk, const cd* r,
+                          const double* dots, const double* apn, bool with_dots, double* result_dev)
+{
+  PtrPack<K> a, b;
+  for (int j = 0; j < K; j++) { a.p[j] = CCD(Ap[j < k ? j : 0]); b.p[j] = CCD(P[j < k ? j : 0]); }
+  Runtime& rtm = rt();
+  int grid = ew_grid(n);
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  if (with_dots)
+  {
+    gcr_ortho_kernel<K, true><<<grid, kEwBlock, 0, rtm.stream>>>(n, a, b, k, apk, dir, pk, r, dots, apn, rtm.d_partials, rtm.d_counter, result_dev);
+    QMG_LAUNCH_CHECK();
+    return skip_result(result_dev, 3);
+  }
+  gcr_ortho_kernel<K, false><<<grid, kEwBlock, 0, rtm.stream>>>(n, a, b, k, apk, dir, pk, r, dots, apn, nullptr, nullptr, nullptr);
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+} // namespace qmg
+
+extern "C" {
+
+// Orthogonalise the new GCR direction against the k stored ones and prepare the step, without a host round trip:
+//   dots_dev[2j..] = <Ap[j]|Ap_k>  (multi-dot, kept on the device) ; beta_j = -dots_j / apn_dev[j] ;
+//   Ap_k += sum beta_j Ap[j] ; p_k = dir + sum beta_j p[j] ; { <Ap_k|r>, |Ap_k|^2 } left where qmg_krylov_step with
+//   QMG_STEP_DOTS_READY expects them.  Same sums in the same order as qmg_multi_dot + host division + 2 qmg_multi_axpyz +
+//   the dot pass of qmg_krylov_step: bit-identical.  k = 0: only the dot products (p_k = dir is the caller's copy or alias).
+int qmg_gcr_orthogonalize(const qmg_cplx* const* Ap_host, const qmg_cplx* const* p_host, int k, qmg_cplx* Apk_, const qmg_cplx* dir_, qmg_cplx* pk_,
+                          const qmg_cplx* r_, long n, double* dots_dev, const double* apn_dev)
+{
+  QMG_REQUIRE_INIT();
+  if (n <= 0) return fail_msg("qmg_gcr_orthogonalize: empty vector");
+  cd* apk = CD(Apk_); const cd* dir = CCD(dir_); cd* pk = CD(pk_); const cd* r = CCD(r_);
+  double* dres = rt().d_result + 64;
+  int rc;
+  // 1. the k projections, left on the device (passes of at most 8 like qmg_multi_dot)
+  int done = 0;
+  while (done < k)
+  {
+    const int left = k - done;
+    int take;
+    const cd* y = apk;
+#define QMG_MDOT_KEEP(KK) { PtrPack<KK> pk_; for (int j = 0; j < KK; j++) pk_.p[j] = CCD(Ap_host[done + (j < take ? j : 0)]); \
+      rc = launch_reduce_keep<2 * KK>(n, [=] __device__(long i, double (&acc)[2 * KK]) { const cd b = __ldg(y + i); cd a[KK]; \
+        _Pragma("unroll") for (int j = 0; j < KK; j++) a[j] = ld_stream(pk_.p[j] + i); \
+        _Pragma("unroll") for (int j = 0; j < KK; j++) { acc[2 * j] += a[j].x * b.x + a[j].y * b.y; acc[2 * j + 1] += a[j].x * b.y - a[j].y * b.x; } }, dots_dev + 2 * done); }
+    if (left >= 8) { take = 8; QMG_MDOT_KEEP(8) }
+    else if (left > 4) { take = left; QMG_MDOT_KEEP(8) }
+    else if (left > 2) { take = left; QMG_MDOT_KEEP(4) }
+    else if (left == 2) { take = 2; QMG_MDOT_KEEP(2) }
+    else { take = 1; QMG_MDOT_KEEP(1) }
+#undef QMG_MDOT_KEEP
+    if (rc) return rc;
+    done += take;
+  }
+  // 2. both basis updates per pass of 8; the last pass also forms the step's dot products
+  done = 0;
+  const cd* src_dir = dir;
+  do
+  {
+    const int left = k - done;
+    const int take = left >= 8 ? 8 : left;
+    const bool last = (done + take >= k);
+    const qmg_cplx* const* A = Ap_host + done; const qmg_cplx* const* Pp = p_host + done;
+    const double* dd = dots_dev + 2 * done; const double* nn = apn_dev + done;
+    if (take > 4) rc = gcr_ortho_pass<8>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
+    else if (take > 2) rc = gcr_ortho_pass<4>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
+    else if (take == 2) rc = gcr_ortho_pass<2>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
+    else rc = gcr_ortho_pass<1>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);     // take == 0 (k == 0): p_k = dir, dots only
+    if (rc) return rc;
+    done += take;
+    src_dir = pk;        // later passes continue in place
+  } while (done < k);
+  return 0;
+}
+
 // The general Krylov step behind the K-cycle's smoothers and (flexible) GCR solves: the same two kernels as
 // qmg_step_xr_norm -- so every sum is formed in the same order and a step without flags is bit-identical to it -- with
 // the start-up and wind-down work of a solve folded in:
@@ -444,7 +549,7 @@ int qmg_step_xr_norm(double omega, const qmg_cplx* p_, const qmg_cplx* q_, qmg_c
 // needs) to the dot-product pass, which reads r_in anyway.
 // result5 = { |r_out|^2, Re<q|r_in>, Im<q|r_in>, <q|q>, |r_in|^2 }; with QMG_STEP_X_ONLY nothing is returned.
 int qmg_krylov_step(double omega, const qmg_cplx* p_, const qmg_cplx* q_, const qmg_cplx* x_in_, qmg_cplx* x_out_,
-                    const qmg_cplx* r_in_, qmg_cplx* r_out_, const qmg_cplx* acc_, long n, int flags, double* result5)
+                    const qmg_cplx* r_in_, qmg_cplx* r_out_, const qmg_cplx* acc_, long n, int flags, double* result5, double* qq_dev)
 {
   QMG_REQUIRE_INIT();
   if (n <= 0) return fail_msg("qmg_krylov_step: empty vector");
@@ -454,22 +559,22 @@ int qmg_krylov_step(double omega, const qmg_cplx* p_, const qmg_cplx* q_, const 
   double* dres = rtm.d_result + 64;                    // device slot of the dot products
   double* aux = rtm.h_result + 256;                    // mapped host slot the second kernel copies them to
   const bool want_rnorm = (flags & QMG_STEP_WANT_RNORM) != 0;
-  int rc;
-  if (want_rnorm)
+  int rc = 0;
+  if (flags & QMG_STEP_DOTS_READY)
+  {
+    // <q|r_in>, |q|^2 are already in the device slot (qmg_gcr_orthogonalize left them there)
+    if (want_rnorm) return fail_msg("qmg_krylov_step: QMG_STEP_DOTS_READY and QMG_STEP_WANT_RNORM exclude each other");
+  }
+  else if (want_rnorm)
     rc = launch_reduce_keep<4>(n, [=] __device__(long i, double (&acc)[4]) {
-      cd a = q[i], b = rin[i];
-      acc[0] += a.x * b.x + a.y * b.y;
-      acc[1] += a.x * b.y - a.y * b.x;
-      acc[2] += a.x * a.x + a.y * a.y;
+      const cd a = q[i], b = rin[i];
+      double a3[3] = { acc[0], acc[1], acc[2] };
+      dot_acc3(a3, a, b);
+      acc[0] = a3[0]; acc[1] = a3[1]; acc[2] = a3[2];
       acc[3] += b.x * b.x + b.y * b.y;
     }, dres);
   else
-    rc = launch_reduce_keep<3>(n, [=] __device__(long i, double (&acc)[3]) {
-      cd a = q[i], b = rin[i];
-      acc[0] += a.x * b.x + a.y * b.y;
-      acc[1] += a.x * b.y - a.y * b.x;
-      acc[2] += a.x * a.x + a.y * a.y;
-    }, dres);
+    rc = launch_reduce_keep<3>(n, [=] __device__(long i, double (&acc)[3]) { dot_acc3(acc, q[i], rin[i]); }, dres);
   if (rc) return rc;
   if (flags & QMG_STEP_X_ONLY)
     return launch_ew(n, [=] __device__(long i) {
@@ -485,7 +590,7 @@ int qmg_krylov_step(double omega, const qmg_cplx* p_, const qmg_cplx* q_, const 
     const double d0 = dres[0], d1 = dres[1], d2 = dres[2];
     const cd a = cmake(__ddiv_rn(__dmul_rn(omega, d0), d2), __ddiv_rn(__dmul_rn(omega, d1), d2));
     const cd ma = cmake(-a.x, -a.y);
-    if (i == 0) { aux[0] = d0; aux[1] = d1; aux[2] = d2; if (want_rnorm) aux[3] = dres[3]; __threadfence_system(); }
+    if (i == 0) { aux[0] = d0; aux[1] = d1; aux[2] = d2; if (want_rnorm) aux[3] = dres[3]; if (qq_dev != nullptr) qq_dev[0] = d2; __threadfence_system(); }
     cd pi = p[i];
     cd ri = rin[i];
     cd xi = (xin != nullptr) ? xin[i] : cmake(0.0, 0.0);

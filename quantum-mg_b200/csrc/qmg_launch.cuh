@@ -7,6 +7,15 @@ namespace qmg {
 
 constexpr int kEwBlock = 256;
 
+// <a|b> and |a|^2 accumulated with pinned roundings, so that every kernel that forms these sums over the same
+// element -> thread assignment produces the same bits (dot_norm, the Krylov step kernels, the fused GCR orthogonalisation)
+__device__ __forceinline__ void dot_acc3(double (&acc)[3], const cd a, const cd b)
+{
+  acc[0] = __dadd_rn(acc[0], __fma_rn(a.y, b.y, __dmul_rn(a.x, b.x)));
+  acc[1] = __dadd_rn(acc[1], __fma_rn(-a.y, b.x, __dmul_rn(a.x, b.y)));
+  acc[2] = __dadd_rn(acc[2], __fma_rn(a.y, a.y, __dmul_rn(a.x, a.x)));
+}
+
 template <class F>
 __global__ void __launch_bounds__(kEwBlock) ew_kernel(long n, F f)
 {

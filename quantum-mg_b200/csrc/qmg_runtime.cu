@@ -321,7 +321,7 @@ int qmg_zero_bytes(void* dptr, size_t bytes)
   QMG_CUDA(cudaMemsetAsync(dptr, 0, bytes, rt().stream));
   return 0;
 }
-int qmg_set_tile_kernel(int mode) { QMG_REQUIRE_INIT(); if (mode < 0 || mode > 4) return fail_msg("qmg_set_tile_kernel: mode must be 0 .. 4"); rt().tile_kernel = mode; return 0; }
+int qmg_set_tile_kernel(int mode) { QMG_REQUIRE_INIT(); if (mode < 0 || mode > 6) return fail_msg("qmg_set_tile_kernel: mode must be 0 .. 6"); rt().tile_kernel = mode; return 0; }
 int qmg_get_tile_kernel(void) { return rt().tile_kernel; }
 int qmg_profile_enable(int on) { rt().profile = on ? 1 : 0; return 0; }
 int qmg_profile_reset(void) { prof_table().clear(); return 0; }

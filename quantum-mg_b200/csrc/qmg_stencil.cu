@@ -392,7 +392,7 @@ template <int NC, int TK, int TY, int SPLIT = 1> struct Tile
 
 // one patch per CTA
 template <int NC, int TK, int TY, int SPLIT>
-__global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT > 1 ? 2 : 1)) stencil_tile_kernel(const StencilKArgs a)
+__global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT > 1 ? 1024 / TileDims<NC, TK, TY, SPLIT>::THREADS : 1)) stencil_tile_kernel(const StencilKArgs a)
 {
   typedef Tile<NC, TK, TY, SPLIT> T;
   extern __shared__ cd tile_smem[];
@@ -627,7 +627,7 @@ template <int NC, int TK, int TY, int SPLIT> struct TmaTile
 };
 
 template <int NC, int TK, int TY, int SPLIT>
-__global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT > 1 ? 2 : 1)) stencil_tma_kernel(const StencilKArgs a)
+__global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT > 1 ? 1024 / TileDims<NC, TK, TY, SPLIT>::THREADS : 1)) stencil_tma_kernel(const StencilKArgs a)
 {
   typedef TmaTile<NC, TK, TY, SPLIT> T;
   typedef Tile<NC, TK, TY, SPLIT> T0;          // the clover / residual register prefetch is shared with the cp.async kernel
@@ -679,6 +679,9 @@ static int launch_tile8(const StencilKArgs& a)
 {
   if (rt().tile_kernel == 2) return launch_tile<8, 4, 4, 1>(a);
   if (rt().tile_kernel == 4) return launch_tma<8, 4, 4, 2>(a);
+  // experiments: 16-site patches (4 rows x 4 sites), 256 threads, four CTAs per SM instead of two
+  if (rt().tile_kernel == 5) return launch_tile<8, 2, 4, 2>(a);
+  if (rt().tile_kernel == 6) return launch_tma<8, 2, 4, 2>(a);
   return launch_tile<8, 4, 4, 2>(a);
 }
 

@@ -381,7 +381,7 @@ def test_krylov_step_flavours(qmg_gpu):
         wx, wr = host(x), host(r)
         q, x, r = dev(qmg, q0), dev(qmg, x0), dev(qmg, r0)
         out = (C.c_double * 5)()
-        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(x), qmg.ptr(r), qmg.ptr(r), NULL, C.c_long(n), 0, out))
+        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(x), qmg.ptr(r), qmg.ptr(r), NULL, C.c_long(n), 0, out, NULL))
         assert np.array_equal(host(x), wx) and np.array_equal(host(r), wr) and tuple(out)[:4] == tuple(want4), n
         # (b) first step from a zero start: x written, b read in place of r, |b|^2 returned == qmg_norm2sq(b)
         q, b = dev(qmg, q0), dev(qmg, r0)
@@ -390,7 +390,7 @@ def test_krylov_step_flavours(qmg_gpu):
         wx, wr = host(x), host(r)
         x2 = dev(qmg, x0)          # garbage on entry: must not be read
         r2 = dev(qmg, a0)
-        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(b), qmg.ptr(q), NULL, qmg.ptr(x2), qmg.ptr(b), qmg.ptr(r2), NULL, C.c_long(n), 1, out))
+        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(b), qmg.ptr(q), NULL, qmg.ptr(x2), qmg.ptr(b), qmg.ptr(r2), NULL, C.c_long(n), 1, out, NULL))
         assert np.array_equal(host(x2), wx) and np.array_equal(host(r2), wr) and tuple(out)[:4] == tuple(want4), n
         assert out[4] == qmg.norm2sq(b) and np.array_equal(host(b), r0), n
         # (c) x-only last step with lhs += z folded in: lhs + (x + alpha p)
@@ -399,8 +399,54 @@ def test_krylov_step_flavours(qmg_gpu):
         qmg.check(lib.qmg_caxpy(C.c_double(1.0), C.c_double(0.0), qmg.ptr(x), qmg.ptr(lhs), C.c_long(n)))
         wl = host(lhs)
         q, x, r, lhs = dev(qmg, q0), dev(qmg, x0), dev(qmg, r0), dev(qmg, a0)
-        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(lhs), qmg.ptr(r), qmg.ptr(r), qmg.ptr(lhs), C.c_long(n), 2, out))
+        qmg.check(lib.qmg_krylov_step(C.c_double(omega), qmg.ptr(r), qmg.ptr(q), qmg.ptr(x), qmg.ptr(lhs), qmg.ptr(r), qmg.ptr(r), qmg.ptr(lhs), C.c_long(n), 2, out, NULL))
         assert np.array_equal(host(lhs), wl) and np.array_equal(host(r), r0), n
+
+
+@pytest.mark.parametrize("k", [1, 3, 8, 11])
+def test_gcr_orthogonalize_on_device(qmg_gpu, k):
+    """qmg_gcr_orthogonalize + qmg_krylov_step(DOTS_READY) == qmg_multi_dot + host division + 2 x qmg_multi_axpyz +
+    qmg_krylov_step, bit for bit (coefficients formed on the device, both basis updates and the step's dot products in one
+    pass; k = 11 takes two passes of the stored set)."""
+    import ctypes as C
+    import torch
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    NULL = C.c_void_p(0)
+    n = 70001
+    Ap0 = [latutil.gaussian_cv(n, 100 + j) for j in range(k)]
+    p0 = [latutil.gaussian_cv(n, 200 + j) for j in range(k)]
+    apk0, dir0, r0, x0 = (latutil.gaussian_cv(n, sd) for sd in (1, 2, 3, 4))
+    apn = np.array([np.vdot(a, a).real for a in Ap0])
+
+    def fresh():
+        return [dev(qmg, a) for a in Ap0], [dev(qmg, a) for a in p0], dev(qmg, apk0), dev(qmg, dir0), qmg.cvec(n), dev(qmg, r0), dev(qmg, x0)
+    # reference sequence (what gcr_core did before)
+    Ap, P, apk, dirv, pk, r, x = fresh()
+    arrA, arrP = (C.c_void_p * k)(*[t.data_ptr() for t in Ap]), (C.c_void_p * k)(*[t.data_ptr() for t in P])
+    dots = (C.c_double * (2 * k))()
+    qmg.check(lib.qmg_multi_dot(arrA, k, qmg.ptr(apk), C.c_long(n), dots))
+    beta = (C.c_double * (2 * k))(*[-dots[i] / apn[i // 2] for i in range(2 * k)])
+    qmg.check(lib.qmg_multi_axpyz(beta, arrA, k, qmg.ptr(apk), qmg.ptr(apk), C.c_long(n)))
+    qmg.check(lib.qmg_multi_axpyz(beta, arrP, k, qmg.ptr(dirv), qmg.ptr(pk), C.c_long(n)))
+    want5 = (C.c_double * 5)()
+    qmg.check(lib.qmg_krylov_step(C.c_double(1.0), qmg.ptr(pk), qmg.ptr(apk), qmg.ptr(x), qmg.ptr(x), qmg.ptr(r), qmg.ptr(r), NULL, C.c_long(n), 0, want5, NULL))
+    want = [host(t) for t in (apk, pk, x, r)]
+    # device-side orthogonalisation
+    Ap, P, apk, dirv, pk, r, x = fresh()
+    arrA, arrP = (C.c_void_p * k)(*[t.data_ptr() for t in Ap]), (C.c_void_p * k)(*[t.data_ptr() for t in P])
+    d_dots = torch.zeros(2 * k, dtype=torch.float64, device="cuda")
+    d_apn = torch.tensor(np.concatenate([apn, [0.0]]), dtype=torch.float64, device="cuda")
+    qmg.check(lib.qmg_gcr_orthogonalize(arrA, arrP, k, qmg.ptr(apk), qmg.ptr(dirv), qmg.ptr(pk), qmg.ptr(r), C.c_long(n), qmg.ptr(d_dots), qmg.ptr(d_apn)))
+    got5 = (C.c_double * 5)()
+    qq = C.c_void_p(d_apn.data_ptr() + 8 * k)
+    qmg.check(lib.qmg_krylov_step(C.c_double(1.0), qmg.ptr(pk), qmg.ptr(apk), qmg.ptr(x), qmg.ptr(x), qmg.ptr(r), qmg.ptr(r), NULL, C.c_long(n), 4, got5, qq))
+    got = [host(t) for t in (apk, pk, x, r)]
+    for u, v in zip(got, want):
+        assert np.array_equal(u, v)
+    assert tuple(got5)[:4] == tuple(want5)[:4]
+    assert np.array_equal(d_dots.cpu().numpy(), np.array(list(dots)))
+    assert float(d_apn[k].item()) == want5[3]
 
 
 @pytest.mark.parametrize("nc,herm", [(2, False), (8, False), (8, True), (1, False), (6, False)])
