@@ -145,10 +145,13 @@ int qmg_stencil_apply_host(const qmg_stencil_desc* st, int pieces, int dir_mask,
  * QMG_APPLY_ACCUMULATE is not allowed.  Bit-identical to qmg_stencil_apply followed by qmg_caxpbyz(1, b, -1, A rhs, lhs). */
 int qmg_stencil_apply_residual(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_cplx* lhs, const qmg_cplx* rhs, const qmg_cplx* b);
 
-/* Which kernel serves gamma5-hermitian (link-compressed) applies at nc = 8 / 4 (also the environment variable QMG_TILE at
- * qmg_init): 0 streaming kernel reading the neighbours' forward blocks through L2; 1 (default) shared-memory patch kernel
- * staged with cp.async, two threads per (site, column); 2 the same with one thread per column; 4 the patch staged by the
- * TMA engine (cp.async.bulk + mbarrier).  All four produce the same result up to the order of the sums. */
+/* Which kernel serves gamma5-hermitian (link-compressed) applies at nc = 8 (also the environment variable QMG_TILE at
+ * qmg_init): 0 streaming kernel reading the neighbours' forward blocks through L2; 1 (default) the persistent ring kernel
+ * (one CTA per SM, a producer warp filling a two-stage ring of 32-site patches with cp.async.bulk copies on mbarriers, 512
+ * consumer threads) on lattices that give every SM at least 8 patches, the one-patch cp.async kernel on smaller ones;
+ * 3 always the one-patch cp.async kernel (two threads per (site, column)); 2 the same with one thread per column; 4 the
+ * one-patch kernel staged by cp.async.bulk; 5-11 experimental patch / ring shapes (csrc/qmg_stencil.cu launch_tile8).
+ * All produce the same result up to the order of the sums. */
 int qmg_set_tile_kernel(int mode);
 int qmg_get_tile_kernel(void);
 

@@ -84,7 +84,8 @@ int peer_timeout_error()
 {
   const unsigned long long e = *rt().h_err;
   char buf[160];
-  if (e > 256) snprintf(buf, sizeof(buf), "rank %d gave up waiting for a halo row from its %s neighbour (peer lost?)", qmg_comm_rank(), (e - 257) ? "upper" : "lower");
+  if (e == 1000) snprintf(buf, sizeof(buf), "a pipeline barrier of the ring stencil kernel did not complete (bulk copy lost?)");
+  else if (e > 256) snprintf(buf, sizeof(buf), "rank %d gave up waiting for a halo row from its %s neighbour (peer lost?)", qmg_comm_rank(), (e - 257) ? "upper" : "lower");
   else snprintf(buf, sizeof(buf), "rank %d gave up waiting for rank %d in an all-reduce (peer lost?)", qmg_comm_rank(), (int)(e - 1));
   return fail_msg(buf);
 }
@@ -221,7 +222,7 @@ int qmg_init(int device)
   const char* env = getenv("QMG_MANAGED");
   if (env != nullptr && env[0] == '1') r.managed = 1;
   env = getenv("QMG_TILE");
-  r.tile_kernel = (env != nullptr && env[0] >= '0' && env[0] <= '9') ? (env[0] - '0') : 1;
+  r.tile_kernel = (env != nullptr && env[0] >= '0' && env[0] <= '9') ? atoi(env) : 1;
   env = getenv("QMG_PROFILE");
   if (env != nullptr && env[0] == '1') r.profile = 1;
   r.ready = true;
@@ -321,7 +322,7 @@ int qmg_zero_bytes(void* dptr, size_t bytes)
   QMG_CUDA(cudaMemsetAsync(dptr, 0, bytes, rt().stream));
   return 0;
 }
-int qmg_set_tile_kernel(int mode) { QMG_REQUIRE_INIT(); if (mode < 0 || mode > 6) return fail_msg("qmg_set_tile_kernel: mode must be 0 .. 6"); rt().tile_kernel = mode; return 0; }
+int qmg_set_tile_kernel(int mode) { QMG_REQUIRE_INIT(); if (mode < 0 || mode > 15) return fail_msg("qmg_set_tile_kernel: mode must be 0 .. 15"); rt().tile_kernel = mode; return 0; }
 int qmg_get_tile_kernel(void) { return rt().tile_kernel; }
 int qmg_profile_enable(int on) { rt().profile = on ? 1 : 0; return 0; }
 int qmg_profile_reset(void) { prof_table().clear(); return 0; }

@@ -18,6 +18,7 @@
 // HBM-bound: 16*(nc^2*(n_clover+4) + 2nc) algorithmic bytes per site
 // (Wilson 384 B, coarse nc=8 5376 B) for 8*nc^2*(n_clover+4) flops.
 #include "qmg_comm.cuh"
+#include <stdlib.h>
 
 namespace qmg {
 
@@ -670,18 +671,138 @@ template <int NC, int TK, int TY, int SPLIT = 1> static int launch_tma(const Ste
   return 0;
 }
 
-// nc = 8 patches.  Default: the cp.async-staged kernel.  QMG_TILE=4 selects the TMA-staged one: a third fewer instructions
-// (issue utilisation 64 % -> 35 %) and the same time inside a power-capped solve (8192^2 K-cycle 6.12 s vs 6.08 s), but
-// 7 % slower as a back-to-back burst (2.63 vs 2.44 ms on 2048^2): both flavours wait on their tile with two CTAs per SM
-// (registers and shared memory both stop at two), and that wait, not the staging instructions, is what bounds them
-// (profiles/r03d_ncu_tile_tma_vs_cp_async.txt).  QMG_TILE=2: cp.async with one thread per column.
+// ---- persistent, warp-specialised flavour: one CTA per SM, a ring of NSTAGE patch buffers filled by a producer warp --------
+// Both one-patch-per-CTA kernels above wait for their tile with two CTAs per SM (registers and shared memory both stop at
+// two), and that wait is what bounds them.  Here ONE resident CTA walks over patches b, b + gridDim, ...: a producer warp
+// issues the bulk copies of patch j + NSTAGE - ... into the ring as soon as the buffer's previous tenant has been consumed
+// (empty barrier), NGROUP consumer groups of 16 x 16 threads each take every NGROUP-th patch as its full barrier completes,
+// and each consumer fetches its clover column for its NEXT patch into registers while it computes the current one.  Patches
+// are 4 rows x 4 sites (TK = 2): 46 KB per stage without the clover, so four stages fit.
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
+// bounded wait: false (and *err set) if the phase did not complete within ~2 s -- a broken pipeline must not hang the GPU
+__device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsigned parity, unsigned long long* err)
+{
+  const unsigned addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;)
+  {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return true;
+    if (clock64() - t0 > 4000000000LL) { st_sys_u64(err, 1000ull); return false; }      // reported by the next fetch / qmg_sync
+  }
+}
+
+template <int NC, int TK, int TY, int SPLIT, int NSTAGE, int NGROUP> struct RingCfg
+{
+  typedef TmaTile<NC, TK, TY, SPLIT> T;
+  static const int GT = TileDims<NC, TK, TY, SPLIT>::THREADS;      // threads of one consumer group = one patch
+  static const int NTHREADS = NGROUP * GT + 32;
+  static const size_t STAGE_BYTES = (T::BYTES + 127) & ~(size_t)127;
+  static const size_t SMEM = 256 + NSTAGE * STAGE_BYTES;
+};
+
+template <int NC, int TK, int TY, int SPLIT, int NSTAGE, int NGROUP>
+__global__ void __launch_bounds__(RingCfg<NC, TK, TY, SPLIT, NSTAGE, NGROUP>::NTHREADS, 1)
+stencil_ring_kernel(const StencilKArgs a, const int npatch, const int nbx, unsigned long long* err, const int dbg)
+{
+  typedef RingCfg<NC, TK, TY, SPLIT, NSTAGE, NGROUP> CFG;
+  typedef TmaTile<NC, TK, TY, SPLIT> T;
+  typedef Tile<NC, TK, TY, SPLIT> T0;
+  static_assert(TileDims<NC, TK, TY, SPLIT>::PASSES == 1, "ring kernel: one patch per consumer group");
+  extern __shared__ __align__(128) unsigned char ring_smem[];
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring_smem);
+  unsigned long long* empty = full + NSTAGE;
+  const int tid = threadIdx.x;
+  if (tid == 0)
+  {
+    for (int s = 0; s < NSTAGE; s++) { mbar_init(full + s, 1); mbar_init(empty + s, CFG::GT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid >= NGROUP * CFG::GT)
+  {
+    // producer warp
+    const int lane = tid - NGROUP * CFG::GT;
+    int j = 0;
+    for (int t = blockIdx.x; t < npatch; t += gridDim.x, j++)
+    {
+      const int s = j % NSTAGE, round = j / NSTAGE;
+      if (!mbar_wait_bounded(empty + s, (unsigned)((round & 1) ^ 1), err)) return;
+      if (dbg == 2) { if (lane == 0) mbar_arrive(full + s); continue; }      // timing experiment: no copies, consumers compute on whatever is there
+      if (lane == 0) mbar_expect_tx(full + s, T::BYTES);
+      __syncwarp();
+      const int by = t / nbx, bx = t - by * nbx;
+      T::stage(a, reinterpret_cast<cd*>(ring_smem + 256 + (size_t)s * CFG::STAGE_BYTES), full + s, bx * TK, a.y_off + by * TY, lane);
+    }
+    return;
+  }
+  // consumer groups: group g takes patches j = g, g + NGROUP, ... of this CTA's list
+  const int g = tid / CFG::GT, gtid = tid - g * CFG::GT;
+  cd CLc[1][T::R], CLn[1][T::R];
+  cd RBc[1], RBn[1];
+  int j = g;
+  long t = (long)blockIdx.x + (long)j * gridDim.x;
+  if (t < npatch) { const int by = (int)(t / nbx), bx = (int)(t - (long)by * nbx); T0::clover(a, bx * TK, a.y_off + by * TY, gtid, CLc, RBc); }
+  for (; t < npatch; j += NGROUP, t += (long)NGROUP * gridDim.x)
+  {
+    const int s = j % NSTAGE, round = j / NSTAGE;
+    const int by = (int)(t / nbx), bx = (int)(t - (long)by * nbx);
+    const long tn = t + (long)NGROUP * gridDim.x;
+    if (tn < npatch) { const int byn = (int)(tn / nbx), bxn = (int)(tn - (long)byn * nbx); T0::clover(a, bxn * TK, a.y_off + byn * TY, gtid, CLn, RBn); }
+    if (!mbar_wait_bounded(full + s, (unsigned)(round & 1), err)) return;
+    if (dbg != 1)      // (timing experiment 1: copies only, nothing computed)
+      T::compute(a, reinterpret_cast<const cd*>(ring_smem + 256 + (size_t)s * CFG::STAGE_BYTES), bx * TK, a.y_off + by * TY, gtid, CLc, RBc);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(empty + s);
+#pragma unroll
+    for (int i = 0; i < T::R; i++) CLc[0][i] = CLn[0][i];
+    RBc[0] = RBn[0];
+  }
+}
+
+static int ring_debug() { static int v = -1; if (v < 0) { const char* e = getenv("QMG_RING_DEBUG"); v = e ? atoi(e) : 0; } return v; }
+
+template <int NC, int TK, int TY, int SPLIT, int NSTAGE, int NGROUP> static int launch_ring(const StencilKArgs& a)
+{
+  typedef RingCfg<NC, TK, TY, SPLIT, NSTAGE, NGROUP> CFG;
+  static bool configured[64] = { false };
+  const int dev = rt().device & 63;
+  if (!configured[dev])
+  {
+    QMG_CUDA(cudaFuncSetAttribute(stencil_ring_kernel<NC, TK, TY, SPLIT, NSTAGE, NGROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::SMEM));
+    configured[dev] = true;
+  }
+  const int nbx = a.g.xh / TK, nby = a.y_cnt / TY;
+  const long npatch = (long)nbx * nby;
+  if (npatch > 0x7fffffffL) return fail_msg("qmg_stencil_apply: lattice too large for the ring kernel");
+  int grid = rt().sm_count;
+  if (grid > npatch) grid = (int)npatch;
+  stencil_ring_kernel<NC, TK, TY, SPLIT, NSTAGE, NGROUP><<<grid, CFG::NTHREADS, CFG::SMEM, rt().stream>>>(a, (int)npatch, nbx, rt().h_err, ring_debug());
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+
+// nc = 8 patches (QMG_TILE / qmg_set_tile_kernel).  1 (default): the persistent ring kernel -- 32-site patches, two stages, one
+// consumer group of 512 threads + a producer warp -- wherever every SM gets at least 8 patches, else the one-patch cp.async
+// kernel; 3: always the cp.async kernel; 2: cp.async with one thread per column; 4: one-patch TMA kernel; 5 / 6: 16-site
+// one-patch kernels; 7 / 8, 10 / 11: ring kernels over 16-site patches (producer-bound: 34 resp. 20 bulk copies per 16 sites).
+// Measured on 2048^2 (profiles/r03r_ring_kernel_variants.txt): cp.async 2.54 ms, ring 2.29 ms; loads alone 1.92 ms, consumers
+// alone 2.00 ms; inside the 8192^2 K-cycle 6.09 -> 5.74 s.
 static int launch_tile8(const StencilKArgs& a)
 {
-  if (rt().tile_kernel == 2) return launch_tile<8, 4, 4, 1>(a);
-  if (rt().tile_kernel == 4) return launch_tma<8, 4, 4, 2>(a);
-  // experiments: 16-site patches (4 rows x 4 sites), 256 threads, four CTAs per SM instead of two
-  if (rt().tile_kernel == 5) return launch_tile<8, 2, 4, 2>(a);
-  if (rt().tile_kernel == 6) return launch_tma<8, 2, 4, 2>(a);
+  const int mode = rt().tile_kernel;
+  if (mode == 2) return launch_tile<8, 4, 4, 1>(a);
+  if (mode == 4) return launch_tma<8, 4, 4, 2>(a);
+  if (mode == 5) return launch_tile<8, 2, 4, 2>(a);
+  if (mode == 6) return launch_tma<8, 2, 4, 2>(a);
+  if (mode == 7) return launch_ring<8, 2, 4, 2, 4, 2>(a);
+  if (mode == 8) return launch_ring<8, 2, 4, 2, 4, 3>(a);
+  if (mode == 10) return launch_ring<8, 4, 2, 2, 4, 2>(a);
+  if (mode == 11) return launch_ring<8, 4, 2, 2, 4, 3>(a);
+  const long npatch = (long)(a.g.xh / 4) * (a.y_cnt / 4);
+  if (mode == 9 || (mode == 1 && npatch >= 8L * rt().sm_count)) return launch_ring<8, 4, 4, 2, 2, 1>(a);
   return launch_tile<8, 4, 4, 2>(a);
 }
 

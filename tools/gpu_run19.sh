@@ -1,0 +1,6 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+for t in 10 11; do for d in 0 1 2; do echo "mode $t ring debug $d"; QMG_RING_DEBUG=$d QMG_TILE=$t TILE_PROBE_SMALL=1 timeout 120 python tools/tile_probe.py 2>&1 | grep "herm=1"; done; done > gpurun_out/r3r_ring.log 2>&1; cat gpurun_out/r3r_ring.log
+QMG_TILE=9 TILE_PROBE_SMALL=1 python tools/tile_probe.py 2>&1 | grep "herm=1"
+QMG_TILE=1 TILE_PROBE_SMALL=1 python tools/tile_probe.py 2>&1 | grep "herm=1"
