@@ -784,6 +784,12 @@ template <int NC, int TK, int TY, int SPLIT, int NSTAGE, int NGROUP> static int 
   return 0;
 }
 
+// (A split-phase ring -- the x half and the y half of every patch with their own full / empty barriers, so that the producer
+// runs up to three half-stages ahead in the same shared memory -- was built and measured too: 2.51 ms against 2.42 ms for the
+// ring above on the same box (profiles/r03r_ring_kernel_variants.txt).  Deeper prefetch does not help: with the loads hidden,
+// the 16 consumer warps are the limit -- consumers alone 2.00 ms, four warps per scheduler on dependent LDS -> DFMA chains --
+// and 1024 threads per CTA with 85 KB per 32-site stage leave no room for more of them.)
+
 // nc = 8 patches (QMG_TILE / qmg_set_tile_kernel).  1 (default): the persistent ring kernel -- 32-site patches, two stages, one
 // consumer group of 512 threads + a producer warp -- wherever every SM gets at least 8 patches, else the one-patch cp.async
 // kernel; 3: always the cp.async kernel; 2: cp.async with one thread per column; 4: one-patch TMA kernel; 5 / 6: 16-site

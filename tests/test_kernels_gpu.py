@@ -520,7 +520,7 @@ def test_tile_kernel_flavours_agree(qmg_gpu, L):
     qmg.check(lib.qmg_stencil_apply_residual(C.byref(stored), C.c_int(15), C.c_int(15), qmg.ptr(want_res), qmg.ptr(x), qmg.ptr(b)))
     old = lib.qmg_get_tile_kernel()
     try:
-        for mode in (0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11):
+        for mode in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11):
             qmg.check(lib.qmg_set_tile_kernel(mode))
             got = qmg.cvec(n)
             qmg.stencil_apply(herm, got, x)
