@@ -446,16 +446,29 @@ __global__ void __launch_bounds__(kEwBlock) gcr_ortho_kernel(long n, PtrPack<K> 
   }
   double acc[3] = {0.0, 0.0, 0.0};
   const long stride = (long)gridDim.x * blockDim.x;
+  // two sweeps, one per basis (each the loop of multi_axpy_pass, which runs at the copy peak; a single sweep over both
+  // bases keeps 2 K + 3 loads per element alive, which ptxas serialised: 3.8 TB/s)
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
   {
-    cd a[K], b[K];
+    cd a[K];
 #pragma unroll
-    for (int j = 0; j < K; j++) { a[j] = ld_stream(Ap.p[j] + i); b[j] = ld_stream(P.p[j] + i); }
-    cd t = apk[i], u = dir[i];
+    for (int j = 0; j < K; j++) a[j] = ld_stream(Ap.p[j] + i);
+    cd t = apk[i];
+    cd rr = DOTS ? __ldg(r + i) : cmake(0.0, 0.0);
 #pragma unroll
-    for (int j = 0; j < K; j++) { cfma(t, beta[j], a[j]); cfma(u, beta[j], b[j]); }
-    apk[i] = t; pk[i] = u;
-    if (DOTS) dot_acc3(acc, t, r[i]);
+    for (int j = 0; j < K; j++) cfma(t, beta[j], a[j]);
+    apk[i] = t;
+    if (DOTS) dot_acc3(acc, t, rr);
+  }
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    cd b[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) b[j] = ld_stream(P.p[j] + i);
+    cd u = dir[i];
+#pragma unroll
+    for (int j = 0; j < K; j++) cfma(u, beta[j], b[j]);
+    pk[i] = u;
   }
   if (DOTS) grid_reduce_finish<3>(acc, smem, partials, counter, result);
 }
@@ -467,8 +480,7 @@ static int gcr_ortho_pass(long n, const qmg_cplx* const* Ap, const qmg_cplx* con
   PtrPack<K> a, b;
   for (int j = 0; j < K; j++) { a.p[j] = CCD(Ap[j < k ? j : 0]); b.p[j] = CCD(P[j < k ? j : 0]); }
   Runtime& rtm = rt();
-  int grid = ew_grid(n);
-  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  const int grid = with_dots ? resident_grid(gcr_ortho_kernel<K, true>, n) : resident_grid(gcr_ortho_kernel<K, false>, n);
   if (with_dots)
   {
     gcr_ortho_kernel<K, true><<<grid, kEwBlock, 0, rtm.stream>>>(n, a, b, k, apk, dir, pk, r, dots, apn, rtm.d_partials, rtm.d_counter, result_dev);

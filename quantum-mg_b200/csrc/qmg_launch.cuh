@@ -51,11 +51,29 @@ template <class F> static inline int launch_ew(long n, F f)
   return 0;
 }
 
+// Grid of a reducing kernel: never more blocks than are resident at once.  The wide reductions (multi-dot: 16 accumulators,
+// 76 registers) fit 3 blocks per SM, not 8; 1184 blocks were then 2.67 waves with a third of the GPU idle during the last one.
+template <class K> static inline int resident_grid(K kernel, long n)
+{
+  static int per_sm[64] = { 0 };
+  const int dev = rt().device & 63;
+  if (per_sm[dev] == 0)
+  {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kEwBlock, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+    per_sm[dev] = nb;
+  }
+  int grid = ew_grid(n > 0 ? n : 1);
+  const long cap = (long)per_sm[dev] * rt().sm_count;
+  if (grid > cap) grid = (int)cap;
+  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  return grid;
+}
+
 template <int W, class F> static inline int launch_reduce(long n, F f, double* host_out)
 {
   Runtime& r = rt();
-  int grid = ew_grid(n > 0 ? n : 1);
-  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  const int grid = resident_grid(reduce_kernel<W, F>, n);
   reduce_kernel<W><<<grid, kEwBlock, 0, r.stream>>>(n, f, r.d_partials, r.d_counter, r.d_result);
   QMG_LAUNCH_CHECK();
   double sink[W];
@@ -95,8 +113,7 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t ctr_lo, u
 template <int W, class F> static inline int launch_reduce_keep(long n, F f, double* result_dev)
 {
   Runtime& r = rt();
-  int grid = ew_grid(n > 0 ? n : 1);
-  if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+  const int grid = resident_grid(reduce_kernel<W, F>, n);
   reduce_kernel<W><<<grid, kEwBlock, 0, r.stream>>>(n, f, r.d_partials, r.d_counter, result_dev);
   QMG_LAUNCH_CHECK();
   return skip_result(result_dev, W);

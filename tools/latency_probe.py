@@ -57,6 +57,15 @@ arrA, arrP = (C.c_void_p * k)(*[t.data_ptr() for t in Ap]), (C.c_void_p * k)(*[t
 dots = torch.zeros(2 * k, dtype=torch.float64, device="cuda")
 apn = torch.ones(k + 1, dtype=torch.float64, device="cuda")
 res["gcr_orthogonalize k=8 (no host wait)"] = wall(lambda: lib.qmg_gcr_orthogonalize(arrA, arrP, k, qmg.ptr(y), qmg.ptr(q), qmg.ptr(p), qmg.ptr(r), C.c_long(n), qmg.ptr(dots), qmg.ptr(apn)))
+for kk in (1, 2, 4, 8, 12, 16, 24):
+    ApK, PK = [rnd(n, 10 + j) for j in range(kk)], [rnd(n, 30 + j) for j in range(kk)]
+    aA, aP = (C.c_void_p * kk)(*[t.data_ptr() for t in ApK]), (C.c_void_p * kk)(*[t.data_ptr() for t in PK])
+    dk = torch.zeros(2 * kk, dtype=torch.float64, device="cuda")
+    ak = torch.ones(kk + 1, dtype=torch.float64, device="cuda")
+    us = wall(lambda: lib.qmg_gcr_orthogonalize(aA, aP, kk, qmg.ptr(y), qmg.ptr(q), qmg.ptr(p), qmg.ptr(r), C.c_long(n), qmg.ptr(dk), qmg.ptr(ak)), reps=100)
+    gb = 16.0 * n * ((kk + 1) + (2 * kk + 3) + 2) / 1e9
+    res["gcr_orthogonalize k=%d: %.0f MB -> %.0f GB/s" % (kk, gb * 1e3, gb / (us * 1e-6))] = us
+    del ApK, PK
 res["caxpy (1 kernel, no wait)"] = wall(lambda: lib.qmg_caxpy(C.c_double(0.0), C.c_double(0.0), qmg.ptr(x), qmg.ptr(y), C.c_long(n)))
 cl, hp = rnd(V * nc * nc, 50), rnd(4 * V * nc * nc, 51)
 d = qmg.stencil_desc(X, Y, nc, cl, hp, shift=0.1)
