@@ -153,7 +153,7 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
             # B200 extension: every level whose stored blocks pass the gamma5-hermiticity check applies its
             # operator from clover / +x / +y blocks only (coarse levels: shared-memory tile kernel).  Same iteration counts.
             stored = out
-            n_sw = kc.gamma5_hermitian(True)
+            n_sw = kc.gamma5_hermitian(True, tile_levels_only=True)      # the nc = 8 levels; the fine level keeps its stored blocks
             out = kc.solve(tol=tol, restart=restart, max_iter=100)
             if os.environ.get("QMG_BENCH_PROFILE") == "1":
                 # one more solve with the per-entry-point profile on (every call bracketed by stream synchronisations: the

@@ -18,12 +18,13 @@ inline void cMATconjtrans_square(qmg_cd* M, long nsites, int nc)
 { QMG_CHK(qmg_cmat_conjtrans(qmg_host::P(M), qmg_host::P(M), nsites, nc)); }
 inline void cMATxtMATyMATz_square(const qmg_cd* X, const qmg_cd* Y, qmg_cd* Z, long nsites, int nc)
 { QMG_CHK(qmg_cmat_mul(qmg_host::P(X), qmg_host::P(Y), qmg_host::P(Z), nsites, nc)); }
-// The reference inverts through a batched QR pair (stencil_2d.h:1536-1537).  Here the first call
-// only records the input; the second produces the inverse with the warp-per-matrix Gauss-Jordan kernel.
+// The reference inverts through a batched QR pair (stencil_2d.h:1536-1537): M = Q R (Q unitary, R upper triangular, as
+// anyone who reads them expects), then Minv = R^-1 Q^dag.  (Stencil2D::build_rbjacobi_stencil itself goes through
+// qmg_build_rbjacobi, whose inverse is the pivoted Gauss-Jordan kernel.)
 inline void cMATx_do_qr_square(const qmg_cd* M, qmg_cd* Q, qmg_cd* R, long nsites, int nc)
-{ copy_vector(Q, M, nsites * nc * nc); (void)R; }
+{ QMG_CHK(qmg_cmat_qr(qmg_host::P(M), qmg_host::P(Q), qmg_host::P(R), nsites, nc)); }
 inline void cMATqr_do_xinv_square(const qmg_cd* Q, const qmg_cd* R, qmg_cd* Minv, long nsites, int nc)
-{ (void)R; QMG_CHK(qmg_cmat_inverse(qmg_host::P(Q), qmg_host::P(Minv), nsites, nc)); }
+{ QMG_CHK(qmg_cmat_qr_inverse(qmg_host::P(Q), qmg_host::P(R), qmg_host::P(Minv), nsites, nc)); }
 inline void cMATinverse_square(const qmg_cd* M, qmg_cd* Minv, long nsites, int nc)
 { QMG_CHK(qmg_cmat_inverse(qmg_host::P(M), qmg_host::P(Minv), nsites, nc)); }
 

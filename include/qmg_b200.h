@@ -185,6 +185,8 @@ int qmg_cmat_single_xy(const qmg_cplx* M, const qmg_cplx* x, qmg_cplx* y, long n
 int qmg_cmat_conjtrans(const qmg_cplx* in, qmg_cplx* out, long nsites, int nc);                           /* qlinalg cMATcopy_conjtrans_square (stencil_2d.h:1097); in == out allowed */
 int qmg_cmat_mul(const qmg_cplx* Xm, const qmg_cplx* Ym, qmg_cplx* Zm, long nsites, int nc);                /* qlinalg cMATxtMATyMATz_square (stencil_2d.h:1564) */
 int qmg_cmat_inverse(const qmg_cplx* M, qmg_cplx* Minv, long nsites, int nc);                             /* qlinalg cMATx_do_qr_square + cMATqr_do_xinv_square (stencil_2d.h:1536-1537) */
+int qmg_cmat_qr(const qmg_cplx* M, qmg_cplx* Q, qmg_cplx* R, long nsites, int nc);                      /* qlinalg cMATx_do_qr_square (stencil_2d.h:1536): M = Q R per site, modified Gram-Schmidt */
+int qmg_cmat_qr_inverse(const qmg_cplx* Q, const qmg_cplx* R, qmg_cplx* Minv, long nsites, int nc);     /* qlinalg cMATqr_do_xinv_square (stencil_2d.h:1537): Minv = R^-1 Q^dag */
 int qmg_cmat_add_pattern(const double* pattern_host, int len, qmg_cplx* v, long nrepeat);                  /* qlinalg capx_pattern (stencil_2d.h:1526); pattern: len complex on HOST */
 
 /* ------------------------------------------------------------- BLAS-1 ---- */

@@ -443,6 +443,72 @@ __global__ void __launch_bounds__(32) cmat_inverse_kernel(const cd* M, cd* Minv,
   }
 }
 
+// One warp factorises one nc x nc matrix, M = Q R, by modified Gram-Schmidt over the columns (Q unitary, R upper
+// triangular with a real positive diagonal) -- the factorisation quantum-linalg's cMATx_do_qr_square hands to
+// cMATqr_do_xinv_square (stencil/stencil_2d.h:1536-1537).  Q and R live in shared memory while the warp works.
+__global__ void __launch_bounds__(32) cmat_qr_kernel(const cd* M, cd* Q, cd* R, long nsites, int nc)
+{
+  extern __shared__ cd qr_smem[];        // q: nc x nc, r: nc x nc
+  cd* q = qr_smem; cd* r = qr_smem + nc * nc;
+  const int lane = threadIdx.x;
+  for (long s = blockIdx.x; s < nsites; s += gridDim.x)
+  {
+    const cd* m = M + s * (long)nc * nc;
+    for (int e = lane; e < nc * nc; e += 32) { q[e] = m[e]; r[e] = cmake(0.0, 0.0); }
+    __syncwarp();
+    for (int j = 0; j < nc; j++)
+    {
+      for (int i = 0; i < j; i++)
+      {
+        cd d = cmake(0.0, 0.0);
+        for (int k = lane; k < nc; k += 32) cfma_conj(d, q[k * nc + i], q[k * nc + j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d = cadd(d, shfl_xor_c(d, o));
+        if (lane == 0) r[i * nc + j] = d;
+        const cd md = cmake(-d.x, -d.y);
+        for (int k = lane; k < nc; k += 32) { cd t = q[k * nc + j]; cfma(t, md, q[k * nc + i]); q[k * nc + j] = t; }
+        __syncwarp();
+      }
+      double nrm = 0.0;
+      for (int k = lane; k < nc; k += 32) { const cd v = q[k * nc + j]; nrm += v.x * v.x + v.y * v.y; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nrm += shfl_xor_d(nrm, o);
+      nrm = sqrt(nrm);
+      if (lane == 0) r[j * nc + j] = cmake(nrm, 0.0);
+      for (int k = lane; k < nc; k += 32) { const cd v = q[k * nc + j]; q[k * nc + j] = cmake(v.x / nrm, v.y / nrm); }
+      __syncwarp();
+    }
+    cd* qo = Q + s * (long)nc * nc; cd* ro = R + s * (long)nc * nc;
+    for (int e = lane; e < nc * nc; e += 32) { qo[e] = q[e]; ro[e] = r[e]; }
+    __syncwarp();
+  }
+}
+
+// Minv = R^-1 Q^dag: lane c owns column c of the result and back-substitutes R x = (Q^dag)[:, c]
+__global__ void __launch_bounds__(32) cmat_qr_inverse_kernel(const cd* Q, const cd* R, cd* Minv, long nsites, int nc)
+{
+  extern __shared__ cd qr_smem[];
+  cd* q = qr_smem; cd* r = qr_smem + nc * nc; cd* x = r + nc * nc;      // x: nc x nc result
+  const int lane = threadIdx.x;
+  for (long s = blockIdx.x; s < nsites; s += gridDim.x)
+  {
+    const cd* qi = Q + s * (long)nc * nc; const cd* ri = R + s * (long)nc * nc;
+    for (int e = lane; e < nc * nc; e += 32) { q[e] = qi[e]; r[e] = ri[e]; }
+    __syncwarp();
+    for (int c = lane; c < nc; c += 32)
+      for (int i = nc - 1; i >= 0; i--)
+      {
+        cd t = cconj(q[c * nc + i]);                      // (Q^dag)[i][c]
+        for (int k = i + 1; k < nc; k++) cfma(t, cmake(-r[i * nc + k].x, -r[i * nc + k].y), x[k * nc + c]);
+        x[i * nc + c] = cdiv(t, r[i * nc + i]);
+      }
+    __syncwarp();
+    cd* out = Minv + s * (long)nc * nc;
+    for (int e = lane; e < nc * nc; e += 32) out[e] = x[e];
+    __syncwarp();
+  }
+}
+
 } // namespace qmg
 
 extern "C" {
@@ -456,6 +522,33 @@ int qmg_cmat_inverse(const qmg_cplx* M_, qmg_cplx* Minv_, long nsites, int nc)
   if (smem > 48 * 1024) QMG_CUDA(cudaFuncSetAttribute(cmat_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long cap = (long)rt().sm_count * 32;
   cmat_inverse_kernel<<<(int)(nsites < cap ? nsites : cap), 32, smem, rt().stream>>>(CCD(M_), CD(Minv_), nsites, nc);
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+
+// M = Q R per site (modified Gram-Schmidt) and Minv = R^-1 Q^dag: the pair quantum-linalg's cMATx_do_qr_square /
+// cMATqr_do_xinv_square name (stencil/stencil_2d.h:1536-1537), for callers that read Q or R
+int qmg_cmat_qr(const qmg_cplx* M_, qmg_cplx* Q_, qmg_cplx* R_, long nsites, int nc)
+{
+  QMG_REQUIRE_INIT();
+  if (nsites <= 0) return 0;
+  if (nc > 48) return fail_msg("qmg_cmat_qr: nc > 48 unsupported");
+  const size_t smem = sizeof(cd) * (size_t)nc * nc * 2;
+  if (smem > 48 * 1024) QMG_CUDA(cudaFuncSetAttribute(cmat_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long cap = (long)rt().sm_count * 32;
+  cmat_qr_kernel<<<(int)(nsites < cap ? nsites : cap), 32, smem, rt().stream>>>(CCD(M_), CD(Q_), CD(R_), nsites, nc);
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+int qmg_cmat_qr_inverse(const qmg_cplx* Q_, const qmg_cplx* R_, qmg_cplx* Minv_, long nsites, int nc)
+{
+  QMG_REQUIRE_INIT();
+  if (nsites <= 0) return 0;
+  if (nc > 48) return fail_msg("qmg_cmat_qr_inverse: nc > 48 unsupported");
+  const size_t smem = sizeof(cd) * (size_t)nc * nc * 3;
+  if (smem > 48 * 1024) QMG_CUDA(cudaFuncSetAttribute(cmat_qr_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long cap = (long)rt().sm_count * 32;
+  cmat_qr_inverse_kernel<<<(int)(nsites < cap ? nsites : cap), 32, smem, rt().stream>>>(CCD(Q_), CCD(R_), CD(Minv_), nsites, nc);
   QMG_LAUNCH_CHECK();
   return 0;
 }

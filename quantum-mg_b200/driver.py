@@ -452,9 +452,10 @@ class KCycle:
         self.be.fn("kcycle_pion")(self.h, x0, y0, max_iter, C.c_double(tol), restart, verbosity, _c(out), info)
         return out, dict(iters=int(info[0]), success=bool(info[1]), seconds=info[2])
 
-    def gamma5_hermitian(self, on=True):
-        """B200 extension: link-compressed applies on every level that passes the check; returns how many levels switched."""
-        return int(self.be.fn("kcycle_gamma5_hermitian")(self.h, 1 if on else 0))
+    def gamma5_hermitian(self, on=True, tile_levels_only=False):
+        """B200 extension: link-compressed applies on every level that passes the check (tile_levels_only: only on the levels
+        with nc >= 4, where the shared-memory patch kernels make it faster); returns how many levels switched."""
+        return int(self.be.fn("kcycle_gamma5_hermitian")(self.h, (2 if tile_levels_only else 1) if on else 0))
 
     def deflate_coarsest(self, num_low, num_high=0):
         """B200 build only: eigenpairs of the coarsest normal operator for the deflated coarsest solve; returns their eigenvalues."""

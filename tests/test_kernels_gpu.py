@@ -539,6 +539,33 @@ def test_tile_kernel_flavours_agree(qmg_gpu, L):
         qmg.check(lib.qmg_set_tile_kernel(old))
 
 
+@pytest.mark.parametrize("nc", [1, 2, 8, 12])
+def test_batched_qr_pair(qmg_gpu, nc):
+    """quantum-linalg's cMATx_do_qr_square / cMATqr_do_xinv_square pair (stencil/stencil_2d.h:1536-1537): M = Q R with Q unitary
+    and R upper triangular with a positive real diagonal (the unique factorisation, so numpy's is the reference), and
+    Minv = R^-1 Q^dag."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    ns = 257
+    rng = np.random.default_rng(nc)
+    M = rng.normal(size=(ns, nc, nc)) + 1j * rng.normal(size=(ns, nc, nc)) + 2.0 * nc * np.eye(nc)[None]
+    dM = dev(qmg, M.reshape(-1))
+    dQ, dR, dI = qmg.cvec(ns * nc * nc), qmg.cvec(ns * nc * nc), qmg.cvec(ns * nc * nc)
+    qmg.check(lib.qmg_cmat_qr(qmg.ptr(dM), qmg.ptr(dQ), qmg.ptr(dR), C.c_long(ns), C.c_int(nc)))
+    qmg.check(lib.qmg_cmat_qr_inverse(qmg.ptr(dQ), qmg.ptr(dR), qmg.ptr(dI), C.c_long(ns), C.c_int(nc)))
+    Q, R, Minv = (host(t).reshape(ns, nc, nc) for t in (dQ, dR, dI))
+    eye = np.eye(nc)[None]
+    assert np.abs(np.conj(np.swapaxes(Q, 1, 2)) @ Q - eye).max() < 1e-13
+    assert np.abs(np.tril(R, -1)).max() == 0.0 and (np.abs(np.imag(np.diagonal(R, axis1=1, axis2=2))).max() == 0.0) and (np.real(np.diagonal(R, axis1=1, axis2=2)) > 0).all()
+    assert np.abs(Q @ R - M).max() < 1e-12 * np.abs(M).max()
+    assert np.abs(Minv @ M - eye).max() < 1e-12
+    Qn, Rn = np.linalg.qr(M)
+    ph = np.sign(np.real(np.diagonal(Rn, axis1=1, axis2=2))) if nc == 0 else (np.diagonal(Rn, axis1=1, axis2=2) / np.abs(np.diagonal(Rn, axis1=1, axis2=2)))
+    assert np.abs(Qn * ph[:, None, :] - Q).max() < 1e-12
+    assert np.abs(np.conj(ph)[:, :, None] * Rn - R).max() < 1e-12 * np.abs(M).max()
+
+
 def test_in_place_hopping_is_sequential(ref, qmg_gpu):
     """apply_M_hopping(x, x): the reference runs apply_M_eo, then apply_M_oe on the UPDATED even rows
     (stencil/stencil_2d.h:843-850); the in-place both-parity request is two ordered launches with that meaning."""

@@ -44,7 +44,7 @@ for L in args.sizes:
     t2 = time.perf_counter()
     if args.backend == "gpu":
         if args.hermitian:
-            print("link-compressed levels:", kc.gamma5_hermitian(True), flush=True)
+            print("link-compressed levels:", kc.gamma5_hermitian(True, tile_levels_only=True), flush=True)
         if args.unfused:
             kc.set_fused(False)
     out = kc.solve(max_iter=args.max_iter, verbosity=args.verbosity, restart=args.restart)
