@@ -812,6 +812,14 @@ static int launch_tile8(const StencilKArgs& a)
   return launch_tile<8, 4, 4, 2>(a);
 }
 
+// (nc = 2, the Wilson fine level: a link-compressed patch kernel in the same style -- 4 rows x 32 sites per CTA, one lane per
+// matrix element, forward and transposed backward elements out of shared memory, clover element straight from global memory,
+// 256 instead of 384 bytes per site -- was built, passed the parity tests and was removed again: 5.39 ms on 8192^2 against
+// 3.60 ms for the stored-block apply and 4.16 ms for the streaming link-compressed one.  A 64-byte block is four lanes' worth of
+// data; per lane the staging and index arithmetic cost more instructions than the 128 bytes saved are worth, and the
+// stored-block kernel already runs at 54 % issue utilisation.  At nc = 2 the stored blocks are the fast path; the K-cycle legs
+// of bench.py switch only the nc = 8 levels to link-compressed applies.)
+
 // Any nc (DWF Ls = 6, 12, 24, 32 give nc = 12, 24, 48, 64): one thread per
 // (site, row), looping over the columns.  Slow path, same arithmetic.
 __global__ void __launch_bounds__(256) stencil_kernel_generic(const StencilKArgs a, int nc, int n_par)

@@ -566,6 +566,49 @@ def test_batched_qr_pair(qmg_gpu, nc):
     assert np.abs(np.conj(ph)[:, :, None] * Rn - R).max() < 1e-12 * np.abs(M).max()
 
 
+@pytest.mark.parametrize("L", [32, 64])
+def test_fine_level_link_compressed_apply(ref, qmg_gpu, L):
+    """nc = 2 (Wilson fine level): the link-compressed apply (clover, +x, +y blocks only; backward hops from the neighbours'
+    forward blocks) against the stored-block apply and the oracle, on the reference's own configs -- plain, accumulating, with
+    the residual epilogue and with shifts."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    g = latutil.load_gauge(L)
+    cl, hp = qmg.fill_wilson(L, L, dev(qmg, g))
+    n = L * L * 2
+    stored = qmg.stencil_desc(L, L, 2, cl, hp, shift=-0.055, dof_shift=0.01)
+    herm = qmg.stencil_desc(L, L, 2, cl, hp, shift=-0.055, dof_shift=0.01, gamma5_hermitian=True)
+    assert qmg.stencil_gamma5_deviation(stored) < 1e-14
+    x0, b0, a0 = (latutil.gaussian_cv(n, sd) for sd in (1, 2, 3))
+    x, b = dev(qmg, x0), dev(qmg, b0)
+    op = ref.lattice(L, L, 2).wilson(-0.055, g)
+    want_ref = op.apply(x0, 0)
+    op.free()
+    want = qmg.cvec(n)
+    qmg.stencil_apply(stored, want, x)
+    old = lib.qmg_get_tile_kernel()
+    try:
+        for mode in (1, 0):
+            qmg.check(lib.qmg_set_tile_kernel(mode))
+            got = qmg.cvec(n)
+            qmg.stencil_apply(herm, got, x)
+            assert latutil.rel_l2(host(got), host(want)) < 1e-14, mode
+            acc = dev(qmg, a0)
+            qmg.stencil_apply(herm, acc, x, qmg.APPLY_ALL | qmg.APPLY_ACCUMULATE)
+            assert latutil.rel_l2(host(acc), host(want) + a0) < 1e-14, mode
+            res = qmg.cvec(n)
+            qmg.check(lib.qmg_stencil_apply_residual(C.byref(herm), C.c_int(15), C.c_int(15), qmg.ptr(res), qmg.ptr(x), qmg.ptr(b)))
+            assert latutil.rel_l2(host(res), b0 - host(want)) < 1e-14, mode
+    finally:
+        qmg.check(lib.qmg_set_tile_kernel(old))
+    # against the oracle: the descriptor's dof_shift is not part of Wilson2D, so compare without it
+    herm0 = qmg.stencil_desc(L, L, 2, cl, hp, shift=-0.055, gamma5_hermitian=True)
+    got = qmg.cvec(n)
+    qmg.stencil_apply(herm0, got, x)
+    assert latutil.rel_l2(host(got), want_ref) < TOL
+
+
 def test_in_place_hopping_is_sequential(ref, qmg_gpu):
     """apply_M_hopping(x, x): the reference runs apply_M_eo, then apply_M_oe on the UPDATED even rows
     (stencil/stencil_2d.h:843-850); the in-place both-parity request is two ordered launches with that meaning."""
