@@ -3,8 +3,8 @@
 // Iteration as stated by the oracle (oracle/qlinalg_shim/inverters/generic_gcr.h; quantum-linalg itself is
 // un-vendored): untruncated GCR, classical Gram-Schmidt of A r against every stored A p_i.
 // Device formulation (qmg_gcr_orthogonalize + qmg_krylov_step): the k projections are ONE multi-dot pass over the stored
-// A p_i whose results stay on the device, the coefficients are formed there, both basis updates are ONE pass that also
-// forms <Ap_k|r> and |Ap_k|^2, and (alpha, x, r, |r|^2) is one fused update -- one host wait per iteration.
+// A p_i whose results stay on the device, the coefficients are formed there, the A p basis update also forms <Ap_k|r> and
+// |Ap_k|^2, and (alpha, r, |r|^2) is one fused update -- one host wait per iteration; x is formed once per solve.
 #ifndef QMG_B200_GCR
 #define QMG_B200_GCR
 
@@ -19,12 +19,21 @@ namespace qmg_host {
 inline precond_op_cplx& overwriting_precond() { static precond_op_cplx f = 0; return f; }
 
 // Shared body of GCR and flexible (variably preconditioned) GCR.  `hints` (inverter_struct.h) as in minres_core: from a
-// zero start r0 = b without applying A to zero, x is written by the first step instead of being zeroed and read, |b|^2
-// can come from the caller, and a solve that ends converged skips the true-residual apply nobody reads.
+// zero start r0 = b without applying A to zero, |b|^2 can come from the caller, and a solve that ends converged skips the
+// true-residual apply nobody reads.
+//
+// Storage is GMRES-style: the raw directions d_k (the residuals themselves, or the preconditioner's outputs) are kept, not
+// their orthogonalised combinations p_k = d_k + sum_i beta_ki p_i.  Per iteration only the A p basis is orthogonalised and the
+// residual recurrence r -= alpha_k A p_k runs -- every convergence decision is taken on the same numbers as in textbook GCR,
+// bit for bit -- and x = x0 + sum_k alpha_k p_k = x0 + sum_j c_j d_j is formed ONCE at the end, c = U alpha with the small
+// unit upper-triangular U the beta's define (host, K^3 flops, K <= restart length).  That removes the p-basis update (k + 2
+// vector passes) and the x update (3 passes) from every iteration; the unpreconditioned solver does not even copy the
+// residual into a direction: each step writes its new residual into a fresh vector and the old one IS d_k.
 inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<double>* phi0, int size, int max_iter, double eps,
                                matrix_op_cplx matrix_vector, void* extra_info,
                                precond_op_cplx precond, void* precond_info, inversion_verbose_struct* verb, SolveHints* hints = 0)
 {
+  typedef complex<double> cplx;
   inversion_info invif;
   invif.name = name;
   inversion_verbose_struct verb_prec = precond_view(verb);
@@ -32,90 +41,121 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
   const bool zero_start = (flags & SOLVE_ZERO_START) != 0;
   const bool zero_for_precond = (precond != 0 && precond != overwriting_precond());
   int executed = 0;
-  complex<double>* r = allocate_vector<complex<double> >(size);
-  complex<double>* z = precond ? allocate_vector<complex<double> >(size) : 0;
-  complex<double>* scratch = 0;
-  std::vector<complex<double>*> p, Ap;
+  std::vector<cplx*> owned;                 // every vector allocated here
+  std::vector<cplx*> d, Ap;                 // raw directions (may alias residual vectors or phi0) and the orthogonalised A p basis
+  std::vector<cplx> alpha;
+  std::vector<double> apn;
+  struct Alloc { std::vector<cplx*>& o; int n; cplx* operator()() { cplx* v = allocate_vector<cplx>(n); o.push_back(v); return v; } } fresh = { owned, size };
+  cplx* scratch = 0;
   double bsq = (hints != 0 && hints->bnorm2 >= 0.0) ? hints->bnorm2 : norm2sq(phi0, size);
   const double bsqrt = sqrt(bsq);
-  complex<double>* r_in = r;
+  cplx* cur_r;
   double rsq;
 
   if (zero_start)
   {
     invif.ops_count++;           // the reference's A.0
-    r_in = phi0; rsq = bsq;
+    cur_r = phi0; rsq = bsq;
   }
   else
   {
     if (hints != 0 && (hints->flags & SOLVE_ZERO_START)) zero_vector(phi, size);
-    scratch = allocate_vector<complex<double> >(size);
+    scratch = fresh();
+    cur_r = fresh();
     matrix_vector(scratch, phi, extra_info); invif.ops_count++; executed++;
-    caxpbyz(1.0, phi0, -1.0, scratch, r, size);
-    rsq = norm2sq(r, size);
+    caxpbyz(1.0, phi0, -1.0, scratch, cur_r, size);
+    rsq = norm2sq(cur_r, size);
   }
 
   int k = 0;
   bool converged = sqrt(rsq) < eps * bsqrt;
-  bool stepped = false;
-  // device scratch of the orthogonalisation: <Ap_i|Ap_k> of the current step, |Ap_i|^2 of every step so far (the coefficients
-  // beta_i = -<Ap_i|Ap_k> / |Ap_i|^2 are formed on the device, qmg_gcr_orthogonalize: one host wait per iteration, not two)
+  // device scratch: row k holds <Ap_i|Ap_k>, i < k, of the orthogonalisation of direction k; |Ap_i|^2 of every step so far
   double* dev_dots = 0; double* dev_apn = 0;
+  long cap = 0;
   if (!converged && max_iter > 0)
   {
-    long cap = max_iter < 64 ? max_iter + 1 : 64;          // grown on demand: an unrestarted solve may be allowed 10^8 iterations
-    dev_dots = allocate_vector<double>(2 * cap);
+    cap = max_iter < 32 ? max_iter + 1 : 32;          // grown on demand: an unrestarted solve may be allowed 10^8 iterations
+    dev_dots = allocate_vector<double>(2 * cap * cap);
     dev_apn = allocate_vector<double>(cap);
-    p.push_back(allocate_vector<complex<double> >(size));
-    Ap.push_back(allocate_vector<complex<double> >(size));
-    if (precond) { if (zero_for_precond) zero_vector(p[0], size); precond(p[0], r_in, size, precond_info, &verb_prec); }
-    else copy_vector(p[0], r_in, size);
-    matrix_vector(Ap[0], p[0], extra_info); invif.ops_count++; executed++;
+    cplx* dk = cur_r;
+    if (precond) { dk = fresh(); if (zero_for_precond) zero_vector(dk, size); precond(dk, cur_r, size, precond_info, &verb_prec); }
+    d.push_back(dk);
+    Ap.push_back(fresh());
+    matrix_vector(Ap[0], d[0], extra_info); invif.ops_count++; executed++;
     bool dots_ready = false;
     for (k = 1; k <= max_iter; k++)
     {
       const int c = k - 1;
-      // alpha = <Ap|r> / <Ap|Ap> formed on the device; x += alpha p ; r -= alpha Ap ; |r|^2 : the one host wait of the step
+      // alpha = <Ap|r> / <Ap|Ap> formed on the device; r' = r - alpha Ap ; |r'|^2 : the one host wait of the iteration.
+      // Unpreconditioned, r' goes into a fresh vector: the old residual is direction d_c and must stay.
+      cplx* next_r = precond ? (cur_r == phi0 ? fresh() : cur_r) : fresh();
       double step[5];
-      QMG_CHK(qmg_krylov_step(1.0, P(p[c]), P(Ap[c]), (zero_start && k == 1) ? 0 : P(phi), P(phi), P(r_in), P(r), 0, size,
-                              dots_ready ? QMG_STEP_DOTS_READY : 0, step, dev_apn + c));
-      r_in = r;
-      stepped = true;
+      QMG_CHK(qmg_krylov_step(1.0, 0, P(Ap[c]), 0, 0, P(cur_r), P(next_r), 0, size, QMG_STEP_R_ONLY | (dots_ready ? QMG_STEP_DOTS_READY : 0), step, dev_apn + c));
+      alpha.push_back(cplx(step[1], step[2]) / step[3]);
+      apn.push_back(step[3]);
+      cur_r = next_r;
       rsq = step[0];
       say(verb, VERB_DETAIL, name, "", false, false, k, invif.ops_count, sqrt(rsq) / bsqrt);
       if (sqrt(rsq) < eps * bsqrt) { converged = true; break; }
       if (k == max_iter) break;
 
-      // next direction: d = M^-1 r (or r), A d straight into its slot, then project out the stored set on the device
-      p.push_back(allocate_vector<complex<double> >(size));
-      Ap.push_back(allocate_vector<complex<double> >(size));
-      complex<double>* dir = r;
-      if (precond) { if (zero_for_precond) zero_vector(z, size); precond(z, r, size, precond_info, &verb_prec); dir = z; }
-      matrix_vector(Ap[k], dir, extra_info); invif.ops_count++; executed++;
+      // next direction: d = M^-1 r (or r itself), A d straight into its slot, then project the stored A p_i out of it on the device
+      dk = cur_r;
+      if (precond) { dk = fresh(); if (zero_for_precond) zero_vector(dk, size); precond(dk, cur_r, size, precond_info, &verb_prec); }
+      d.push_back(dk);
+      Ap.push_back(fresh());
+      matrix_vector(Ap[k], dk, extra_info); invif.ops_count++; executed++;
       if (k + 1 > cap)
       {
-        double* grown = allocate_vector<double>(2 * cap);
-        copy_vector(grown, dev_apn, cap);
-        deallocate_vector(&dev_apn); deallocate_vector(&dev_dots);
-        cap *= 2;
-        dev_apn = grown;
-        dev_dots = allocate_vector<double>(2 * cap);
+        double* gd = allocate_vector<double>(8 * cap * cap);        // (2 cap)^2 rows x columns, 2 doubles each
+        double* ga = allocate_vector<double>(2 * cap);
+        for (long row = 1; row < k; row++) copy_vector(gd + row * 4 * cap, dev_dots + row * 2 * cap, 2 * row);
+        copy_vector(ga, dev_apn, cap);
+        deallocate_vector(&dev_dots); deallocate_vector(&dev_apn);
+        dev_dots = gd; dev_apn = ga; cap *= 2;
       }
-      std::vector<const qmg_cplx*> aps(k), ps(k);
-      for (int i = 0; i < k; i++) { aps[i] = P(Ap[i]); ps[i] = P(p[i]); }
-      QMG_CHK(qmg_gcr_orthogonalize(aps.data(), ps.data(), k, P(Ap[k]), P(dir), P(p[k]), P(r), size, dev_dots, dev_apn));
+      std::vector<const qmg_cplx*> aps(k);
+      for (int i = 0; i < k; i++) aps[i] = P(Ap[i]);
+      QMG_CHK(qmg_gcr_orthogonalize(aps.data(), 0, k, P(Ap[k]), 0, 0, P(cur_r), size, dev_dots + (long)k * 2 * cap, dev_apn));
       dots_ready = true;
     }
   }
   if (k > max_iter) k = max_iter;
-  // a zero start that took no step (b = 0, or no iterations allowed) still owes the caller its x = 0
-  if (zero_start && !stepped) zero_vector(phi, size);
+
+  // x = x0 + sum_j c_j d_j,  c = U alpha,  U[:,k] = e_k + sum_{i<k} beta_ki U[:,i],  beta_ki = -<Ap_i|Ap_k> / |Ap_i|^2
+  const int K = (int)alpha.size();
+  if (zero_start) zero_vector(phi, size);      // (also the zero start that took no step: b = 0)
+  if (K > 0)
+  {
+    std::vector<double> hd((size_t)K * 2 * cap, 0.0);
+    if (K > 1) QMG_CHK(qmg_memcpy_d2h(hd.data(), dev_dots, sizeof(double) * (size_t)K * 2 * cap));
+    std::vector<std::vector<cplx> > U(K, std::vector<cplx>(K, cplx(0.0, 0.0)));
+    for (int kk = 0; kk < K; kk++)
+    {
+      U[kk][kk] = 1.0;
+      for (int i = 0; i < kk; i++)
+      {
+        const cplx beta = -cplx(hd[(size_t)kk * 2 * cap + 2 * i], hd[(size_t)kk * 2 * cap + 2 * i + 1]) / apn[i];
+        for (int j = 0; j <= i; j++) U[j][kk] += beta * U[j][i];
+      }
+    }
+    std::vector<double> coef(2 * K);
+    std::vector<const qmg_cplx*> ds(K);
+    for (int j = 0; j < K; j++)
+    {
+      cplx cj(0.0, 0.0);
+      for (int kk = j; kk < K; kk++) cj += U[j][kk] * alpha[kk];
+      coef[2 * j] = cj.real(); coef[2 * j + 1] = cj.imag();
+      ds[j] = P(d[j]);
+    }
+    QMG_CHK(qmg_multi_axpy(coef.data(), ds.data(), K, P(phi), size));
+  }
 
   invif.ops_count++;
   if ((flags & SOLVE_NO_FINAL_RESIDUAL) && converged) invif.resSq = rsq;     // converged: nothing downstream reads the true residual
   else
   {
-    if (scratch == 0) scratch = allocate_vector<complex<double> >(size);
+    if (scratch == 0) scratch = fresh();
     matrix_vector(scratch, phi, extra_info); executed++;
     invif.resSq = diffnorm2sq(scratch, phi0, size);
   }
@@ -124,12 +164,9 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
   say(verb, VERB_SUMMARY, name, "", true, invif.success, invif.iter, invif.ops_count, sqrt(invif.resSq) / bsqrt);
   if (hints != 0) hints->executed += executed;
 
-  for (size_t i = 0; i < p.size(); i++) { deallocate_vector(&p[i]); deallocate_vector(&Ap[i]); }
+  for (size_t i = 0; i < owned.size(); i++) deallocate_vector(&owned[i]);
   if (dev_dots != 0) deallocate_vector(&dev_dots);
   if (dev_apn != 0) deallocate_vector(&dev_apn);
-  deallocate_vector(&r);
-  if (scratch != 0) deallocate_vector(&scratch);
-  if (z != 0) deallocate_vector(&z);
   return invif;
 }
 

@@ -244,7 +244,8 @@ int qmg_step_xr_norm(double omega, const qmg_cplx* p, const qmg_cplx* q, qmg_cpl
  * result5 = { |r_out|^2, Re<q|r_in>, Im<q|r_in>, <q|q>, |r_in|^2 }.  Without flags bit-identical to qmg_step_xr_norm.
  * QMG_STEP_DOTS_READY: <q|r_in> and <q|q> were left on the device by qmg_gcr_orthogonalize -- the dot pass is skipped.
  * qq_dev (device, may be NULL): receives <q|q>, the |Ap_k|^2 later GCR orthogonalisations divide by. */
-enum { QMG_STEP_WANT_RNORM = 1, QMG_STEP_X_ONLY = 2, QMG_STEP_DOTS_READY = 4 };
+enum { QMG_STEP_WANT_RNORM = 1, QMG_STEP_X_ONLY = 2, QMG_STEP_DOTS_READY = 4,
+       QMG_STEP_R_ONLY = 8 /* r_out = r_in - alpha q and |r_out|^2 only: p, x_in, x_out, acc are not touched (GCR forming x at the end) */ };
 int qmg_krylov_step(double omega, const qmg_cplx* p, const qmg_cplx* q, const qmg_cplx* x_in, qmg_cplx* x_out,
                     const qmg_cplx* r_in, qmg_cplx* r_out, const qmg_cplx* acc, long n, int flags, double* result5, double* qq_dev);
 /* GCR: orthogonalise the new direction against the k stored ones with the coefficients formed ON THE DEVICE and prepare the
@@ -252,8 +253,9 @@ int qmg_krylov_step(double omega, const qmg_cplx* p, const qmg_cplx* q, const qm
  * the x / r update):  dots_dev[2j..] = <Ap[j]|Ap_k> ;  beta_j = -dots_j / apn_dev[j] ;  Ap_k += sum beta_j Ap[j] ;
  * p_k = dir + sum beta_j p[j] (dir == p_k allowed) ;  { <Ap_k|r>, |Ap_k|^2 } stay on the device for qmg_krylov_step with
  * QMG_STEP_DOTS_READY.  Ap_host / p_host: HOST arrays of k device pointers; dots_dev: 2k doubles of device scratch;
- * apn_dev: k doubles on the device (filled by qmg_krylov_step's qq_dev).  k >= 1.  Bit-identical to qmg_multi_dot + host
- * division + 2 qmg_multi_axpyz + the dot pass of the step. */
+ * apn_dev: k doubles on the device (filled by qmg_krylov_step's qq_dev).  k >= 1.  Same sums as qmg_multi_dot + host
+ * division + 2 qmg_multi_axpyz + the dot pass of the step.  p_host NULL: only the A p basis is orthogonalised (dir, pk
+ * unused) -- the solver keeps the raw directions and forms x from them once, at the end of the solve. */
 int qmg_gcr_orthogonalize(const qmg_cplx* const* Ap_host, const qmg_cplx* const* p_host, int k, qmg_cplx* Apk, const qmg_cplx* dir, qmg_cplx* pk,
                           const qmg_cplx* r, long n, double* dots_dev, const double* apn_dev);
 /* y += sum_j a_j xs[j]   (GCR: p_k += sum beta_i p_i) ; a: HOST 2k doubles; xs: HOST array of k device pointers */

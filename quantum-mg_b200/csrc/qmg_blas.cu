@@ -431,7 +431,7 @@ namespace qmg {
 //   Ap_k = (first ? Ap_k : Ap_k) + sum_j beta_j Ap_j ;  p_k = (first ? dir : p_k) + sum_j beta_j p_j
 //   last pass only: { <Ap_k|r>, |Ap_k|^2 } -> result (device)
 // One pass holds K vectors; the host chains passes of 8 in the order qmg_multi_axpyz uses, so the sums come out bit-identical.
-template <int K, bool DOTS>
+template <int K, bool DOTS, bool WITHP>
 __global__ void __launch_bounds__(kEwBlock) gcr_ortho_kernel(long n, PtrPack<K> Ap, PtrPack<K> P, int k, cd* apk, const cd* dir,
                                                              cd* pk, const cd* __restrict__ r, const double* __restrict__ dots,
                                                              const double* __restrict__ apn, double* partials, unsigned int* counter, double* result)
@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(kEwBlock) gcr_ortho_kernel(long n, PtrPack<K> 
     apk[i] = t;
     if (DOTS) dot_acc3(acc, t, rr);
   }
+  if (WITHP)
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
   {
     cd b[K];
@@ -473,21 +474,21 @@ __global__ void __launch_bounds__(kEwBlock) gcr_ortho_kernel(long n, PtrPack<K> 
   if (DOTS) grid_reduce_finish<3>(acc, smem, partials, counter, result);
 }
 
-template <int K>
+template <int K, bool WITHP>
 static int gcr_ortho_pass(long n, const qmg_cplx* const* Ap, const qmg_cplx* const* P, int k, cd* apk, const cd* dir, cd* pk, const cd* r,
                           const double* dots, const double* apn, bool with_dots, double* result_dev)
 {
   PtrPack<K> a, b;
-  for (int j = 0; j < K; j++) { a.p[j] = CCD(Ap[j < k ? j : 0]); b.p[j] = CCD(P[j < k ? j : 0]); }
+  for (int j = 0; j < K; j++) { a.p[j] = CCD(Ap[j < k ? j : 0]); b.p[j] = WITHP ? CCD(P[j < k ? j : 0]) : nullptr; }
   Runtime& rtm = rt();
-  const int grid = with_dots ? resident_grid(gcr_ortho_kernel<K, true>, n) : resident_grid(gcr_ortho_kernel<K, false>, n);
+  const int grid = with_dots ? resident_grid(gcr_ortho_kernel<K, true, WITHP>, n) : resident_grid(gcr_ortho_kernel<K, false, WITHP>, n);
   if (with_dots)
   {
-    gcr_ortho_kernel<K, true><<<grid, kEwBlock, 0, rtm.stream>>>(n, a, b, k, apk, dir, pk, r, dots, apn, rtm.d_partials, rtm.d_counter, result_dev);
+    gcr_ortho_kernel<K, true, WITHP><<<grid, kEwBlock, 0, rtm.stream>>>(n, a, b, k, apk, dir, pk, r, dots, apn, rtm.d_partials, rtm.d_counter, result_dev);
     QMG_LAUNCH_CHECK();
     return skip_result(result_dev, 3);
   }
-  gcr_ortho_kernel<K, false><<<grid, kEwBlock, 0, rtm.stream>>>(n, a, b, k, apk, dir, pk, r, dots, apn, nullptr, nullptr, nullptr);
+  gcr_ortho_kernel<K, false, WITHP><<<grid, kEwBlock, 0, rtm.stream>>>(n, a, b, k, apk, dir, pk, r, dots, apn, nullptr, nullptr, nullptr);
   QMG_LAUNCH_CHECK();
   return 0;
 }
@@ -505,6 +506,7 @@ int qmg_gcr_orthogonalize(const qmg_cplx* const* Ap_host, const qmg_cplx* const*
 {
   QMG_REQUIRE_INIT();
   if (n <= 0) return fail_msg("qmg_gcr_orthogonalize: empty vector");
+  if (k < 1) return fail_msg("qmg_gcr_orthogonalize: k >= 1 stored directions needed");
   cd* apk = CD(Apk_); const cd* dir = CCD(dir_); cd* pk = CD(pk_); const cd* r = CCD(r_);
   double* dres = rt().d_result + 64;
   int rc;
@@ -536,12 +538,23 @@ int qmg_gcr_orthogonalize(const qmg_cplx* const* Ap_host, const qmg_cplx* const*
     const int left = k - done;
     const int take = left >= 8 ? 8 : left;
     const bool last = (done + take >= k);
-    const qmg_cplx* const* A = Ap_host + done; const qmg_cplx* const* Pp = p_host + done;
+    const qmg_cplx* const* A = Ap_host + done; const qmg_cplx* const* Pp = (p_host != nullptr) ? p_host + done : nullptr;
     const double* dd = dots_dev + 2 * done; const double* nn = apn_dev + done;
-    if (take > 4) rc = gcr_ortho_pass<8>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
-    else if (take > 2) rc = gcr_ortho_pass<4>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
-    else if (take == 2) rc = gcr_ortho_pass<2>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
-    else rc = gcr_ortho_pass<1>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);     // take == 0 (k == 0): p_k = dir, dots only
+    if (p_host != nullptr)
+    {
+      if (take > 4) rc = gcr_ortho_pass<8, true>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
+      else if (take > 2) rc = gcr_ortho_pass<4, true>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
+      else if (take == 2) rc = gcr_ortho_pass<2, true>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
+      else rc = gcr_ortho_pass<1, true>(n, A, Pp, take, apk, src_dir, pk, r, dd, nn, last, dres);
+    }
+    else
+    {
+      // the directions are kept unorthogonalised (the solver forms x from them once, at the end): only the A p basis moves
+      if (take > 4) rc = gcr_ortho_pass<8, false>(n, A, A, take, apk, nullptr, nullptr, r, dd, nn, last, dres);
+      else if (take > 2) rc = gcr_ortho_pass<4, false>(n, A, A, take, apk, nullptr, nullptr, r, dd, nn, last, dres);
+      else if (take == 2) rc = gcr_ortho_pass<2, false>(n, A, A, take, apk, nullptr, nullptr, r, dd, nn, last, dres);
+      else rc = gcr_ortho_pass<1, false>(n, A, A, take, apk, nullptr, nullptr, r, dd, nn, last, dres);
+    }
     if (rc) return rc;
     done += take;
     src_dir = pk;        // later passes continue in place
@@ -588,6 +601,25 @@ int qmg_krylov_step(double omega, const qmg_cplx* p_, const qmg_cplx* q_, const 
   else
     rc = launch_reduce_keep<3>(n, [=] __device__(long i, double (&acc)[3]) { dot_acc3(acc, q[i], rin[i]); }, dres);
   if (rc) return rc;
+  if (flags & QMG_STEP_R_ONLY)
+  {
+    // GCR with the solution formed once at the end: only the residual recurrence runs per step
+    double out1[1];
+    rc = launch_reduce<1>(n, [=] __device__(long i, double (&acc)[1]) {
+      const double d0 = dres[0], d1 = dres[1], d2 = dres[2];
+      const cd a = cmake(__ddiv_rn(__dmul_rn(omega, d0), d2), __ddiv_rn(__dmul_rn(omega, d1), d2));
+      const cd ma = cmake(-a.x, -a.y);
+      if (i == 0) { aux[0] = d0; aux[1] = d1; aux[2] = d2; if (qq_dev != nullptr) qq_dev[0] = d2; __threadfence_system(); }
+      cd ri = rin[i];
+      cfma(ri, ma, q[i]); r[i] = ri;
+      acc[0] += ri.x * ri.x + ri.y * ri.y;
+    }, out1);
+    if (rc) return rc;
+    result5[0] = out1[0];
+    if (rtm.publish_now) { result5[1] = aux[0]; result5[2] = aux[1]; result5[3] = aux[2]; result5[4] = 0.0; }
+    else { QMG_CUDA(cudaMemcpy(result5 + 1, dres, sizeof(double) * 3, cudaMemcpyDeviceToHost)); result5[4] = 0.0; }
+    return 0;
+  }
   if (flags & QMG_STEP_X_ONLY)
     return launch_ew(n, [=] __device__(long i) {
       const double d0 = dres[0], d1 = dres[1], d2 = dres[2];

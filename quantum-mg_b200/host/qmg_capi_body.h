@@ -814,6 +814,11 @@ void* CAPI(kcycle_new)(int X, int Y, double mass, const capi_cd* gauge, const in
   capi::kcycle_build_hierarchy(h);
   capi_barrier();
   h->setup_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+#ifdef QMG_B200_HOST
+  // the set-up's work vectors (14 per BiCGstab-6 solve, the raw null vectors) are parked in the allocator's cache: hand them
+  // back to the driver so that the solve's own vectors -- other sizes, other counts -- have the room
+  QMG_CHK(qmg_trim());
+#endif
   return h;
 }
 // ---- adaptive set-up (tests/n22_wilson_kcycle_adaptive/wilson_kcycle.cpp:226-440): test vectors relaxed with
