@@ -485,15 +485,18 @@ template <int NC, int TK, int TY, int SPLIT> struct TmaTile
   // copies: +x rows 2 TY, +x halo column TY, +y rows 2 TY, +y halo row 2, spinor (row, parity) pairs 2 (TY + 2)
   static const int NCOPY = 2 * TY + TY + 2 * TY + 2 + 2 * (TY + 2);
 
-  // issued by ONE warp: lane l takes copies l, l + 32, ...
-  __device__ static __forceinline__ void stage(const StencilKArgs& a, cd* buf, unsigned long long* bar, int k0, int y0, int lane)
+  // Issued by ONE warp: lane l takes copies l, l + 32, ...  Two halves with their own completion barriers and their own
+  // destination regions, so that the ring kernel can recycle them separately: X = +x blocks (rows, left halo column) and the
+  // spinor rows with their ring; Y = +y blocks (rows, halo row below).
+  static const unsigned BYTES_Y = (unsigned)(sizeof(cd) * (size_t)NHY * LPS);
+  static const unsigned BYTES_X = BYTES - BYTES_Y;
+  static const int NCOPY_X = 2 * TY + TY + 2 * (TY + 2), NCOPY_Y = 2 * TY + 2;
+  __device__ static __forceinline__ void stage_x(const StencilKArgs& a, cd* sHx, cd* sV, unsigned long long* bar, int k0, int y0, int lane)
   {
-    cd* sHx = buf; cd* sHy = sHx + (size_t)NHX * LPS; cd* sV = sHy + (size_t)NHY * LPS;
     const int xh = a.g.xh, Y = a.g.Y;
     const size_t half = a.g.half;
     const cd* hopx = a.hop;
-    const cd* hopy = a.hop + a.size_cm;
-    for (int c = lane; c < NCOPY; c += 32)
+    for (int c = lane; c < NCOPY_X; c += 32)
     {
       int j = c;
       if (j < 2 * TY)
@@ -510,20 +513,6 @@ template <int NC, int TK, int TY, int SPLIT> struct TmaTile
         continue;
       }
       j -= TY;
-      if (j < 2 * TY)
-      {
-        const int ty = j >> 1, p = j & 1;
-        bulk_g2s(sHy + (size_t)(j * TK) * LPS, hopy + ((size_t)p * half + (size_t)(y0 + ty) * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
-        continue;
-      }
-      j -= 2 * TY;
-      if (j < 2)
-      {
-        const int p = j, y = (y0 == 0) ? Y - 1 : y0 - 1;       // the row below the patch
-        bulk_g2s(sHy + (size_t)(S + p * TK) * LPS, hopy + ((size_t)p * half + (size_t)y * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
-        continue;
-      }
-      j -= 2;
       {
         // spinor row ry - 1 of the patch (ry = 0 .. TY + 1), parity p, sites k0 - 1 .. k0 + TK: contiguous except across the x wrap
         const int ry = j >> 1, p = j & 1;
@@ -537,6 +526,32 @@ template <int NC, int TK, int TY, int SPLIT> struct TmaTile
         if (wr) bulk_g2s(dst + (size_t)(VK - 1) * NC, row, NC * sizeof(cd), bar);
       }
     }
+  }
+  __device__ static __forceinline__ void stage_y(const StencilKArgs& a, cd* sHy, unsigned long long* bar, int k0, int y0, int lane)
+  {
+    const int xh = a.g.xh, Y = a.g.Y;
+    const size_t half = a.g.half;
+    const cd* hopy = a.hop + a.size_cm;
+    for (int j = lane; j < NCOPY_Y; j += 32)
+    {
+      if (j < 2 * TY)
+      {
+        const int ty = j >> 1, p = j & 1;
+        bulk_g2s(sHy + (size_t)(j * TK) * LPS, hopy + ((size_t)p * half + (size_t)(y0 + ty) * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
+      }
+      else
+      {
+        const int p = j - 2 * TY, y = (y0 == 0) ? Y - 1 : y0 - 1;       // the row below the patch
+        bulk_g2s(sHy + (size_t)(S + p * TK) * LPS, hopy + ((size_t)p * half + (size_t)y * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
+      }
+    }
+  }
+  // the one-patch kernel: everything into one buffer [Hx | Hy | V], one barrier
+  __device__ static __forceinline__ void stage(const StencilKArgs& a, cd* buf, unsigned long long* bar, int k0, int y0, int lane)
+  {
+    cd* sHx = buf; cd* sHy = sHx + (size_t)NHX * LPS; cd* sV = sHy + (size_t)NHY * LPS;
+    stage_x(a, sHx, sV, bar, k0, y0, lane);
+    stage_y(a, sHy, bar, k0, y0, lane);
   }
 
   __device__ static __forceinline__ void compute(const StencilKArgs& a, const cd* buf, int k0, int y0, int tid, const cd (&CLc)[PASSES][R], const cd (&RBc)[PASSES])
@@ -627,6 +642,57 @@ template <int NC, int TK, int TY, int SPLIT> struct TmaTile
   }
 };
 
+// The persistent ring kernel runs the patch arithmetic for patch after patch with the SAME thread -> (site, column, rows)
+// assignment, so everything that depends on the thread alone -- the element offsets of its nine operand streams inside a
+// stage, its signs, which of its rows receives the backward sum, where its output element sits relative to the patch origin --
+// is worked out ONCE (a third of the consumer's instructions were this index arithmetic: 289 IMAD against 92 DFMA in the
+// SASS) and a patch costs the loads, the products, the butterfly and one add for the global offset of its origin.  Needs the
+// parity of the first row of every patch to be the same (TY even, so y0 = y_off + by TY has the parity of y_off).
+template <int NC, int TK, int TY, int SPLIT> struct RingInv
+{
+  typedef TmaTile<NC, TK, TY, SPLIT> T;
+  static const int R = T::R, LPS = T::LPS, S = T::S, VK = T::VK;
+  int oVC, oV0, oV1, ov2, ov3;       // element offsets into the spinor region of the stage
+  int ohx, obx;                      // ... into its +x region
+  int ohy, oby;                      // ... into its +y region
+  int out_local, cl_local;           // output element / first clover element relative to the patch origin (units of elements)
+  int back_row;                      // index i of acc[] that receives the backward row sum on this thread, or -1
+  double sg;
+  bool writer;
+  cd dg;
+
+  __device__ __forceinline__ void init(const StencilKArgs& a, int tid, int y_parity)
+  {
+    static_assert((TY & 1) == 0, "RingInv: TY must be even");
+    const int c2 = tid % NC, hf = (tid / NC) % SPLIT;
+    const bool top = (2 * c2 < NC);
+    const int slot = tid / (NC * SPLIT);
+    const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; const int p = r / TK, tk = r - p * TK;
+    const int q = 1 - p, sft = (y_parity + ty + p) & 1;
+    const int nx = sft ? (ty * 2 + q) * TK + tk : (tk > 0 ? (ty * 2 + q) * TK + tk - 1 : S + ty);
+    const int ny = (ty > 0) ? ((ty - 1) * 2 + q) * TK + tk : S + q * TK + tk;
+    const int vbase = ((ty + 1) * 2) * VK * NC;        // row ty of the patch, parity 0, kk = 0
+    oVC = vbase + (p * VK + tk + 1) * NC + c2;
+    oV0 = vbase + (q * VK + tk + 1 + sft) * NC + c2;
+    oV1 = vbase + ((2 + q) * VK + tk + 1) * NC + c2;
+    ov2 = vbase + (q * VK + tk + sft) * NC + hf * R;
+    ov3 = vbase + (q * VK + tk + 1 - 2 * VK) * NC + hf * R;
+    ohx = slot * LPS + (hf * R) * NC + c2;
+    ohy = slot * LPS + (hf * R) * NC + c2;
+    obx = nx * LPS + (hf * R) * NC + c2;
+    oby = ny * LPS + (hf * R) * NC + c2;
+    sg = (top == (2 * hf * R < NC)) ? 1.0 : -1.0;
+    back_row = (c2 >= hf * R && c2 < hf * R + R) ? c2 - hf * R : -1;
+    writer = (SPLIT == 1 || (c2 % SPLIT) == 0);
+    const int row = hf * R + c2 / SPLIT;
+    // site = p half + (y0 + ty) xh + (k0 + tk): the patch origin contributes (y0 xh + k0), the rest is local
+    const long site_local = (long)p * a.g.half + (long)ty * a.g.xh + tk;
+    out_local = (int)(site_local * NC + row);
+    cl_local = (int)(site_local * LPS + (hf * R) * NC + c2);
+    dg = a.use_diag ? a.diag[p][top ? 0 : 1] : cmake(0.0, 0.0);
+  }
+};
+
 template <int NC, int TK, int TY, int SPLIT>
 __global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT > 1 ? 1024 / TileDims<NC, TK, TY, SPLIT>::THREADS : 1)) stencil_tma_kernel(const StencilKArgs a)
 {
@@ -694,84 +760,204 @@ __device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsig
   }
 }
 
-template <int NC, int TK, int TY, int SPLIT, int NSTAGE, int NGROUP> struct RingCfg
+template <int NC, int TK, int TY, int SPLIT, int NSTAGE> struct RingCfg
 {
   typedef TmaTile<NC, TK, TY, SPLIT> T;
-  static const int GT = TileDims<NC, TK, TY, SPLIT>::THREADS;      // threads of one consumer group = one patch
-  static const int NTHREADS = NGROUP * GT + 32;
-  static const size_t STAGE_BYTES = (T::BYTES + 127) & ~(size_t)127;
-  static const size_t SMEM = 256 + NSTAGE * STAGE_BYTES;
+  static const int GT = TileDims<NC, TK, TY, SPLIT>::THREADS;      // consumer threads = one patch
+  static const int NTHREADS = GT + 32;
+  static const int NVSLOT = 2 * NSTAGE;                            // spinor tiles ride in their own, longer ring (see the kernel)
+  static const size_t BX = sizeof(cd) * (size_t)T::NHX * T::LPS, BY = sizeof(cd) * (size_t)T::NHY * T::LPS, BV = (sizeof(cd) * (size_t)T::NV + 127) & ~(size_t)127;
+  static const size_t OFF_X = 256, OFF_Y = OFF_X + NSTAGE * BX, OFF_V = OFF_Y + NSTAGE * BY;
+  static const size_t SMEM = OFF_V + NVSLOT * BV;
 };
 
-template <int NC, int TK, int TY, int SPLIT, int NSTAGE, int NGROUP>
-__global__ void __launch_bounds__(RingCfg<NC, TK, TY, SPLIT, NSTAGE, NGROUP>::NTHREADS, 1)
+// One consumer group of GT threads, one producer warp.  A stage is an X buffer (+x blocks) and a Y buffer (+y blocks) with their
+// own full / empty barriers; the spinor tile of patch j sits in slot j mod 2 NSTAGE of a third, small ring and completes on the X
+// barrier.  The consumers hand the X buffer back right after the x half of the arithmetic, so the producer refills it while
+// they are still on the y half and on the next patch: about one and a half stages are in flight instead of one, which is what
+// hides the DRAM latency at the head of a stage.  (A spinor slot is reused 2 NSTAGE patches later -- its previous tenant was
+// finished before the X buffer that gates the refill was even handed over.)
+template <int NC, int TK, int TY, int SPLIT, int NSTAGE>
+__global__ void __launch_bounds__(RingCfg<NC, TK, TY, SPLIT, NSTAGE>::NTHREADS, 1)
 stencil_ring_kernel(const StencilKArgs a, const int npatch, const int nbx, unsigned long long* err, const int dbg)
 {
-  typedef RingCfg<NC, TK, TY, SPLIT, NSTAGE, NGROUP> CFG;
+  typedef RingCfg<NC, TK, TY, SPLIT, NSTAGE> CFG;
   typedef TmaTile<NC, TK, TY, SPLIT> T;
-  typedef Tile<NC, TK, TY, SPLIT> T0;
-  static_assert(TileDims<NC, TK, TY, SPLIT>::PASSES == 1, "ring kernel: one patch per consumer group");
+  static_assert(TileDims<NC, TK, TY, SPLIT>::PASSES == 1, "ring kernel: one patch per pass of the consumer group");
   extern __shared__ __align__(128) unsigned char ring_smem[];
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring_smem);
-  unsigned long long* empty = full + NSTAGE;
+  unsigned long long* full_x = reinterpret_cast<unsigned long long*>(ring_smem);      // +x blocks and spinors have landed
+  unsigned long long* full_y = full_x + NSTAGE;                                       // +y blocks have landed
+  unsigned long long* empty_x = full_y + NSTAGE;
+  unsigned long long* empty_y = empty_x + NSTAGE;
   const int tid = threadIdx.x;
   if (tid == 0)
   {
-    for (int s = 0; s < NSTAGE; s++) { mbar_init(full + s, 1); mbar_init(empty + s, CFG::GT / 32); }
+    for (int s = 0; s < NSTAGE; s++) { mbar_init(full_x + s, 1); mbar_init(full_y + s, 1); mbar_init(empty_x + s, CFG::GT / 32); mbar_init(empty_y + s, CFG::GT / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid >= NGROUP * CFG::GT)
+  if (tid >= CFG::GT)
   {
     // producer warp
-    const int lane = tid - NGROUP * CFG::GT;
+    const int lane = tid - CFG::GT;
     int j = 0;
     for (int t = blockIdx.x; t < npatch; t += gridDim.x, j++)
     {
       const int s = j % NSTAGE, round = j / NSTAGE;
-      if (!mbar_wait_bounded(empty + s, (unsigned)((round & 1) ^ 1), err)) return;
-      if (dbg == 2) { if (lane == 0) mbar_arrive(full + s); continue; }      // timing experiment: no copies, consumers compute on whatever is there
-      if (lane == 0) mbar_expect_tx(full + s, T::BYTES);
-      __syncwarp();
       const int by = t / nbx, bx = t - by * nbx;
-      T::stage(a, reinterpret_cast<cd*>(ring_smem + 256 + (size_t)s * CFG::STAGE_BYTES), full + s, bx * TK, a.y_off + by * TY, lane);
+      const int k0 = bx * TK, y0 = a.y_off + by * TY;
+      if (!mbar_wait_bounded(empty_x + s, (unsigned)((round & 1) ^ 1), err)) return;
+      if (dbg == 2) { if (lane == 0) mbar_arrive(full_x + s); }      // timing experiment 2: no copies, the consumers compute on whatever is there
+      else
+      {
+        if (lane == 0) mbar_expect_tx(full_x + s, T::BYTES_X);
+        __syncwarp();
+        T::stage_x(a, reinterpret_cast<cd*>(ring_smem + CFG::OFF_X + (size_t)s * CFG::BX),
+                   reinterpret_cast<cd*>(ring_smem + CFG::OFF_V + (size_t)(j % CFG::NVSLOT) * CFG::BV), full_x + s, k0, y0, lane);
+      }
+      if (!mbar_wait_bounded(empty_y + s, (unsigned)((round & 1) ^ 1), err)) return;
+      if (dbg == 2) { if (lane == 0) mbar_arrive(full_y + s); }
+      else
+      {
+        if (lane == 0) mbar_expect_tx(full_y + s, T::BYTES_Y);
+        __syncwarp();
+        T::stage_y(a, reinterpret_cast<cd*>(ring_smem + CFG::OFF_Y + (size_t)s * CFG::BY), full_y + s, k0, y0, lane);
+      }
     }
     return;
   }
-  // consumer groups: group g takes patches j = g, g + NGROUP, ... of this CTA's list
-  const int g = tid / CFG::GT, gtid = tid - g * CFG::GT;
-  cd CLc[1][T::R], CLn[1][T::R];
-  cd RBc[1], RBn[1];
-  int j = g;
-  long t = (long)blockIdx.x + (long)j * gridDim.x;
-  if (t < npatch) { const int by = (int)(t / nbx), bx = (int)(t - (long)by * nbx); T0::clover(a, bx * TK, a.y_off + by * TY, gtid, CLc, RBc); }
-  for (; t < npatch; j += NGROUP, t += (long)NGROUP * gridDim.x)
+  // consumers
+  RingInv<NC, TK, TY, SPLIT> inv;
+  inv.init(a, tid, a.y_off & 1);
+  constexpr int R = T::R;
+  const cd zero = cmake(0.0, 0.0);
+  const bool has_cl = (a.clover != nullptr), has_rb = (a.resid != nullptr) && inv.writer, acc_old = (a.accumulate != 0) && inv.writer;
+  // this CTA's patch sequence without a division per patch: t advances by gridDim.x, (bx, by) by the matching (dx, dy)
+  const int stride = (int)gridDim.x;
+  const int dy = stride / nbx, dx = stride - dy * nbx;
+  int j = 0;
+  long t = blockIdx.x;
+  int by = (int)(t / nbx), bx = (int)(t - (long)by * nbx);
+  cd CLc[R], CLn[R];
+  cd RBc = zero, RBn = zero;
+#pragma unroll
+  for (int i = 0; i < R; i++) { CLc[i] = zero; CLn[i] = zero; }
+  if (t < npatch)
+  {
+    const long origin = (long)(a.y_off + by * TY) * a.g.xh + bx * TK;
+    if (has_cl) { const cd* cp = a.clover + origin * T::LPS + inv.cl_local;
+#pragma unroll
+      for (int i = 0; i < R; i++) CLc[i] = ld_stream(cp + i * NC); }
+    if (has_rb) RBc = ld_stream(a.resid + origin * NC + inv.out_local);
+  }
+  for (; t < npatch; j++, t += stride)
   {
     const int s = j % NSTAGE, round = j / NSTAGE;
-    const int by = (int)(t / nbx), bx = (int)(t - (long)by * nbx);
-    const long tn = t + (long)NGROUP * gridDim.x;
-    if (tn < npatch) { const int byn = (int)(tn / nbx), bxn = (int)(tn - (long)byn * nbx); T0::clover(a, bxn * TK, a.y_off + byn * TY, gtid, CLn, RBn); }
-    if (!mbar_wait_bounded(full + s, (unsigned)(round & 1), err)) return;
-    if (dbg != 1)      // (timing experiment 1: copies only, nothing computed)
-      T::compute(a, reinterpret_cast<const cd*>(ring_smem + 256 + (size_t)s * CFG::STAGE_BYTES), bx * TK, a.y_off + by * TY, gtid, CLc, RBc);
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(empty + s);
+    const long origin = (long)(a.y_off + by * TY) * a.g.xh + bx * TK;
+    // next patch: its clover column (and residual element) travel in registers while this one is computed
+    int bxn = bx + dx, byn = by + dy;
+    if (bxn >= nbx) { bxn -= nbx; byn++; }
+    if (t + stride < npatch)
+    {
+      const long on = (long)(a.y_off + byn * TY) * a.g.xh + bxn * TK;
+      if (has_cl) { const cd* cp = a.clover + on * T::LPS + inv.cl_local;
 #pragma unroll
-    for (int i = 0; i < T::R; i++) CLc[0][i] = CLn[0][i];
-    RBc[0] = RBn[0];
+        for (int i = 0; i < R; i++) CLn[i] = ld_stream(cp + i * NC); }
+      if (has_rb) RBn = ld_stream(a.resid + on * NC + inv.out_local);
+    }
+    const cd* sHx = reinterpret_cast<const cd*>(ring_smem + CFG::OFF_X + (size_t)s * CFG::BX);
+    const cd* sHy = reinterpret_cast<const cd*>(ring_smem + CFG::OFF_Y + (size_t)s * CFG::BY);
+    const cd* sV = reinterpret_cast<const cd*>(ring_smem + CFG::OFF_V + (size_t)(j % CFG::NVSLOT) * CFG::BV);
+    cd acc[R];
+    cd backx = zero, backy = zero;
+#pragma unroll
+    for (int i = 0; i < R; i++) acc[i] = zero;
+    // ---- x half: spinors and +x blocks have landed -> clover and x terms; then the X buffer goes back to the producer
+    if (!mbar_wait_bounded(full_x + s, (unsigned)(round & 1), err)) return;
+    const cd VC = sV[inv.oVC], V0 = sV[inv.oV0], V1 = sV[inv.oV1];
+    if (dbg != 1)      // (timing experiment 1: copies only, nothing computed)
+    {
+      const cd* hx = sHx + inv.ohx; const cd* bxp = sHx + inv.obx; const cd* v2 = sV + inv.ov2;
+#pragma unroll
+      for (int i = 0; i < R; i++)
+      {
+        cd tt = zero;
+        cfma(tt, CLc[i], VC);
+        cfma(tt, hx[i * NC], V0);
+        acc[i] = tt;
+        cfma_conj(backx, bxp[i * NC], v2[i]);
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(empty_x + s);
+    // ---- y half
+    if (!mbar_wait_bounded(full_y + s, (unsigned)(round & 1), err)) return;
+    if (dbg != 1)
+    {
+      const cd* hy = sHy + inv.ohy; const cd* byp = sHy + inv.oby; const cd* v3 = sV + inv.ov3;
+#pragma unroll
+      for (int i = 0; i < R; i++)
+      {
+        cfma(acc[i], hy[i * NC], V1);
+        cfma_conj(backy, byp[i * NC], v3[i]);
+      }
+      cd back = cadd(backx, backy);
+      back = cmake(inv.sg * back.x, inv.sg * back.y);
+#pragma unroll
+      for (int off = NC * (SPLIT / 2); off >= NC; off >>= 1) back = cadd(back, shfl_xor_c(back, off));
+      // the thread whose row set holds row a = c2 adds the backward row sum (and the diagonal shift on that row) to it
+      if (a.use_diag) cfma(back, inv.dg, VC);
+#pragma unroll
+      for (int i = 0; i < R; i++) if (inv.back_row == i) acc[i] = cadd(acc[i], back);
+      const int c2 = tid % NC;
+      int left = R;
+#pragma unroll
+      for (int off = NC / 2; off > 0; off >>= 1)
+      {
+        if (left > 1)
+        {
+          const int hl = left / 2;
+          const bool upper = (c2 & off) != 0;
+#pragma unroll
+          for (int i = 0; i < R / 2; i++)
+            if (i < hl)
+            {
+              const cd send = upper ? acc[i] : acc[i + hl];
+              const cd keep = upper ? acc[i + hl] : acc[i];
+              acc[i] = cadd(keep, shfl_xor_c(send, off));
+            }
+          left = hl;
+        }
+        else acc[0] = cadd(acc[0], shfl_xor_c(acc[0], off));
+      }
+      if (inv.writer)
+      {
+        cd* op = a.out + origin * NC + inv.out_local;
+        cd res = acc[0];
+        if (acc_old) res = cadd(res, *op);
+        if (has_rb) res = csub(RBc, res);
+        *op = res;
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(empty_y + s);
+#pragma unroll
+    for (int i = 0; i < R; i++) CLc[i] = CLn[i];
+    RBc = RBn;
+    bx = bxn; by = byn;
   }
 }
 
 static int ring_debug() { static int v = -1; if (v < 0) { const char* e = getenv("QMG_RING_DEBUG"); v = e ? atoi(e) : 0; } return v; }
 
-template <int NC, int TK, int TY, int SPLIT, int NSTAGE, int NGROUP> static int launch_ring(const StencilKArgs& a)
+template <int NC, int TK, int TY, int SPLIT, int NSTAGE> static int launch_ring(const StencilKArgs& a)
 {
-  typedef RingCfg<NC, TK, TY, SPLIT, NSTAGE, NGROUP> CFG;
+  typedef RingCfg<NC, TK, TY, SPLIT, NSTAGE> CFG;
   static bool configured[64] = { false };
   const int dev = rt().device & 63;
   if (!configured[dev])
   {
-    QMG_CUDA(cudaFuncSetAttribute(stencil_ring_kernel<NC, TK, TY, SPLIT, NSTAGE, NGROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::SMEM));
+    QMG_CUDA(cudaFuncSetAttribute(stencil_ring_kernel<NC, TK, TY, SPLIT, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::SMEM));
     configured[dev] = true;
   }
   const int nbx = a.g.xh / TK, nby = a.y_cnt / TY;
@@ -779,23 +965,17 @@ template <int NC, int TK, int TY, int SPLIT, int NSTAGE, int NGROUP> static int 
   if (npatch > 0x7fffffffL) return fail_msg("qmg_stencil_apply: lattice too large for the ring kernel");
   int grid = rt().sm_count;
   if (grid > npatch) grid = (int)npatch;
-  stencil_ring_kernel<NC, TK, TY, SPLIT, NSTAGE, NGROUP><<<grid, CFG::NTHREADS, CFG::SMEM, rt().stream>>>(a, (int)npatch, nbx, rt().h_err, ring_debug());
+  stencil_ring_kernel<NC, TK, TY, SPLIT, NSTAGE><<<grid, CFG::NTHREADS, CFG::SMEM, rt().stream>>>(a, (int)npatch, nbx, rt().h_err, ring_debug());
   QMG_LAUNCH_CHECK();
   return 0;
 }
 
-// (A split-phase ring -- the x half and the y half of every patch with their own full / empty barriers, so that the producer
-// runs up to three half-stages ahead in the same shared memory -- was built and measured too: 2.51 ms against 2.42 ms for the
-// ring above on the same box (profiles/r03r_ring_kernel_variants.txt).  Deeper prefetch does not help: with the loads hidden,
-// the 16 consumer warps are the limit -- consumers alone 2.00 ms, four warps per scheduler on dependent LDS -> DFMA chains --
-// and 1024 threads per CTA with 85 KB per 32-site stage leave no room for more of them.)
-
-// nc = 8 patches (QMG_TILE / qmg_set_tile_kernel).  1 (default): the persistent ring kernel -- 32-site patches, two stages, one
-// consumer group of 512 threads + a producer warp -- wherever every SM gets at least 8 patches, else the one-patch cp.async
-// kernel; 3: always the cp.async kernel; 2: cp.async with one thread per column; 4: one-patch TMA kernel; 5 / 6: 16-site
-// one-patch kernels; 7 / 8, 10 / 11: ring kernels over 16-site patches (producer-bound: 34 resp. 20 bulk copies per 16 sites).
-// Measured on 2048^2 (profiles/r03r_ring_kernel_variants.txt): cp.async 2.54 ms, ring 2.29 ms; loads alone 1.92 ms, consumers
-// alone 2.00 ms; inside the 8192^2 K-cycle 6.09 -> 5.74 s.
+// nc = 8 patches (QMG_TILE / qmg_set_tile_kernel).  1 (default): the persistent ring kernel -- 32-site patches, two stages of
+// separately recycled x / y halves, 512 consumer threads + a producer warp -- wherever every SM gets at least 8 patches, else
+// the one-patch cp.async kernel; 9: always the ring; 3: always the cp.async kernel; 2: cp.async with one thread per column;
+// 4: one-patch TMA kernel; 5 / 6: 16-site one-patch kernels.  (Ring kernels over 16-site patches with 2 - 3 consumer groups,
+// modes 7 / 8 / 10 / 11 of an earlier build, were producer-bound -- 34 resp. 20 bulk copies per 16 sites -- and are gone;
+// their timings are in profiles/r03r_ring_kernel_variants.txt.)
 static int launch_tile8(const StencilKArgs& a)
 {
   const int mode = rt().tile_kernel;
@@ -803,12 +983,8 @@ static int launch_tile8(const StencilKArgs& a)
   if (mode == 4) return launch_tma<8, 4, 4, 2>(a);
   if (mode == 5) return launch_tile<8, 2, 4, 2>(a);
   if (mode == 6) return launch_tma<8, 2, 4, 2>(a);
-  if (mode == 7) return launch_ring<8, 2, 4, 2, 4, 2>(a);
-  if (mode == 8) return launch_ring<8, 2, 4, 2, 4, 3>(a);
-  if (mode == 10) return launch_ring<8, 4, 2, 2, 4, 2>(a);
-  if (mode == 11) return launch_ring<8, 4, 2, 2, 4, 3>(a);
   const long npatch = (long)(a.g.xh / 4) * (a.y_cnt / 4);
-  if (mode == 9 || (mode == 1 && npatch >= 8L * rt().sm_count)) return launch_ring<8, 4, 4, 2, 2, 1>(a);
+  if (mode == 9 || (mode == 1 && npatch >= 8L * rt().sm_count)) return launch_ring<8, 4, 4, 2, 2>(a);
   return launch_tile<8, 4, 4, 2>(a);
 }
 
