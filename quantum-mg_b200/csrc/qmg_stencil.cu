@@ -642,57 +642,6 @@ template <int NC, int TK, int TY, int SPLIT> struct TmaTile
   }
 };
 
-// The persistent ring kernel runs the patch arithmetic for patch after patch with the SAME thread -> (site, column, rows)
-// assignment, so everything that depends on the thread alone -- the element offsets of its nine operand streams inside a
-// stage, its signs, which of its rows receives the backward sum, where its output element sits relative to the patch origin --
-// is worked out ONCE (a third of the consumer's instructions were this index arithmetic: 289 IMAD against 92 DFMA in the
-// SASS) and a patch costs the loads, the products, the butterfly and one add for the global offset of its origin.  Needs the
-// parity of the first row of every patch to be the same (TY even, so y0 = y_off + by TY has the parity of y_off).
-template <int NC, int TK, int TY, int SPLIT> struct RingInv
-{
-  typedef TmaTile<NC, TK, TY, SPLIT> T;
-  static const int R = T::R, LPS = T::LPS, S = T::S, VK = T::VK;
-  int oVC, oV0, oV1, ov2, ov3;       // element offsets into the spinor region of the stage
-  int ohx, obx;                      // ... into its +x region
-  int ohy, oby;                      // ... into its +y region
-  int out_local, cl_local;           // output element / first clover element relative to the patch origin (units of elements)
-  int back_row;                      // index i of acc[] that receives the backward row sum on this thread, or -1
-  double sg;
-  bool writer;
-  cd dg;
-
-  __device__ __forceinline__ void init(const StencilKArgs& a, int tid, int y_parity)
-  {
-    static_assert((TY & 1) == 0, "RingInv: TY must be even");
-    const int c2 = tid % NC, hf = (tid / NC) % SPLIT;
-    const bool top = (2 * c2 < NC);
-    const int slot = tid / (NC * SPLIT);
-    const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; const int p = r / TK, tk = r - p * TK;
-    const int q = 1 - p, sft = (y_parity + ty + p) & 1;
-    const int nx = sft ? (ty * 2 + q) * TK + tk : (tk > 0 ? (ty * 2 + q) * TK + tk - 1 : S + ty);
-    const int ny = (ty > 0) ? ((ty - 1) * 2 + q) * TK + tk : S + q * TK + tk;
-    const int vbase = ((ty + 1) * 2) * VK * NC;        // row ty of the patch, parity 0, kk = 0
-    oVC = vbase + (p * VK + tk + 1) * NC + c2;
-    oV0 = vbase + (q * VK + tk + 1 + sft) * NC + c2;
-    oV1 = vbase + ((2 + q) * VK + tk + 1) * NC + c2;
-    ov2 = vbase + (q * VK + tk + sft) * NC + hf * R;
-    ov3 = vbase + (q * VK + tk + 1 - 2 * VK) * NC + hf * R;
-    ohx = slot * LPS + (hf * R) * NC + c2;
-    ohy = slot * LPS + (hf * R) * NC + c2;
-    obx = nx * LPS + (hf * R) * NC + c2;
-    oby = ny * LPS + (hf * R) * NC + c2;
-    sg = (top == (2 * hf * R < NC)) ? 1.0 : -1.0;
-    back_row = (c2 >= hf * R && c2 < hf * R + R) ? c2 - hf * R : -1;
-    writer = (SPLIT == 1 || (c2 % SPLIT) == 0);
-    const int row = hf * R + c2 / SPLIT;
-    // site = p half + (y0 + ty) xh + (k0 + tk): the patch origin contributes (y0 xh + k0), the rest is local
-    const long site_local = (long)p * a.g.half + (long)ty * a.g.xh + tk;
-    out_local = (int)(site_local * NC + row);
-    cl_local = (int)(site_local * LPS + (hf * R) * NC + c2);
-    dg = a.use_diag ? a.diag[p][top ? 0 : 1] : cmake(0.0, 0.0);
-  }
-};
-
 template <int NC, int TK, int TY, int SPLIT>
 __global__ void __launch_bounds__(TileDims<NC, TK, TY, SPLIT>::THREADS, (SPLIT > 1 ? 1024 / TileDims<NC, TK, TY, SPLIT>::THREADS : 1)) stencil_tma_kernel(const StencilKArgs a)
 {
@@ -740,20 +689,28 @@ template <int NC, int TK, int TY, int SPLIT = 1> static int launch_tma(const Ste
 // ---- persistent, warp-specialised flavour: one CTA per SM, a ring of NSTAGE patch buffers filled by a producer warp --------
 // Both one-patch-per-CTA kernels above wait for their tile with two CTAs per SM (registers and shared memory both stop at
 // two), and that wait is what bounds them.  Here ONE resident CTA walks over patches b, b + gridDim, ...: a producer warp
-// issues the bulk copies of patch j + NSTAGE - ... into the ring as soon as the buffer's previous tenant has been consumed
-// (empty barrier), NGROUP consumer groups of 16 x 16 threads each take every NGROUP-th patch as its full barrier completes,
-// and each consumer fetches its clover column for its NEXT patch into registers while it computes the current one.  Patches
-// are 4 rows x 4 sites (TK = 2): 46 KB per stage without the clover, so four stages fit.
+// issues the bulk copies of a patch into the ring as soon as the buffer's previous tenant has been consumed (empty barrier),
+// 512 consumer threads take patch after patch as its full barrier completes, and each consumer fetches what it reads straight
+// from global memory for its NEXT patch (clover column, residual element, halo blocks) while it computes the current one.
+//
+// The stage holds the forward blocks of the patch's sites, the left halo column (+x) and the halo row below (+y) that the
+// backward hops of its edge sites need, and the spinor tile cut down to the sites that are read (one ring site per row and
+// parity, none on the rows above and below): 85 KB, two stages.  (Three 75 KB stages -- the halo row below read from global
+// memory into registers one patch ahead by the threads that use it -- were built and measured: 2.81 ms against 2.30 ms,
+// profiles/r05_ring_three_stages.txt.  With 17 warps the SM sub-partition that hosts five of them caps a thread at 96
+// registers, and the clover column plus the halo rows cannot both be kept in flight a patch ahead inside that budget.)
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
 // bounded wait: false (and *err set) if the phase did not complete within ~2 s -- a broken pipeline must not hang the GPU
 __device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsigned parity, unsigned long long* err)
 {
   const unsigned addr = smem_u32(bar);
+  unsigned ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  if (ok) return true;
   const long long t0 = clock64();
   for (;;)
   {
-    unsigned ok;
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     if (ok) return true;
     if (clock64() - t0 > 4000000000LL) { st_sys_u64(err, 1000ull); return false; }      // reported by the next fetch / qmg_sync
@@ -762,37 +719,156 @@ __device__ __forceinline__ bool mbar_wait_bounded(unsigned long long* bar, unsig
 
 template <int NC, int TK, int TY, int SPLIT, int NSTAGE> struct RingCfg
 {
-  typedef TmaTile<NC, TK, TY, SPLIT> T;
-  static const int GT = TileDims<NC, TK, TY, SPLIT>::THREADS;      // consumer threads = one patch
+  typedef TileDims<NC, TK, TY, SPLIT> D;
+  static const int S = D::S, LPS = NC * NC, VK = TK + 1, R = NC / SPLIT;
+  static const int GT = D::THREADS;                                // consumer threads = one patch
   static const int NTHREADS = GT + 32;
-  static const int NVSLOT = 2 * NSTAGE;                            // spinor tiles ride in their own, longer ring (see the kernel)
-  static const size_t BX = sizeof(cd) * (size_t)T::NHX * T::LPS, BY = sizeof(cd) * (size_t)T::NHY * T::LPS, BV = (sizeof(cd) * (size_t)T::NV + 127) & ~(size_t)127;
-  static const size_t OFF_X = 256, OFF_Y = OFF_X + NSTAGE * BX, OFF_V = OFF_Y + NSTAGE * BY;
-  static const size_t SMEM = OFF_V + NVSLOT * BV;
+  // spinor tile: [row below: 2 parities x TK sites][rows of the patch: 2 parities x (TK + 1) sites][row above: 2 x TK]; a row
+  // of the patch holds sites k0 - 1 + sh .. k0 + TK - 1 + sh of its parity P, sh = (y + 1 - P) & 1: the sites themselves plus
+  // the ONE ring site that the other parity's +-x hops reach
+  static const int NV = (4 * TK + TY * 2 * VK) * NC;
+  static const size_t BHX = sizeof(cd) * (size_t)(S + TY) * LPS;   // +x blocks of the patch's sites, then the left halo column
+  static const size_t BHY = sizeof(cd) * (size_t)(S + 2 * TK) * LPS;      // +y blocks of the patch's sites, then the halo row below (parity 0, parity 1)
+  static const size_t BV = sizeof(cd) * (size_t)NV;
+  static const size_t STAGE = BHX + BHY + BV;
+  static_assert(STAGE % 128 == 0, "ring kernel: stage size");
+  static const unsigned TX_BYTES = (unsigned)STAGE;
+  static const size_t SMEM = 256 + NSTAGE * STAGE;
+  static const int NCOPY = 2 * TY + TY + 2 * TY + 2 + 2 * (TY + 2);
+
+  // Issued by the producer warp: lane l takes copies l, l + 32, ...  The TK blocks of one (row, parity) are contiguous in the
+  // reference's layout (4 KB at nc = 8, TK = 4); a spinor row with its ring site is contiguous except across the x wrap.
+  __device__ static __forceinline__ void stage(const StencilKArgs& a, unsigned char* buf, unsigned long long* bar, int k0, int y0, int lane)
+  {
+    cd* sHx = reinterpret_cast<cd*>(buf); cd* sHy = reinterpret_cast<cd*>(buf + BHX); cd* sV = reinterpret_cast<cd*>(buf + BHX + BHY);
+    const int xh = a.g.xh, Y = a.g.Y;
+    const size_t half = a.g.half;
+    for (int c = lane; c < NCOPY; c += 32)
+    {
+      int j = c;
+      if (j < 2 * TY)
+      {
+        const int ty = j >> 1, p = j & 1;
+        bulk_g2s(sHx + (size_t)(j * TK) * LPS, a.hop + ((size_t)p * half + (size_t)(y0 + ty) * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
+        continue;
+      }
+      j -= 2 * TY;
+      if (j < TY)
+      {
+        const int ty = j, p = 1 - ((y0 + ty) & 1), k = (k0 == 0) ? xh - 1 : k0 - 1;     // left neighbour of the row's first site that hops back inside its parity index
+        bulk_g2s(sHx + (size_t)(S + ty) * LPS, a.hop + ((size_t)p * half + (size_t)(y0 + ty) * xh + k) * LPS, LPS * sizeof(cd), bar);
+        continue;
+      }
+      j -= TY;
+      if (j < 2 * TY)
+      {
+        const int ty = j >> 1, p = j & 1;
+        bulk_g2s(sHy + (size_t)(j * TK) * LPS, a.hop + a.size_cm + ((size_t)p * half + (size_t)(y0 + ty) * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
+        continue;
+      }
+      j -= 2 * TY;
+      if (j < 2)
+      {
+        const int p = j, y = (y0 == 0) ? Y - 1 : y0 - 1;       // the row below the patch
+        bulk_g2s(sHy + (size_t)(S + p * TK) * LPS, a.hop + a.size_cm + ((size_t)p * half + (size_t)y * xh + k0) * LPS, TK * LPS * sizeof(cd), bar);
+        continue;
+      }
+      j -= 2;
+      {
+        const int ry = j >> 1, p = j & 1;        // ry = 0: the row below, 1 .. TY: the patch, TY + 1: the row above
+        int y = y0 + ry - 1; y = (y < 0) ? Y - 1 : ((y >= Y) ? 0 : y);
+        const cd* row = a.in + ((size_t)p * half + (size_t)y * xh) * NC;
+        if (ry == 0 || ry == TY + 1)
+        {
+          cd* dst = sV + (size_t)((ry == 0 ? 0 : 2 * TK + TY * 2 * VK) + p * TK) * NC;
+          bulk_g2s(dst, row + (size_t)k0 * NC, TK * NC * sizeof(cd), bar);
+        }
+        else
+        {
+          const int sh = (y0 + ry - 1 + 1 - p) & 1;
+          cd* dst = sV + (size_t)(2 * TK + ((ry - 1) * 2 + p) * VK) * NC;
+          const int ks = k0 - 1 + sh;            // first site of the run of TK + 1
+          if (ks < 0)
+          {
+            bulk_g2s(dst, row + (size_t)(xh - 1) * NC, NC * sizeof(cd), bar);
+            bulk_g2s(dst + NC, row, TK * NC * sizeof(cd), bar);
+          }
+          else if (ks + VK > xh)
+          {
+            bulk_g2s(dst, row + (size_t)ks * NC, TK * NC * sizeof(cd), bar);
+            bulk_g2s(dst + (size_t)TK * NC, row, NC * sizeof(cd), bar);
+          }
+          else bulk_g2s(dst, row + (size_t)ks * NC, VK * NC * sizeof(cd), bar);
+        }
+      }
+    }
+  }
 };
 
-// One consumer group of GT threads, one producer warp.  A stage is an X buffer (+x blocks) and a Y buffer (+y blocks) with their
-// own full / empty barriers; the spinor tile of patch j sits in slot j mod 2 NSTAGE of a third, small ring and completes on the X
-// barrier.  The consumers hand the X buffer back right after the x half of the arithmetic, so the producer refills it while
-// they are still on the y half and on the next patch: about one and a half stages are in flight instead of one, which is what
-// hides the DRAM latency at the head of a stage.  (A spinor slot is reused 2 NSTAGE patches later -- its previous tenant was
-// finished before the X buffer that gates the refill was even handed over.)
+// The consumers run the patch arithmetic for patch after patch with the SAME thread -> (site, column, rows) assignment, so
+// everything that depends on the thread alone -- the element offsets of its nine operand streams inside a stage, its signs,
+// which of its rows receives the backward sum, where its output element sits relative to the patch origin -- is worked out
+// ONCE (a third of the consumer's instructions were this index arithmetic: 289 IMAD against 92 DFMA in the SASS) and a patch
+// costs the loads, the products, the butterfly and one add for the global offset of its origin.  Needs the parity of the first
+// row of every patch to be the same (TY even, so y0 = y_off + by TY has the parity of y_off).
+template <int NC, int TK, int TY, int SPLIT> struct RingInv
+{
+  static const int R = NC / SPLIT, LPS = NC * NC, S = TileDims<NC, TK, TY, SPLIT>::S, VK = TK + 1;
+  int oVC, oV0, oV1, ov2, ov3;       // element offsets into the spinor tile of the stage
+  int ohf, obx, oby;                 // ... into its block regions: own forward blocks (same offset in +x and +y), backward neighbours
+  long out_local, cl_local;          // output element / first clover element relative to the patch origin (units of elements)
+  int back_row;                      // index i of acc[] that receives the backward row sum on this thread, or -1
+  bool neg;                          // the backward sum of this thread's rows enters with a minus sign (rows and column in different chiral halves)
+  bool writer;
+  int dgi;                           // which of the four diagonal shifts applies to this thread's column
+
+  __device__ __forceinline__ void init(const StencilKArgs& a, int tid, int y_parity)
+  {
+    static_assert((TY & 1) == 0, "RingInv: TY must be even");
+    const int c2 = tid % NC, hf = (tid / NC) % SPLIT;
+    const bool top = (2 * c2 < NC);
+    const int slot = tid / (NC * SPLIT);
+    const int ty = slot / (2 * TK); const int r = slot - ty * 2 * TK; const int p = r / TK, tk = r - p * TK;
+    const int q = 1 - p, sft = (y_parity + ty + p) & 1;
+    const int el = (hf * R) * NC + c2;                 // first element of this thread inside a block: [hf R + i][c2] at + i NC
+    const int nx = sft ? (ty * 2 + q) * TK + tk : (tk > 0 ? (ty * 2 + q) * TK + tk - 1 : S + ty);
+    const int ny = (ty > 0) ? ((ty - 1) * 2 + q) * TK + tk : S + q * TK + tk;
+    // spinor tile (see RingCfg): a row of the patch with parity P starts at site k0 - 1 + sh_P; sh_q = sft, sh_p = 1 - sft
+    const int rowp = (2 * TK + (ty * 2 + p) * VK) * NC, rowq = (2 * TK + (ty * 2 + q) * VK) * NC;
+    oVC = rowp + (tk + sft) * NC + c2;                 // in(x)
+    oV0 = rowq + (tk + 1) * NC + c2;                   // in(x + x^): site k0 + tk + sft of parity q
+    ov2 = rowq + tk * NC + hf * R;                     // in(x - x^): site k0 + tk - 1 + sft; rows of this thread, broadcast reads
+    oV1 = ((ty + 1 < TY) ? (2 * TK + ((ty + 1) * 2 + q) * VK + tk + sft) : (2 * TK + TY * 2 * VK + q * TK + tk)) * NC + c2;      // in(x + y^)
+    ov3 = ((ty > 0) ? (2 * TK + ((ty - 1) * 2 + q) * VK + tk + sft) : (q * TK + tk)) * NC + hf * R;                            // in(x - y^)
+    ohf = slot * LPS + el;
+    obx = nx * LPS + el;
+    oby = ny * LPS + el;
+    neg = (top != (2 * hf * R < NC));
+    back_row = (c2 >= hf * R && c2 < hf * R + R) ? c2 - hf * R : -1;
+    writer = (SPLIT == 1 || (c2 % SPLIT) == 0);
+    const int row = hf * R + c2 / SPLIT;
+    // site = p half + (y0 + ty) xh + (k0 + tk): the patch origin contributes (y0 xh + k0), the rest is local
+    const long site_local = (long)p * a.g.half + (long)ty * a.g.xh + tk;
+    out_local = site_local * NC + row;
+    cl_local = site_local * LPS + el;
+    dgi = p * 2 + (top ? 0 : 1);
+  }
+};
+
 template <int NC, int TK, int TY, int SPLIT, int NSTAGE>
 __global__ void __launch_bounds__(RingCfg<NC, TK, TY, SPLIT, NSTAGE>::NTHREADS, 1)
 stencil_ring_kernel(const StencilKArgs a, const int npatch, const int nbx, unsigned long long* err, const int dbg)
 {
   typedef RingCfg<NC, TK, TY, SPLIT, NSTAGE> CFG;
-  typedef TmaTile<NC, TK, TY, SPLIT> T;
   static_assert(TileDims<NC, TK, TY, SPLIT>::PASSES == 1, "ring kernel: one patch per pass of the consumer group");
+  static_assert(CFG::SMEM <= 232448, "ring kernel: stages do not fit in shared memory");
   extern __shared__ __align__(128) unsigned char ring_smem[];
-  unsigned long long* full_x = reinterpret_cast<unsigned long long*>(ring_smem);      // +x blocks and spinors have landed
-  unsigned long long* full_y = full_x + NSTAGE;                                       // +y blocks have landed
-  unsigned long long* empty_x = full_y + NSTAGE;
-  unsigned long long* empty_y = empty_x + NSTAGE;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring_smem);
+  unsigned long long* empty = full + NSTAGE;
   const int tid = threadIdx.x;
   if (tid == 0)
   {
-    for (int s = 0; s < NSTAGE; s++) { mbar_init(full_x + s, 1); mbar_init(full_y + s, 1); mbar_init(empty_x + s, CFG::GT / 32); mbar_init(empty_y + s, CFG::GT / 32); }
+    for (int s = 0; s < NSTAGE; s++) { mbar_init(full + s, 1); mbar_init(empty + s, CFG::GT / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -800,113 +876,96 @@ stencil_ring_kernel(const StencilKArgs a, const int npatch, const int nbx, unsig
   {
     // producer warp
     const int lane = tid - CFG::GT;
-    int j = 0;
-    for (int t = blockIdx.x; t < npatch; t += gridDim.x, j++)
+    int s = 0; unsigned ph = 1;          // waiting on a fresh barrier with parity 1 returns at once: the ring starts empty
+    for (int t = blockIdx.x; t < npatch; t += gridDim.x)
     {
-      const int s = j % NSTAGE, round = j / NSTAGE;
       const int by = t / nbx, bx = t - by * nbx;
-      const int k0 = bx * TK, y0 = a.y_off + by * TY;
-      if (!mbar_wait_bounded(empty_x + s, (unsigned)((round & 1) ^ 1), err)) return;
-      if (dbg == 2) { if (lane == 0) mbar_arrive(full_x + s); }      // timing experiment 2: no copies, the consumers compute on whatever is there
+      if (!mbar_wait_bounded(empty + s, ph, err)) return;
+      if (dbg == 2) { if (lane == 0) mbar_arrive(full + s); }      // timing experiment 2: no copies, the consumers compute on whatever is there
       else
       {
-        if (lane == 0) mbar_expect_tx(full_x + s, T::BYTES_X);
+        if (lane == 0) mbar_expect_tx(full + s, CFG::TX_BYTES);
         __syncwarp();
-        T::stage_x(a, reinterpret_cast<cd*>(ring_smem + CFG::OFF_X + (size_t)s * CFG::BX),
-                   reinterpret_cast<cd*>(ring_smem + CFG::OFF_V + (size_t)(j % CFG::NVSLOT) * CFG::BV), full_x + s, k0, y0, lane);
+        CFG::stage(a, ring_smem + 256 + (size_t)s * CFG::STAGE, full + s, bx * TK, a.y_off + by * TY, lane);
       }
-      if (!mbar_wait_bounded(empty_y + s, (unsigned)((round & 1) ^ 1), err)) return;
-      if (dbg == 2) { if (lane == 0) mbar_arrive(full_y + s); }
-      else
-      {
-        if (lane == 0) mbar_expect_tx(full_y + s, T::BYTES_Y);
-        __syncwarp();
-        T::stage_y(a, reinterpret_cast<cd*>(ring_smem + CFG::OFF_Y + (size_t)s * CFG::BY), full_y + s, k0, y0, lane);
-      }
+      if (++s == NSTAGE) { s = 0; ph ^= 1u; }
     }
     return;
   }
   // consumers
   RingInv<NC, TK, TY, SPLIT> inv;
   inv.init(a, tid, a.y_off & 1);
-  constexpr int R = T::R;
+  constexpr int R = CFG::R, LPS = CFG::LPS;
   const cd zero = cmake(0.0, 0.0);
   const bool has_cl = (a.clover != nullptr), has_rb = (a.resid != nullptr) && inv.writer, acc_old = (a.accumulate != 0) && inv.writer;
+  const int xh = a.g.xh;
   // this CTA's patch sequence without a division per patch: t advances by gridDim.x, (bx, by) by the matching (dx, dy)
   const int stride = (int)gridDim.x;
   const int dy = stride / nbx, dx = stride - dy * nbx;
-  int j = 0;
-  long t = blockIdx.x;
-  int by = (int)(t / nbx), bx = (int)(t - (long)by * nbx);
+  int t = blockIdx.x;
+  int by = t / nbx, bx = t - by * nbx;
   cd CLc[R], CLn[R];
   cd RBc = zero, RBn = zero;
 #pragma unroll
   for (int i = 0; i < R; i++) { CLc[i] = zero; CLn[i] = zero; }
-  if (t < npatch)
+  // the operands that come straight from global memory (clover column, residual element) travel in registers, one patch ahead
+  auto fetch = [&](int fbx, int fby, cd (&CL)[R], cd& RB)
   {
-    const long origin = (long)(a.y_off + by * TY) * a.g.xh + bx * TK;
-    if (has_cl) { const cd* cp = a.clover + origin * T::LPS + inv.cl_local;
+    const long origin = (long)(a.y_off + fby * TY) * xh + fbx * TK;
+    if (has_cl) { const cd* cp = a.clover + origin * LPS + inv.cl_local;
 #pragma unroll
-      for (int i = 0; i < R; i++) CLc[i] = ld_stream(cp + i * NC); }
-    if (has_rb) RBc = ld_stream(a.resid + origin * NC + inv.out_local);
-  }
-  for (; t < npatch; j++, t += stride)
+      for (int i = 0; i < R; i++) CL[i] = ld_stream(cp + i * NC); }
+    if (has_rb) RB = ld_stream(a.resid + origin * NC + inv.out_local);
+  };
+  if (t < npatch) fetch(bx, by, CLc, RBc);
+  int s = 0; unsigned ph = 0;
+  for (; t < npatch; t += stride)
   {
-    const int s = j % NSTAGE, round = j / NSTAGE;
-    const long origin = (long)(a.y_off + by * TY) * a.g.xh + bx * TK;
-    // next patch: its clover column (and residual element) travel in registers while this one is computed
-    int bxn = bx + dx, byn = by + dy;
-    if (bxn >= nbx) { bxn -= nbx; byn++; }
-    if (t + stride < npatch)
-    {
-      const long on = (long)(a.y_off + byn * TY) * a.g.xh + bxn * TK;
-      if (has_cl) { const cd* cp = a.clover + on * T::LPS + inv.cl_local;
-#pragma unroll
-        for (int i = 0; i < R; i++) CLn[i] = ld_stream(cp + i * NC); }
-      if (has_rb) RBn = ld_stream(a.resid + on * NC + inv.out_local);
-    }
-    const cd* sHx = reinterpret_cast<const cd*>(ring_smem + CFG::OFF_X + (size_t)s * CFG::BX);
-    const cd* sHy = reinterpret_cast<const cd*>(ring_smem + CFG::OFF_Y + (size_t)s * CFG::BY);
-    const cd* sV = reinterpret_cast<const cd*>(ring_smem + CFG::OFF_V + (size_t)(j % CFG::NVSLOT) * CFG::BV);
+    const long origin = (long)(a.y_off + by * TY) * xh + bx * TK;
+    bx += dx; by += dy;
+    if (bx >= nbx) { bx -= nbx; by++; }
+    if (t < npatch - stride) fetch(bx, by, CLn, RBn);
+    const unsigned char* buf = ring_smem + 256 + (size_t)s * CFG::STAGE;
+    const cd* sHx = reinterpret_cast<const cd*>(buf);
+    const cd* sHy = reinterpret_cast<const cd*>(buf + CFG::BHX);
+    const cd* sV = reinterpret_cast<const cd*>(buf + CFG::BHX + CFG::BHY);
     cd acc[R];
-    cd backx = zero, backy = zero;
+    cd backx = zero, backy = zero;      // two independent chains
 #pragma unroll
     for (int i = 0; i < R; i++) acc[i] = zero;
-    // ---- x half: spinors and +x blocks have landed -> clover and x terms; then the X buffer goes back to the producer
-    if (!mbar_wait_bounded(full_x + s, (unsigned)(round & 1), err)) return;
-    const cd VC = sV[inv.oVC], V0 = sV[inv.oV0], V1 = sV[inv.oV1];
+    if (!mbar_wait_bounded(full + s, ph, err)) return;
+    const cd VC = sV[inv.oVC];
     if (dbg != 1)      // (timing experiment 1: copies only, nothing computed)
     {
-      const cd* hx = sHx + inv.ohx; const cd* bxp = sHx + inv.obx; const cd* v2 = sV + inv.ov2;
+      const cd V0 = sV[inv.oV0], V1 = sV[inv.oV1];
+      const cd* hx = sHx + inv.ohf; const cd* hy = sHy + inv.ohf;
+      const cd* bxp = sHx + inv.obx; const cd* byp = sHy + inv.oby;
+      const cd* v2 = sV + inv.ov2; const cd* v3 = sV + inv.ov3;
 #pragma unroll
       for (int i = 0; i < R; i++)
       {
         cd tt = zero;
         cfma(tt, CLc[i], VC);
         cfma(tt, hx[i * NC], V0);
+        cfma(tt, hy[i * NC], V1);
         acc[i] = tt;
+        // s_a s_b conj(B[b][a]) in(x - mu)[b], b = hf R + i: the sign is applied once below
         cfma_conj(backx, bxp[i * NC], v2[i]);
-      }
-    }
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(empty_x + s);
-    // ---- y half
-    if (!mbar_wait_bounded(full_y + s, (unsigned)(round & 1), err)) return;
-    if (dbg != 1)
-    {
-      const cd* hy = sHy + inv.ohy; const cd* byp = sHy + inv.oby; const cd* v3 = sV + inv.ov3;
-#pragma unroll
-      for (int i = 0; i < R; i++)
-      {
-        cfma(acc[i], hy[i * NC], V1);
         cfma_conj(backy, byp[i * NC], v3[i]);
       }
+    }
+    // every operand of this patch is in registers: hand the stage back
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(empty + s);
+    if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+    if (dbg != 1)
+    {
       cd back = cadd(backx, backy);
-      back = cmake(inv.sg * back.x, inv.sg * back.y);
+      if (inv.neg) back = cmake(-back.x, -back.y);
 #pragma unroll
       for (int off = NC * (SPLIT / 2); off >= NC; off >>= 1) back = cadd(back, shfl_xor_c(back, off));
       // the thread whose row set holds row a = c2 adds the backward row sum (and the diagonal shift on that row) to it
-      if (a.use_diag) cfma(back, inv.dg, VC);
+      if (a.use_diag) cfma(back, (&a.diag[0][0])[inv.dgi], VC);
 #pragma unroll
       for (int i = 0; i < R; i++) if (inv.back_row == i) acc[i] = cadd(acc[i], back);
       const int c2 = tid % NC;
@@ -939,12 +998,9 @@ stencil_ring_kernel(const StencilKArgs a, const int npatch, const int nbx, unsig
         *op = res;
       }
     }
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(empty_y + s);
 #pragma unroll
     for (int i = 0; i < R; i++) CLc[i] = CLn[i];
     RBc = RBn;
-    bx = bxn; by = byn;
   }
 }
 
@@ -970,12 +1026,13 @@ template <int NC, int TK, int TY, int SPLIT, int NSTAGE> static int launch_ring(
   return 0;
 }
 
-// nc = 8 patches (QMG_TILE / qmg_set_tile_kernel).  1 (default): the persistent ring kernel -- 32-site patches, two stages of
-// separately recycled x / y halves, 512 consumer threads + a producer warp -- wherever every SM gets at least 8 patches, else
-// the one-patch cp.async kernel; 9: always the ring; 3: always the cp.async kernel; 2: cp.async with one thread per column;
-// 4: one-patch TMA kernel; 5 / 6: 16-site one-patch kernels.  (Ring kernels over 16-site patches with 2 - 3 consumer groups,
-// modes 7 / 8 / 10 / 11 of an earlier build, were producer-bound -- 34 resp. 20 bulk copies per 16 sites -- and are gone;
-// their timings are in profiles/r03r_ring_kernel_variants.txt.)
+// nc = 8 patches (QMG_TILE / qmg_set_tile_kernel).  1 (default): the persistent ring kernel -- 32-site patches, two stages,
+// 512 loop-invariant consumer threads + a producer warp -- wherever every SM
+// gets at least 8 patches, else the one-patch cp.async kernel; 9: always the ring; 3: always the cp.async kernel; 2: cp.async
+// with one thread per column; 4: one-patch TMA kernel; 5 / 6: 16-site one-patch kernels.  (Ring kernels over 16-site patches
+// with 2 - 3 consumer groups, modes 7 / 8 / 10 / 11 of an earlier build, were producer-bound -- 34 resp. 20 bulk copies per
+// 16 sites -- and are gone, as is a ring whose x and y halves were recycled separately: the wait between the halves cost the
+// consumers their instruction-level parallelism.  Timings: profiles/r03r_ring_kernel_variants.txt, r05_ring_three_stages.txt.)
 static int launch_tile8(const StencilKArgs& a)
 {
   const int mode = rt().tile_kernel;

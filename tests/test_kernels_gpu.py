@@ -502,9 +502,9 @@ def _herm_stencil(L, nc, seed):
 def test_tile_kernel_flavours_agree(qmg_gpu, L):
     """nc = 8 link-compressed apply: streaming (0), cp.async patch kernel with two / one thread per column (1, 2) and the
     TMA-staged patch kernel (4: cp.async.bulk + mbarrier), the 16-site patch experiments (5, 6) and the persistent
-    warp-specialised ring kernel (9: producer warp + mbarrier ring of separately recycled x / y halves) against the stored-block apply
+    warp-specialised ring kernel (9: producer warp + mbarrier ring, loop-invariant consumers) against the stored-block apply
     -- plain, accumulating and with the residual epilogue; L = 16 makes every patch touch the periodic wrap in x, L = 128 makes
-    every CTA of the ring kernels go round its 4-stage ring."""
+    every CTA of the ring kernel go round its ring."""
     import ctypes as C
     qmg = qmg_gpu
     lib = qmg.lib()

@@ -9,6 +9,8 @@ for p in (ROOT, os.path.join(ROOT, "quantum-mg_b200"), os.path.join(ROOT, "tests
 import torch  # noqa: E402
 import qmg  # noqa: E402
 
+if os.environ.get("QMG_LIB_OVERRIDE"):      # A / B timing against an older build of the kernel library
+    qmg.LIB_PATH = os.environ["QMG_LIB_OVERRIDE"]
 qmg.init(0)
 lib = qmg.lib()
 
