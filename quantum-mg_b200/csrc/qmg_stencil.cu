@@ -698,7 +698,9 @@ template <int NC, int TK, int TY, int SPLIT = 1> static int launch_tma(const Ste
 // parity, none on the rows above and below): 85 KB, two stages.  (Three 75 KB stages -- the halo row below read from global
 // memory into registers one patch ahead by the threads that use it -- were built and measured: 2.81 ms against 2.30 ms,
 // profiles/r05_ring_three_stages.txt.  With 17 warps the SM sub-partition that hosts five of them caps a thread at 96
-// registers, and the clover column plus the halo rows cannot both be kept in flight a patch ahead inside that budget.)
+// registers, and the clover column plus the halo rows cannot both be kept in flight a patch ahead inside that budget.
+// L2 prefetches by the producer for the patch after the ones in the ring -- cp.async.bulk.prefetch.L2 per 4 KB run or
+// prefetch.global.L2 per line, one to three patches ahead -- make it slower, 2.37 -> 2.83 - 2.95 ms, copies alone 1.9 -> 2.5.)
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
 // bounded wait: false (and *err set) if the phase did not complete within ~2 s -- a broken pipeline must not hang the GPU
