@@ -37,5 +37,19 @@ for nc, L in ((8, 2048), (8, 512)) if not os.environ.get('TILE_PROBE_SMALL') els
         e1.record()
         torch.cuda.synchronize()
         print("QMG_TILE=%s nc=%d %dx%d herm=%d: %.4f ms" % (os.environ.get("QMG_TILE", "1"), nc, L, L, herm, e0.elapsed_time(e1) / 20), flush=True)
+        if os.environ.get("TILE_PROBE_ISOLATED"):
+            # one launch at a time with the GPU idle in between (what ncu times) against the burst above (what a solver sees)
+            import time
+            ts = []
+            for _ in range(8):
+                time.sleep(0.05)
+                e0.record(); qmg.stencil_apply(d, y, x); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            print("   isolated launches (50 ms idle before each): " + " ".join("%.4f" % v for v in ts), flush=True)
+            e0.record()
+            for _ in range(400):
+                qmg.stencil_apply(d, y, x)
+            e1.record(); torch.cuda.synchronize()
+            print("   burst of 400: %.4f ms per apply" % (e0.elapsed_time(e1) / 400), flush=True)
     del cl, hp, x, y
     torch.cuda.empty_cache()
