@@ -373,6 +373,36 @@ def run_gpu(args):
     else:
         pcie["numa_node_of_gpu"] = numa
     pcie["pinned_staging"] = "allocated and first touched on the GPU's NUMA node (qmg_malloc_host)"
+    # ... and with both directions busy at once, which is what the pipelined host-vector apply asks of the link: the time of
+    # one upload and one download of the same buffers issued together bounds an e2e step from below (context, not part of e2e)
+    try:
+        import numpy as np
+        h_in = torch.from_numpy(np.ctypeslib.as_array(C.cast(hin, C.POINTER(C.c_double)), shape=(2 * n,)))
+        h_out = torch.from_numpy(np.ctypeslib.as_array(C.cast(hout, C.POINTER(C.c_double)), shape=(2 * n,)))
+        d_in, d_out = torch.view_as_real(rhs).view(-1), torch.view_as_real(lhs).view(-1)
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        both = []
+        for _ in range(3):
+            barrier()
+            tb0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s_down):
+                h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            both.append(time.perf_counter() - tb0)
+        tb = min(both[1:])
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([tb], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tb = float(t.item())
+        pcie["both_directions_at_once"] = {"seconds": tb, "GBps_each_way": 16 * n / tb / 1e9, "pinned": bool(h_in.is_pinned()),
+                                           "e2e_bound_GBps": BYTES_PER_SITE * V * world / tb / 1e9,
+                                           "note": "an e2e step cannot be shorter than this; e2e.value / e2e_bound_GBps is the pipeline's efficiency"}
+        del h_in, h_out, d_in, d_out
+    except Exception as exc:      # context only: never fail the bench over it
+        pcie["both_directions_at_once"] = {"error": repr(exc)[:200]}
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

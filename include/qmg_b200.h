@@ -262,6 +262,21 @@ int qmg_gcr_orthogonalize(const qmg_cplx* const* Ap_host, const qmg_cplx* const*
 int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y, long n);
 /* y = x0 + sum_j a_j xs[j]   (GCR: p_k = r + sum beta_i p_i without a separate copy); x0 == y allowed */
 int qmg_multi_axpyz(const double* a_host, const qmg_cplx* const* xs_host, int k, const qmg_cplx* x0, qmg_cplx* y, long n);
+/* BiCGstab(L) sweeps (quantum-linalg minv_vector_bicgstab_l as the K-cycle set-up calls it,
+ * /root/reference/tests/n13_wilson_kcycle/wilson_kcycle.cpp:359) with the BLAS-1 traffic of a sweep cut from 280 to 148 vector
+ * passes; every element sees the floating-point operations of the call-by-call sequence in the same order.  L <= qmg_bicgstab_max_l().
+ * replay: the updates of the LOWER vectors of the BiCG part (u_i = r_i - beta_j u_i, r_i -= alpha_j u_{i+1}, i < j; x += alpha_j u_0)
+ *   for all L steps in one pass, after the solver did the top ones (i = j) step by step.  r_host / u_host: HOST arrays of L device
+ *   pointers r_0..r_{L-1}, u_0..u_{L-1}; alpha_host / beta_host: 2 L doubles.
+ * mgs: modified Gram-Schmidt of r_1..r_L in place (right-looking order, coefficients formed on the device, no host wait between
+ *   the L passes); sums_host: L rows of 2 L + 2 doubles, row i-1 = { |r_i|^2, <r_i|r_0>, <r_i|r_{i+1}>, ..., <r_i|r_L> } (complex as re, im).
+ * finish: x += sum_{j<L} cx_j r_j ; r_0 += sum_{j=1..L} cr_j r_j ; result = |r_0|^2 -- one pass over r_0..r_L (r_host: L + 1 pointers). */
+int qmg_bicgstab_max_l(void);
+int qmg_set_bicgstab_fused(int on);   /* 0: the call-by-call sequence (default 1; QMG_BICGSTAB_FUSED=0 at qmg_init) */
+int qmg_get_bicgstab_fused(void);
+int qmg_bicgstab_replay(int L, qmg_cplx* const* r_host, qmg_cplx* const* u_host, qmg_cplx* x, const double* alpha_host, const double* beta_host, long n);
+int qmg_bicgstab_mgs(int L, qmg_cplx* const* r_host, long n, double* sums_host);
+int qmg_bicgstab_finish(int L, qmg_cplx* const* r_host, qmg_cplx* x, const double* cx_host, const double* cr_host, long n, double* result);
 /* gaussian fill, counter-based (Philox) so results do not depend on the launch shape; when sharded the counter is the
  * GLOBAL element index of an even-odd field (the ranks together draw what one GPU draws for the whole lattice) */
 int qmg_gaussian(qmg_cplx* x, long n, uint64_t seed, uint64_t stream_id, double dev);

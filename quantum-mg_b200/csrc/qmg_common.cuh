@@ -28,6 +28,7 @@ struct Runtime
   unsigned long long* h_err = nullptr;    // pinned, mapped: non-zero once a kernel gave up waiting for a peer (1 + the peer's rank; +256 for a halo row)
   unsigned long long red_seq = 0;   // host mirror of that number (reductions launched)
   int publish = 1;                  // 1: results arrive through h_result / h_flag; 0 (QMG_PUBLISH=0): copy + stream synchronise
+  int bicgstab_fused = 1;           // BiCGstab(L) sweeps through the fused kernels (QMG_BICGSTAB_FUSED=0: call by call)
   int tile_kernel = 1;              // gamma5-hermitian applies use the shared-memory tile kernel (QMG_TILE=0: streaming HERM kernel)
   int publish_now = 1;              // publish, and the kernels hold the final (all-reduced) values themselves
   void** d_ptrs = nullptr;          // small device table for pointer arrays (multi-dot etc.)

@@ -223,6 +223,7 @@ int qmg_init(int device)
   if (env != nullptr && env[0] == '1') r.managed = 1;
   env = getenv("QMG_TILE");
   r.tile_kernel = (env != nullptr && env[0] >= '0' && env[0] <= '9') ? atoi(env) : 1;
+  { const char* eb = getenv("QMG_BICGSTAB_FUSED"); r.bicgstab_fused = (eb != nullptr && eb[0] == '0') ? 0 : 1; }
   env = getenv("QMG_PROFILE");
   if (env != nullptr && env[0] == '1') r.profile = 1;
   r.ready = true;
@@ -324,6 +325,8 @@ int qmg_zero_bytes(void* dptr, size_t bytes)
 }
 int qmg_set_tile_kernel(int mode) { QMG_REQUIRE_INIT(); if (mode < 0 || mode > 15) return fail_msg("qmg_set_tile_kernel: mode must be 0 .. 15"); rt().tile_kernel = mode; return 0; }
 int qmg_get_tile_kernel(void) { return rt().tile_kernel; }
+int qmg_set_bicgstab_fused(int on) { QMG_REQUIRE_INIT(); rt().bicgstab_fused = on ? 1 : 0; return 0; }
+int qmg_get_bicgstab_fused(void) { return rt().bicgstab_fused; }
 int qmg_profile_enable(int on) { rt().profile = on ? 1 : 0; return 0; }
 int qmg_profile_reset(void) { prof_table().clear(); return 0; }
 // prints "name calls seconds" rows sorted by time to stdout and returns the total seconds

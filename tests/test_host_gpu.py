@@ -170,6 +170,37 @@ def test_solvers_iteration_parity(ref, gpu, solver, kind, type, kw):
     assert abs(np.sqrt(ig["resSq"]) - np.sqrt(ir["resSq"])) <= 1e-3 * np.sqrt(ir["resSq"]) + 1e-14
 
 
+@pytest.mark.parametrize("Lb", [1, 2, 4, 6, 7, 8])
+def test_bicgstab_l_fused_sweep_matches_call_by_call(gpu, Lb):
+    """BiCGstab(L) through the fused kernels (qmg_bicgstab_replay / _mgs / _finish: 148 instead of 280 vector passes per L = 6
+    sweep) against the call-by-call sequence of the same solver: same iteration and operator counts, solutions equal to
+    rounding (the replay and finish passes repeat the element arithmetic exactly; the Gram-Schmidt sums are added in another
+    order).  L = 8 exceeds qmg_bicgstab_max_l() and must take the call-by-call path on its own."""
+    import ctypes as C
+    import qmg
+    lib = qmg.lib()
+    L = 32
+    g = latutil.load_gauge(L)
+    b_src = latutil.gaussian_cv(L * L * 2, 31)
+    x0 = latutil.gaussian_cv(b_src.size, 5)
+    out = {}
+    was = lib.qmg_get_bicgstab_fused()
+    try:
+        for fused in (1, 0):
+            qmg.check(lib.qmg_set_bicgstab_fused(C.c_int(fused)))
+            op = gpu.lattice(L, L, 2).wilson(0.05, g)
+            out[fused] = op.solve(5, b_src, type=0, x0=x0, tol=5e-7, iparam=Lb, max_iter=600)
+            op.free()
+    finally:
+        qmg.check(lib.qmg_set_bicgstab_fused(C.c_int(was)))
+    (xf, inf_f), (xc, inf_c) = out[1], out[0]
+    assert inf_f["success"] and inf_c["success"]
+    assert inf_f["iter"] == inf_c["iter"] and inf_f["ops"] == inf_c["ops"], (inf_f, inf_c)
+    assert latutil.rel_l2(xf, xc) < 1e-9
+    if Lb > lib.qmg_bicgstab_max_l():
+        assert np.array_equal(xf, xc)
+
+
 TRANSFER_CASES = [(16, 16, 2, 4, 4, 8), (8, 8, 8, 2, 2, 8), (8, 8, 1, 4, 4, 2), (4, 4, 2, 1, 1, 6)]
 
 
