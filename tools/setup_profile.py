@@ -15,6 +15,8 @@ import qmg  # noqa: E402
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 qmg.init(0)
 be = capi.Backend("gpu")
+if os.environ.get("SETUP_LINK_COMPRESSED", "1") != "0":      # as bench.py builds its hierarchies
+    be.fn("kcycle_setup_link_compressed")(1)
 g = latutil.synthetic_gauge(L, L, 6.0, 1337, slab=True)
 kc = capi.KCycle(be, L, -0.05, g, n_refine=2, inner_iters=100, coarsest_iters=400)      # warm allocator
 print("warm set-up seconds", kc.solve(max_iter=1)["setup_seconds"], flush=True)
