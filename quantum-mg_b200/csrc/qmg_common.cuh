@@ -100,7 +100,9 @@ typedef double2 cd;
 __host__ __device__ __forceinline__ cd cmake(double r, double i) { cd z; z.x = r; z.y = i; return z; }
 __device__ __forceinline__ cd cadd(cd a, cd b) { return cmake(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cd csub(cd a, cd b) { return cmake(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ cd cmul(cd a, cd b) { return cmake(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a*b with its roundings spelt out (one product rounded, the other fused -- what nvcc's contraction made of the plain expression),
+// so that every kernel that multiplies the same numbers gets the same bits whatever surrounds the call
+__device__ __forceinline__ cd cmul(cd a, cd b) { return cmake(fma(a.x, b.x, -__dmul_rn(a.y, b.y)), fma(a.y, b.x, __dmul_rn(a.x, b.y))); }
 __device__ __forceinline__ cd cconj(cd a) { return cmake(a.x, -a.y); }
 // acc += a*b
 __device__ __forceinline__ void cfma(cd& acc, cd a, cd b)

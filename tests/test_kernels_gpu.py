@@ -364,6 +364,90 @@ def test_fused_krylov_step(qmg_gpu):
             assert out[0] == want[2] and (out[1], out[2], out[3]) == want[3], (n, alias)
 
 
+@pytest.mark.parametrize("L", [1, 2, 3, 6, 7])
+def test_bicgstab_fused_kernels(qmg_gpu, L):
+    """The three kernels behind the fused BiCGstab(L) sweep against the BLAS calls they replace.
+    qmg_bicgstab_replay: the lower-vector updates of the L BiCG steps (u_i = r_i - beta_j u_i, r_i -= alpha_j u_{i+1}, i < j,
+    x += alpha_j u_0) == the same updates issued step by step with qmg_caxpby / qmg_caxpy, BIT FOR BIT;
+    qmg_bicgstab_finish: x, r_0 == two qmg_multi_axpy calls bit for bit, |r_0|^2 to rounding;
+    qmg_bicgstab_mgs: the right-looking Gram-Schmidt == the left-looking loop of dot / caxpy / dot_norm calls to rounding."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    lib.qmg_bicgstab_max_l.restype = C.c_int
+    assert lib.qmg_bicgstab_max_l() >= 7
+    PP = C.c_void_p * (L + 1)
+
+    def ptrs(vs):
+        return PP(*[qmg.ptr(v) for v in vs])
+
+    def coef(cs):
+        return (C.c_double * (2 * len(cs)))(*[t for c in cs for t in (c.real, c.imag)])
+
+    for n in (7, 100003):
+        rng = np.random.default_rng(17 * L + n)
+        r0 = [latutil.gaussian_cv(n, 10 + i) for i in range(L + 1)]
+        u0 = [latutil.gaussian_cv(n, 40 + i) for i in range(L + 1)]
+        x0 = latutil.gaussian_cv(n, 99)
+        al = [complex(a, b) for a, b in rng.normal(size=(L, 2))]
+        be = [complex(a, b) for a, b in rng.normal(size=(L, 2))]
+        # ---- replay.  Step by step: only the lower vectors (i < j) move here -- the solver has done the top ones itself
+        r, u, x = [dev(qmg, v) for v in r0], [dev(qmg, v) for v in u0], dev(qmg, x0)
+        for j in range(L):
+            for i in range(j):
+                qmg.check(lib.qmg_caxpby(C.c_double(1.0), C.c_double(0.0), qmg.ptr(r[i]), C.c_double(-be[j].real), C.c_double(-be[j].imag), qmg.ptr(u[i]), C.c_long(n)))
+            for i in range(j):
+                qmg.check(lib.qmg_caxpy(C.c_double(-al[j].real), C.c_double(-al[j].imag), qmg.ptr(u[i + 1]), qmg.ptr(r[i]), C.c_long(n)))
+            qmg.check(lib.qmg_caxpy(C.c_double(al[j].real), C.c_double(al[j].imag), qmg.ptr(u[0]), qmg.ptr(x), C.c_long(n)))
+        want = [host(v) for v in r] + [host(v) for v in u] + [host(x)]
+        r, u, x = [dev(qmg, v) for v in r0], [dev(qmg, v) for v in u0], dev(qmg, x0)
+        qmg.check(lib.qmg_bicgstab_replay(C.c_int(L), ptrs(r), ptrs(u), qmg.ptr(x), coef(al), coef(be), C.c_long(n)))
+        got = [host(v) for v in r] + [host(v) for v in u] + [host(x)]
+        for k, (a, b) in enumerate(zip(got, want)):
+            assert np.array_equal(a, b), (L, n, k)
+        # ---- finish
+        cx = [complex(a, b) for a, b in rng.normal(size=(L, 2))]
+        cr = [complex(a, b) for a, b in rng.normal(size=(L, 2))]
+        r, x = [dev(qmg, v) for v in r0], dev(qmg, x0)
+        PL = C.c_void_p * L
+        qmg.check(lib.qmg_multi_axpy(coef(cx), PL(*[qmg.ptr(v) for v in r[:L]]), C.c_int(L), qmg.ptr(x), C.c_long(n)))
+        qmg.check(lib.qmg_multi_axpy(coef(cr), PL(*[qmg.ptr(v) for v in r[1:]]), C.c_int(L), qmg.ptr(r[0]), C.c_long(n)))
+        wn = C.c_double()
+        qmg.check(lib.qmg_norm2sq(qmg.ptr(r[0]), C.c_long(n), C.byref(wn)))
+        wx, wr = host(x), host(r[0])
+        r, x = [dev(qmg, v) for v in r0], dev(qmg, x0)
+        gn = C.c_double()
+        qmg.check(lib.qmg_bicgstab_finish(C.c_int(L), ptrs(r), qmg.ptr(x), coef(cx), coef(cr), C.c_long(n), C.byref(gn)))
+        assert np.array_equal(host(x), wx) and np.array_equal(host(r[0]), wr), (L, n)
+        assert abs(gn.value - wn.value) <= 1e-13 * wn.value
+        # ---- Gram-Schmidt: left-looking loop of the call-by-call solver
+        r = [dev(qmg, v) for v in r0]
+        sigma, gp, tau = {}, {}, {}
+        d2, d3 = (C.c_double * 2)(), (C.c_double * 3)()
+        for j in range(1, L + 1):
+            for i in range(1, j):
+                qmg.check(lib.qmg_dot(qmg.ptr(r[i]), qmg.ptr(r[j]), C.c_long(n), d2))
+                tau[(i, j)] = complex(d2[0], d2[1]) / sigma[i]
+                qmg.check(lib.qmg_caxpy(C.c_double(-tau[(i, j)].real), C.c_double(-tau[(i, j)].imag), qmg.ptr(r[i]), qmg.ptr(r[j]), C.c_long(n)))
+            qmg.check(lib.qmg_dot_norm(qmg.ptr(r[j]), qmg.ptr(r[0]), C.c_long(n), d3))
+            sigma[j] = d3[2]
+            gp[j] = complex(d3[0], d3[1]) / sigma[j]
+        want = [host(v) for v in r]
+        r = [dev(qmg, v) for v in r0]
+        stride = 2 * lib.qmg_bicgstab_max_l() + 2
+        sums = (C.c_double * (L * stride))()
+        qmg.check(lib.qmg_bicgstab_mgs(C.c_int(L), ptrs(r), C.c_long(n), sums))
+        for j in range(L + 1):
+            assert latutil.rel_l2(host(r[j]), want[j]) < 1e-12, (L, n, j)
+        for j in range(1, L + 1):
+            row = sums[(j - 1) * stride:j * stride]
+            assert abs(row[0] - sigma[j]) <= 1e-12 * sigma[j]
+            assert abs(complex(row[1], row[2]) / row[0] - gp[j]) <= 1e-11 * (1 + abs(gp[j]))
+            for m in range(j + 1, L + 1):
+                t = complex(row[3 + 2 * (m - j - 1)], row[4 + 2 * (m - j - 1)]) / row[0]
+                assert abs(t - tau[(j, m)]) <= 1e-11 * (1 + abs(tau[(j, m)])), (L, n, j, m)
+
+
 def test_krylov_step_flavours(qmg_gpu):
     """qmg_krylov_step: without flags bit-identical to qmg_step_xr_norm; the zero-start first step (x_in NULL, r_in = b != r_out,
     |b|^2 on the side), the x-only last step and the accumulate-into flavour reproduce the separate sweeps bit for bit."""
