@@ -1055,9 +1055,10 @@ static int launch_tile8(const StencilKArgs& a)
 // stored-block kernel already runs at 54 % issue utilisation.  At nc = 2 the stored blocks are the fast path; the K-cycle legs
 // of bench.py switch only the nc = 8 levels to link-compressed applies.)
 
-// Any nc (DWF Ls = 6, 12, 24, 32 give nc = 12, 24, 48, 64): one thread per
-// (site, row), looping over the columns.  Slow path, same arithmetic.
-__global__ void __launch_bounds__(256) stencil_kernel_generic(const StencilKArgs a, int nc, int n_par)
+// Any nc below 16 (DWF Ls = 6 gives nc = 12; odd dof counts): one thread per (site, row), looping over the columns; the rows of a
+// site are short enough for L1 to catch the sectors a warp's strided requests share (nc = 12 on 1024^2: 0.78 of the copy peak, the
+// lane-group kernel below 0.72 - 0.75).
+__global__ void __launch_bounds__(256) stencil_kernel_rows(const StencilKArgs a, int nc, int n_par)
 {
   const long sub_half = (long)a.y_cnt * a.g.xh;     // sites per parity in this launch's row set
   const long rows = (long)n_par * sub_half * nc;
@@ -1094,6 +1095,78 @@ __global__ void __launch_bounds__(256) stencil_kernel_generic(const StencilKArgs
     if (a.accumulate) acc = cadd(acc, a.out[idx]);
     if (a.resid != nullptr) acc = csub(a.resid[idx], acc);
     a.out[idx] = acc;
+  }
+}
+
+// Any nc from 16 up (DWF Ls = 12, 24, 32 give nc = 24, 48, 64): G = 8 lanes per (site, row), lane g taking the columns g, g + G, ...
+// of the row -- consecutive lanes read consecutive matrix and spinor elements, so a warp request covers 32 / G runs of G x 16
+// contiguous bytes (whole sectors) instead of 32 single elements one matrix row apart -- and a log2(G)-step shuffle tree
+// finishing the row sum; the five blocks of a row keep their own accumulators (10 loads in flight per step).  nc = 24 / 48:
+// 0.62 -> 0.77 / 0.83 of the copy peak (profiles/r05p_kernel_probe_any_nc.txt).  (The first version ran one thread per row over all its columns.)
+template <int G>
+__global__ void __launch_bounds__(256, 2) stencil_kernel_generic(const StencilKArgs a, int nc, int n_par)
+{
+  const long sub_half = (long)a.y_cnt * a.g.xh;     // sites per parity in this launch's row set
+  const long rows = (long)n_par * sub_half * nc;
+  const int g = threadIdx.x % G;
+  // a warp stays together (the row sums are finished with full-warp shuffles): lane groups beyond the last row recompute it and do not store
+  for (long t0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) / G; ; t0 += ((long)gridDim.x * blockDim.x) / G)
+  {
+    const bool active = t0 < rows;
+    if (!__any_sync(0xffffffffu, active)) break;
+    const long t = active ? t0 : rows - 1;
+    const int c1 = (int)(t % nc);
+    const long s = t / nc;
+    const int p = a.p_begin + (int)(s / sub_half);
+    const long hs = s % sub_half;
+    const int y = a.y_off + (int)(hs / a.g.xh) * a.y_stride, k = (int)(hs % a.g.xh);
+    const unsigned h = (unsigned)y * a.g.xh + k;
+    const size_t site = (size_t)p * a.g.half + h;
+    const int q = 1 - p;
+    const size_t lps = (size_t)nc * nc;
+    // the five operand streams of the row (matrix row, spinor) with their own accumulators: 10 loads in flight per column step
+    const cd* mp[5]; const cd* vp[5]; bool on[5];
+    on[4] = (a.clover != nullptr);
+    mp[4] = on[4] ? a.clover + site * lps + (size_t)c1 * nc : a.in;
+    vp[4] = a.in + site * nc;
+    const bool hop = (a.hop != nullptr) && a.hop_to[p];
+    const cd* in_q = a.in + (size_t)q * a.g.half * nc;
+#pragma unroll
+    for (int mu = 0; mu < 4; mu++)
+    {
+      on[mu] = hop && ((a.dir_mask >> mu) & 1);
+      const cd* src;
+      if (mu == 1 && a.halo_yp != nullptr && y == a.g.Y - 1) src = a.halo_yp + ((size_t)q * a.g.xh + k) * nc;
+      else if (mu == 3 && a.halo_ym != nullptr && y == 0) src = a.halo_ym + ((size_t)q * a.g.xh + k) * nc;
+      else src = in_q + (size_t)nbr_h(a.g, p, y, k, mu) * nc;
+      vp[mu] = src;
+      mp[mu] = on[mu] ? a.hop + (size_t)mu * a.size_cm + site * lps + (size_t)c1 * nc : a.in;
+    }
+    cd part[5];
+#pragma unroll
+    for (int b = 0; b < 5; b++) part[b] = cmake(0.0, 0.0);
+    for (int c2 = g; c2 < nc; c2 += G)
+    {
+      cd mm[5], vv[5];
+#pragma unroll
+      for (int b = 0; b < 5; b++) if (on[b]) { mm[b] = ld_stream(mp[b] + c2); vv[b] = vp[b][c2]; }
+#pragma unroll
+      for (int b = 0; b < 5; b++) if (on[b]) cfma(part[b], mm[b], vv[b]);
+    }
+    // clover first, then +x, +y, -x, -y: the order of the one-thread-per-row loop
+    cd acc = part[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc = cadd(acc, part[b]);
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc = cadd(acc, shfl_xor_c(acc, o));
+    if (g == 0 && active)
+    {
+      if (a.use_diag) cfma(acc, a.diag[p][(2 * c1 >= nc && nc > 1) ? 1 : 0], a.in[site * nc + c1]);
+      const size_t idx = site * nc + c1;
+      if (a.accumulate) acc = cadd(acc, a.out[idx]);
+      if (a.resid != nullptr) acc = csub(a.resid[idx], acc);
+      a.out[idx] = acc;
+    }
   }
 }
 
@@ -1203,8 +1276,16 @@ static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduc
   if (a.herm) return fail_msg("qmg_stencil_apply: the gamma5-hermitian apply needs nc in {2,4,8,16,32}");
   Runtime& r = rt();
   const long rows = (long)n_par * a.y_cnt * a.g.xh * nc;
-  long blocks = (rows + 255) / 256, cap = (long)r.sm_count * 8;
-  stencil_kernel_generic<<<(int)(blocks < cap ? blocks : cap), 256, 0, r.stream>>>(a, nc, n_par);
+  if (nc >= 16)
+  {
+    long blocks = (rows * 8 + 255) / 256, cap = (long)r.sm_count * 8;
+    stencil_kernel_generic<8><<<(int)(blocks < cap ? blocks : cap), 256, 0, r.stream>>>(a, nc, n_par);
+  }
+  else
+  {
+    long blocks = (rows + 255) / 256, cap = (long)r.sm_count * 8;
+    stencil_kernel_rows<<<(int)(blocks < cap ? blocks : cap), 256, 0, r.stream>>>(a, nc, n_par);
+  }
   QMG_LAUNCH_CHECK();
   return 0;
 }

@@ -15,6 +15,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--only", default="")
 args = ap.parse_args()
+if os.environ.get("QMG_LIB_OVERRIDE"):      # A / B timing against an older build of the kernel library
+    qmg.LIB_PATH = os.environ["QMG_LIB_OVERRIDE"]
 qmg.init(0)
 lib = qmg.lib()
 
@@ -46,14 +48,16 @@ def report(name, sec, nbytes):
 
 
 if not args.only or "stencil" in args.only:
-    for nc, L in ((2, 8192), (2, 4096), (2, 1024), (8, 2048), (8, 1024), (8, 256), (1, 8192), (4, 2048), (16, 512)):
+    # nc = 12, 24, 48: domain-wall operators with Ls = 6, 12, 24 (the any-nc kernel)
+    cases = ((12, 1024), (24, 512), (48, 256)) if os.environ.get("PROBE_GENERIC_ONLY") else None
+    for nc, L in cases or ((2, 8192), (2, 4096), (2, 1024), (8, 2048), (8, 1024), (8, 256), (1, 8192), (4, 2048), (16, 512), (12, 1024), (24, 512), (48, 256)):
         V = L * L
         cl, hp = rnd(V * nc * nc), rnd(4 * V * nc * nc)
         x, y = rnd(V * nc), qmg.cvec(V * nc)
         d = qmg.stencil_desc(L, L, nc, cl, hp, shift=0.1)
         sec = timed(lambda: qmg.stencil_apply(d, y, x))
         report("stencil apply nc=%d %dx%d" % (nc, L, L), sec, 16.0 * V * (nc * nc * 5 + 2 * nc))
-        if nc % 2 == 0:
+        if nc in (2, 4, 8, 16, 32):
             dh = qmg.stencil_desc(L, L, nc, cl, hp, shift=0.1, gamma5_hermitian=True)
             sec = timed(lambda: qmg.stencil_apply(dh, y, x))
             report("  link-compressed (3 of 5 blocks) nc=%d %dx%d" % (nc, L, L), sec, 16.0 * V * (nc * nc * 5 + 2 * nc))
