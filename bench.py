@@ -55,7 +55,7 @@ def measured_peak():
 
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,clocks.mem,power.draw,power.limit"
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -79,7 +79,20 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         mx = max([float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()] or [0.0])
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(self.rows)}
+
+        def median(col):
+            v = []
+            for r in self.rows:
+                try:
+                    v.append(float(r[col]))
+                except (IndexError, ValueError):
+                    pass
+            v.sort()
+            return v[len(v) // 2] if v else None
+        # context for sw_power_cap: memory clock and board power against its limit while the kernel runs
+        out["mem_mhz"], out["power_w"], out["power_limit_w"] = median(6), median(7), median(8)
+        return out
 
 
 def cpu_reference_apply(L, reps, warm=1):

@@ -30,7 +30,9 @@ inline inversion_info minres_core(complex<double>* phi, complex<double>* phi0, i
   const int flags = (hints != 0 && eps < 1.0 && max_iter > 0) ? hints->flags : 0;
   const bool zero_start = (flags & SOLVE_ZERO_START) != 0;
   int executed = 0;
-  complex<double>* r = allocate_vector<complex<double> >(size);
+  // a caller that takes the residual over gets it in its own vector: the recurrence runs there
+  complex<double>* rout = (hints != 0 && flags != 0) ? hints->residual_out : 0;
+  complex<double>* r = (rout != 0) ? rout : allocate_vector<complex<double> >(size);
   complex<double>* p = allocate_vector<complex<double> >(size);
   double bsq = (hints != 0 && hints->bnorm2 >= 0.0) ? hints->bnorm2 : -1.0;
   const complex<double>* r_in = r;
@@ -68,10 +70,12 @@ inline inversion_info minres_core(complex<double>* phi, complex<double>* phi0, i
     const bool x_only = (flags & SOLVE_LAST_X_ONLY) && k == max_iter;
     const bool want_b = first && bsq < 0.0 && !x_only;
     double step[5];
+    // the last step of a smoother: x only -- or, when the caller takes the residual over, x and r without the norm of r
+    const int last_flag = x_only ? (rout != 0 ? QMG_STEP_NO_NORM : QMG_STEP_X_ONLY) : 0;
     QMG_CHK(qmg_krylov_step(omega, P(r_in), P(p), first ? 0 : P(phi), P(x_only && acc != 0 ? acc : phi), P(r_in), P(r),
-                            x_only && acc != 0 ? P(acc) : 0, size, (want_b ? QMG_STEP_WANT_RNORM : 0) | (x_only ? QMG_STEP_X_ONLY : 0), step, 0));
+                            x_only && acc != 0 ? P(acc) : 0, size, (want_b ? QMG_STEP_WANT_RNORM : 0) | last_flag, step, 0));
     r_in = r;
-    if (x_only) { acc_done = (acc != 0); break; }     // nobody reads this residual: no reduction, no host wait
+    if (x_only) { acc_done = (acc != 0); break; }     // nobody reads this residual's norm: no reduction, no host wait
     if (want_b) { bsq = step[4]; bsqrt = sqrt(bsq); }
     rsq = step[0];
     say(verb, VERB_DETAIL, "MR", "", false, false, k, invif.ops_count, sqrt(rsq) / bsqrt);
@@ -92,7 +96,10 @@ inline inversion_info minres_core(complex<double>* phi, complex<double>* phi0, i
   say(verb, VERB_SUMMARY, "MR", "", true, invif.success, invif.iter, invif.ops_count, sqrt(invif.resSq) / bsqrt);
   if (hints != 0) hints->executed += executed;
 
-  deallocate_vector(&r);
+  // r holds b - A x of the returned x whenever at least one step ran (every step updates x and r together) or the solve started
+  // from an explicit residual; from a zero start without a step x = 0 and the residual is b itself, which was never copied
+  if (rout != 0) hints->residual_valid = (r_in == r);
+  else deallocate_vector(&r);
   deallocate_vector(&p);
   return invif;
 }

@@ -28,13 +28,18 @@ enum
   SOLVE_NO_FINAL_RESIDUAL = 2,   // do not recompute |b - A x| at exit (resSq then holds the recursive value)
   SOLVE_LAST_X_ONLY = 4,         // smoother: the last permitted iteration updates x only (its residual is never read)
 };
+// (SolveHints::residual_out, MR only: the solver's own residual vector at exit -- b - A x by the recurrence r -= alpha A r --
+//  is left there for the caller, who then does not have to apply A to x to get it.  With SOLVE_LAST_X_ONLY the last step
+//  still forms that vector, only its norm is not taken.)
 struct SolveHints
 {
   int flags;
   double bnorm2;                            // |b|^2 when the caller has just computed it, else < 0
   std::complex<double>* accumulate_into;    // MR: add the solution to this vector as well (folded into the last step)
+  std::complex<double>* residual_out;       // MR: where to leave the recursive residual of the returned x (0: nobody wants it)
+  bool residual_valid;                      // out: residual_out holds b - A x of the returned x
   int executed;                             // out: operator applications actually launched (ops_count keeps the reference's count)
-  SolveHints(int f = 0, double b2 = -1.0) : flags(f), bnorm2(b2), accumulate_into(0), executed(0) { }
+  SolveHints(int f = 0, double b2 = -1.0) : flags(f), bnorm2(b2), accumulate_into(0), residual_out(0), residual_valid(false), executed(0) { }
 };
 }
 

@@ -97,6 +97,7 @@ protected:
   complex<double>* coarsest_evals;
   complex<double>** coarsest_evecs;
   bool fused_cycle;
+  bool residual_handover;
 
   static void check_level_solve(LevelSolveMG* s, const char* where)
   {
@@ -118,6 +119,8 @@ public:
     dslash_tracker_list.push_back(new DslashTrackerMG());
     const char* e = getenv("QMG_FUSED_CYCLE");
     fused_cycle = !(e != 0 && e[0] == '0');
+    const char* e2 = getenv("QMG_RESIDUAL_HANDOVER");
+    residual_handover = !(e2 != 0 && e2[0] == '0');
     qmg_host::overwriting_precond() = mg_preconditioner;    // writes every element of its output: the solvers need not zero it
   }
   ~StatefulMultigridMG()
@@ -272,6 +275,13 @@ public:
   // 0: the reference's sequence of separate sweeps, launch for launch (what round 1 ran).  Results are bit-identical.
   void set_fused_cycle(bool on) { fused_cycle = on; }
   bool get_fused_cycle() { return fused_cycle; }
+  // With the fused cycle: 1 (default) the pre-smoother hands its own residual r = rhs - A z1 (the MR recurrence r -= alpha A r,
+  // which its last step then completes without taking the norm) to the restriction, so that the reference's explicit
+  // "Atmp = A z1; r1 = rhs - Atmp" (:863-866) is not launched: one operator apply less per K-cycle application and level
+  // (7 -> 6 at the BASELINE settings).  The two residuals are the same vector up to rounding (two MR steps from a zero start),
+  // so this is the one shortcut that is NOT bit-identical: 0 keeps the explicit residual and with it the bits of the unfused cycle.
+  void set_residual_handover(bool on) { residual_handover = on; }
+  bool get_residual_handover() { return residual_handover; }
   void shift_all_to_nullvec(int i) { if (tracker_ok(i, "shift to null vectors")) dslash_tracker_list[i]->shift_all_to_nullvec(); }
   int get_tracker_count(QMGDslashType type, int i) { return tracker_ok(i, "query tracker") ? dslash_tracker_list[i]->get_tracker_count(type) : -1; }
   int get_total_count(int i) { return tracker_ok(i, "query tracker") ? dslash_tracker_list[i]->get_total_count() : -1; }
@@ -335,8 +345,10 @@ public:
   // of them feeds only inversion_info::resSq, which this function never reads (:854,:861,:996 use ops_count and iter) --
   // and steps the reference spells as several sweeps run as one: r = b - A z (:863-866, :1023-1029), zero + restrict
   // (:876-878), zero + prolong + z1 + z2 (:1005-1019), lhs += z3 (:1050).  Every number that IS computed is formed by
-  // the same kernel arithmetic in the same order: lhs is bit-identical with fused_cycle on and off.  The trackers keep
-  // the reference's operator counts; add_executed_count records what was launched.
+  // the same kernel arithmetic in the same order: lhs is bit-identical with fused_cycle on and off -- with ONE exception that
+  // has its own switch (set_residual_handover, on by default): the residual after the pre-smoother is the smoother's own
+  // (recurrence) residual instead of a fresh rhs - A z1, equal to it up to rounding.  The trackers keep the reference's
+  // operator counts; add_executed_count records what was launched.
   static void mg_preconditioner(complex<double>* lhs, complex<double>* rhs, int size, void* extra_data, inversion_verbose_struct* verb)
   {
     (void)size;
@@ -398,18 +410,20 @@ public:
     if (ls->pre_iters > 0)
     {
       SolveHints hints(smooth_flags);
+      if (fuse && mg->residual_handover) hints.residual_out = r1;      // the smoother's own residual, if it can give one
       int executed = 0;
       const int ops = smooth(fine, fpool, ftype, ls->pre_cgne, ls->pre_iters, ls->pre_tol, z1, rhs, nf_solve, nf, fuse ? &hints : 0, executed);
       mg->add_tracker_count(QMG_DSLASH_TYPE_PRESMOOTH, ops, level);
-      if (!(fuse && fine->apply_residual(r1, rhs, z1, ftype)))
+      const bool handed = fuse && hints.residual_valid;
+      if (!handed && !(fuse && fine->apply_residual(r1, rhs, z1, ftype)))
       {
         complex<double>* Az = fpool->check_out();
         fine_op(Az, z1, (void*)fine);
         caxpbyz(1.0, rhs, -1.0, Az, r1, nf_solve);
         fpool->check_in(Az);
       }
-      mg->add_tracker_count(QMG_DSLASH_TYPE_PRESMOOTH, 1, level);
-      mg->add_executed_count(executed + 1, level);
+      mg->add_tracker_count(QMG_DSLASH_TYPE_PRESMOOTH, 1, level);      // the reference's count: it applies the operator here
+      mg->add_executed_count(executed + (handed ? 0 : 1), level);
     }
     else
     {

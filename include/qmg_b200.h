@@ -245,7 +245,9 @@ int qmg_step_xr_norm(double omega, const qmg_cplx* p, const qmg_cplx* q, qmg_cpl
  * QMG_STEP_DOTS_READY: <q|r_in> and <q|q> were left on the device by qmg_gcr_orthogonalize -- the dot pass is skipped.
  * qq_dev (device, may be NULL): receives <q|q>, the |Ap_k|^2 later GCR orthogonalisations divide by. */
 enum { QMG_STEP_WANT_RNORM = 1, QMG_STEP_X_ONLY = 2, QMG_STEP_DOTS_READY = 4,
-       QMG_STEP_R_ONLY = 8 /* r_out = r_in - alpha q and |r_out|^2 only: p, x_in, x_out, acc are not touched (GCR forming x at the end) */ };
+       QMG_STEP_R_ONLY = 8 /* r_out = r_in - alpha q and |r_out|^2 only: p, x_in, x_out, acc are not touched (GCR forming x at the end) */,
+       QMG_STEP_NO_NORM = 16 /* x_out and r_out as without flags, but |r_out|^2 is not formed: no reduction, no host wait, nothing returned
+                                (a smoother's last step whose residual the caller takes over but whose norm nobody reads) */ };
 int qmg_krylov_step(double omega, const qmg_cplx* p, const qmg_cplx* q, const qmg_cplx* x_in, qmg_cplx* x_out,
                     const qmg_cplx* r_in, qmg_cplx* r_out, const qmg_cplx* acc, long n, int flags, double* result5, double* qq_dev);
 /* GCR: orthogonalise the new direction against the k stored ones with the coefficients formed ON THE DEVICE and prepare the

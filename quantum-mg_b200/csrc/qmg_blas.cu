@@ -620,6 +620,23 @@ int qmg_krylov_step(double omega, const qmg_cplx* p_, const qmg_cplx* q_, const 
     else { QMG_CUDA(cudaMemcpy(result5 + 1, dres, sizeof(double) * 3, cudaMemcpyDeviceToHost)); result5[4] = 0.0; }
     return 0;
   }
+  if (flags & QMG_STEP_NO_NORM)
+  {
+    if (flags & (QMG_STEP_X_ONLY | QMG_STEP_R_ONLY | QMG_STEP_WANT_RNORM)) return fail_msg("qmg_krylov_step: QMG_STEP_NO_NORM excludes X_ONLY, R_ONLY and WANT_RNORM");
+    // the element arithmetic of the general step below, without its reduction
+    return launch_ew(n, [=] __device__(long i) {
+      const double d0 = dres[0], d1 = dres[1], d2 = dres[2];
+      const cd a = cmake(__ddiv_rn(__dmul_rn(omega, d0), d2), __ddiv_rn(__dmul_rn(omega, d1), d2));
+      const cd ma = cmake(-a.x, -a.y);
+      cd pi = p[i];
+      cd ri = rin[i];
+      cd xi = (xin != nullptr) ? xin[i] : cmake(0.0, 0.0);
+      cfma(xi, a, pi);
+      if (accv != nullptr) xi = cadd(accv[i], xi);
+      x[i] = xi;
+      cfma(ri, ma, q[i]); r[i] = ri;
+    });
+  }
   if (flags & QMG_STEP_X_ONLY)
     return launch_ew(n, [=] __device__(long i) {
       const double d0 = dres[0], d1 = dres[1], d2 = dres[2];

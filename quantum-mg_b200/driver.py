@@ -379,8 +379,9 @@ class Multigrid:
         return int(f(self.h, level))
 
     def set_fused(self, on):
-        """B200 extension: fused K-cycle on (default) / off (the reference's sweep-for-sweep sequence); returns the old setting."""
-        return int(self.be.fn("mg_set_fused")(self.h, 1 if on else 0))
+        """B200 extension: 1 / True fused K-cycle with the pre-smoother's residual handed over (default), 2 fused with the explicit
+        residual (bit-identical to 0), 0 / False the reference's sweep-for-sweep sequence; returns the old setting."""
+        return int(self.be.fn("mg_set_fused")(self.h, int(on)))
 
     def apply_stencil(self, level, rhs, type=0):
         rhs = carr(rhs)
@@ -437,7 +438,7 @@ class KCycle:
         return int(f(self._mg, level))
 
     def set_fused(self, on):
-        return int(self.be.fn("mg_set_fused")(self._mg, 1 if on else 0))
+        return int(self.be.fn("mg_set_fused")(self._mg, int(on)))
 
     def update_links(self, gauge):
         """New gauge links into the same Wilson operator and a fresh hierarchy (the n16 measurement-loop step)."""

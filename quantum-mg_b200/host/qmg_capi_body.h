@@ -652,13 +652,15 @@ long CAPI(mg_executed)(void* h_, int level)
   return ((capi::MgH*)h_)->mg->get_total_count(level);
 #endif
 }
-// B200 extension: 1 = fused K-cycle (default), 0 = the reference's sequence of separate sweeps; bit-identical results.  Returns the previous setting.
+// B200 extension: 1 = fused K-cycle with the pre-smoother's residual handed over (default), 2 = fused K-cycle with the explicit
+// residual (bit-identical to 0), 0 = the reference's sequence of separate sweeps.  Returns the previous setting.
 int CAPI(mg_set_fused)(void* h_, int on)
 {
 #ifdef QMG_B200_HOST
   StatefulMultigridMG* mg = ((capi::MgH*)h_)->mg;
-  const int was = mg->get_fused_cycle() ? 1 : 0;
+  const int was = mg->get_fused_cycle() ? (mg->get_residual_handover() ? 1 : 2) : 0;
   mg->set_fused_cycle(on != 0);
+  if (on != 0) mg->set_residual_handover(on == 1);
   return was;
 #else
   (void)h_; (void)on; return 0;

@@ -1,0 +1,8 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_host_gpu.py tests/test_kernels_gpu.py -m gpu -q -x -k "fused or kcycle or krylov or n22 or n16 or staggered" 2>&1 | tail -6
+for m in 0 1; do QMG_RESIDUAL_HANDOVER=$m timeout 400 python tools/kcycle_probe.py gpu 8192 --hermitian --hermitian-setup --restart 8 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('handover $m', {k: d.get(k) for k in ('iter', 'seconds', 'second_solve_s', 'second_solve_iter', 'setup_seconds', 'check_relres', 'executed')})"; done
