@@ -18,6 +18,15 @@ namespace qmg_host {
 // needs no zeroed output vector; any other callback still gets one, as quantum-linalg's callers expect.
 inline precond_op_cplx& overwriting_precond() { static precond_op_cplx f = 0; return f; }
 
+// A preconditioner that knows A z of the z it returns (the K-cycle does: its post-smoother's recurrence residual r' satisfies
+// A z = rhs - r') can spare the flexible solver the operator apply that follows every preconditioner call.  The solver posts
+// a request -- where A z should go, for which operator -- before the call; a callback that can serve it fills `out` and sets
+// `valid`, any other ignores it and the solver applies the operator itself.  Requests nest with the solves: whoever posts
+// one restores the previous one after the call, and the K-cycle takes the pending request off the board before it starts
+// the solves one level down.
+struct PrecondAzRequest { complex<double>* out; matrix_op_cplx op; void* op_data; bool valid; };
+inline PrecondAzRequest*& precond_az_request() { static PrecondAzRequest* r = 0; return r; }
+
 // Shared body of GCR and flexible (variably preconditioned) GCR.  `hints` (inverter_struct.h) as in minres_core: from a
 // zero start r0 = b without applying A to zero, |b|^2 can come from the caller, and a solve that ends converged skips the
 // true-residual apply nobody reads.
@@ -46,6 +55,17 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
   std::vector<cplx> alpha;
   std::vector<double> apn;
   struct Alloc { std::vector<cplx*>& o; int n; cplx* operator()() { cplx* v = allocate_vector<cplx>(n); o.push_back(v); return v; } } fresh = { owned, size };
+  // d = M^-1 r and A d: from the preconditioner itself when it can say (see PrecondAzRequest), else by an apply
+  auto precond_then_apply = [&](cplx* dk, cplx* r, cplx* Adk)
+  {
+    PrecondAzRequest req = { Adk, matrix_vector, extra_info, false };
+    PrecondAzRequest* pending = precond_az_request();
+    precond_az_request() = &req;
+    precond(dk, r, size, precond_info, &verb_prec);
+    precond_az_request() = pending;
+    invif.ops_count++;
+    if (!req.valid) { matrix_vector(Adk, dk, extra_info); executed++; }
+  };
   cplx* scratch = 0;
   double bsq = (hints != 0 && hints->bnorm2 >= 0.0) ? hints->bnorm2 : norm2sq(phi0, size);
   const double bsqrt = sqrt(bsq);
@@ -78,10 +98,10 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
     dev_dots = allocate_vector<double>(2 * cap * cap);
     dev_apn = allocate_vector<double>(cap);
     cplx* dk = cur_r;
-    if (precond) { dk = fresh(); if (zero_for_precond) zero_vector(dk, size); precond(dk, cur_r, size, precond_info, &verb_prec); }
-    d.push_back(dk);
     Ap.push_back(fresh());
-    matrix_vector(Ap[0], d[0], extra_info); invif.ops_count++; executed++;
+    if (precond) { dk = fresh(); if (zero_for_precond) zero_vector(dk, size); precond_then_apply(dk, cur_r, Ap[0]); }
+    else { matrix_vector(Ap[0], dk, extra_info); invif.ops_count++; executed++; }
+    d.push_back(dk);
     bool dots_ready = false;
     for (k = 1; k <= max_iter; k++)
     {
@@ -101,10 +121,10 @@ inline inversion_info gcr_core(const char* name, complex<double>* phi, complex<d
 
       // next direction: d = M^-1 r (or r itself), A d straight into its slot, then project the stored A p_i out of it on the device
       dk = cur_r;
-      if (precond) { dk = fresh(); if (zero_for_precond) zero_vector(dk, size); precond(dk, cur_r, size, precond_info, &verb_prec); }
-      d.push_back(dk);
       Ap.push_back(fresh());
-      matrix_vector(Ap[k], dk, extra_info); invif.ops_count++; executed++;
+      if (precond) { dk = fresh(); if (zero_for_precond) zero_vector(dk, size); precond_then_apply(dk, cur_r, Ap[k]); }
+      else { matrix_vector(Ap[k], dk, extra_info); invif.ops_count++; executed++; }
+      d.push_back(dk);
       if (k + 1 > cap)
       {
         double* gd = allocate_vector<double>(8 * cap * cap);        // (2 cap)^2 rows x columns, 2 doubles each

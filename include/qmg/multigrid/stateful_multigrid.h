@@ -280,6 +280,8 @@ public:
   // "Atmp = A z1; r1 = rhs - Atmp" (:863-866) is not launched: one operator apply less per K-cycle application and level
   // (7 -> 6 at the BASELINE settings).  The two residuals are the same vector up to rounding (two MR steps from a zero start),
   // so this is the one shortcut that is NOT bit-identical: 0 keeps the explicit residual and with it the bits of the unfused cycle.
+  // The same switch lets the post-smoother answer a flexible solver's request for A lhs (A lhs = rhs - r2', r2' its recurrence
+  // residual; inverters/generic_gcr.h PrecondAzRequest): the Krylov apply after each K-cycle application goes too (6 -> 5).
   void set_residual_handover(bool on) { residual_handover = on; }
   bool get_residual_handover() { return residual_handover; }
   void shift_all_to_nullvec(int i) { if (tracker_ok(i, "shift to null vectors")) dslash_tracker_list[i]->shift_all_to_nullvec(); }
@@ -358,6 +360,11 @@ public:
     const bool fuse = mg->fused_cycle;
     using qmg_host::SolveHints;
     using qmg_host::SOLVE_ZERO_START; using qmg_host::SOLVE_NO_FINAL_RESIDUAL; using qmg_host::SOLVE_LAST_X_ONLY;
+
+    // a flexible solver above may have asked for A lhs along with lhs (inverters/generic_gcr.h); the request is taken off the
+    // board here so that the solves one level down, which post their own, do not see it
+    qmg_host::PrecondAzRequest* az_req = qmg_host::precond_az_request();
+    qmg_host::precond_az_request() = 0;
 
     LevelSolveMG* ls = mg->get_level_solve();
     if (ls == 0) { std::cout << "[QMG-MG-SOLVE-ERROR]: Level solve for level " << level << " does not exist.\n"; return; }
@@ -547,12 +554,17 @@ public:
       complex<double>* z3 = fpool->check_out();
       SolveHints hints(smooth_flags);
       hints.accumulate_into = lhs;        // lhs += z3 rides on the smoother's last step
+      // A lhs for the solver that asked: r2 = rhs - A (z1 + P e) is exact here, the smoother's recurrence turns it (in place)
+      // into r2' = r2 - A z3, so A lhs = rhs - r2' -- two more vector passes instead of an operator apply
+      const bool serve_az = fuse && mg->residual_handover && az_req != 0 && az_req->op == fine_op && az_req->op_data == (void*)fine && nf_solve == nf;
+      if (serve_az) hints.residual_out = r2;
       int executed = 0;
       if (!fuse) zero_vector(z3, nf);
       const int ops = smooth(fine, fpool, ftype, ls->post_cgne, ls->post_iters, ls->post_tol, z3, r2, nf_solve, nf, fuse ? &hints : 0, executed);
       mg->add_tracker_count(QMG_DSLASH_TYPE_POSTSMOOTH, ops, level);
       mg->add_executed_count(executed + 1, level);
       if (!fuse) cxpy(z3, lhs, nf_solve);
+      if (serve_az && hints.residual_valid) { caxpbyz(1.0, rhs, -1.0, r2, az_req->out, nf_solve); az_req->valid = true; }
       fpool->check_in(r2);
       fpool->check_in(z3);
     }
