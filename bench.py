@@ -137,8 +137,15 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
             gauge = latutil.load_gauge(L)          # the reference's own thermalised config where one exists (32, 64, 128, 256)
             cfg = "tests/common_cfgs_u1 l%dt%db60" % (L, L)
         except Exception:
-            gauge = latutil.synthetic_gauge(L, Yl or L, beta=6.0, seed=seed + rank, slab=True)
-            cfg = "synthetic non-compact U(1), beta 6.0, seed %d + rank, one stackable slab per rank (tests/latutil.py synthetic_phases)" % seed
+            # The global field is a stack of (L x L/8) stackable slabs, slab u drawn with seed + u; this rank's rows are units
+            # [u0, u0 + n_u).  One rank: units 0..7.  Strong scaling (Yl = L / world): the SAME eight units cut N ways -- the N = 1
+            # leg of this bench is its reference point.  Weak scaling: eight more units per rank, rank 0's slab = the N = 1 field.
+            Ys = Yl or L
+            unit = L // 8 if (L % 8 == 0 and (L // 8) % 32 == 0 and Ys % (L // 8) == 0) else Ys
+            u0 = rank * (Ys // unit)
+            gauge = latutil.synthetic_gauge_units(L, Ys, unit, u0, beta=6.0, seed=seed)
+            cfg = ("synthetic non-compact U(1), beta 6.0: stack of stackable (%d x %d) slabs, slab u drawn with seed %d + u; this rank: units %d..%d "
+                   "(quantum-mg_b200/latutil.py synthetic_gauge_units)" % (L, unit, seed, u0, u0 + Ys // unit - 1))
     else:
         cfg = "caller-supplied"
     if world > 1:

@@ -72,6 +72,16 @@ def synthetic_gauge(X, Y, beta=6.0, seed=1337, slab=False):
     return phases_to_gauge(synthetic_phases(X, Y, beta, seed, slab), X, Y)
 
 
+def synthetic_gauge_units(X, Y, unit_rows, first_unit, beta=6.0, seed=1337):
+    """Rows [first_unit * unit_rows, ... + Y) of the periodic field that is the stack of stackable (X, unit_rows) slabs, slab u drawn
+    with seed + u.  Every rank of an N-way y-slab decomposition, for every N that divides the number of units, gets its part of the
+    SAME global field this way (strong scaling on one lattice), and a taller lattice is the same field continued (weak scaling)."""
+    if Y % unit_rows:
+        raise ValueError("synthetic_gauge_units: Y must be a multiple of unit_rows")
+    parts = [synthetic_phases(X, unit_rows, beta, seed + first_unit + u, slab=True).reshape(X, unit_rows, 2) for u in range(Y // unit_rows)]
+    return phases_to_gauge(np.concatenate(parts, axis=1).ravel(), X, Y)
+
+
 def average_plaquette(gauge, X, Y):
     """<Re U_x(x) U_y(x+x^) U_x*(x+y^) U_y*(x)> (u1/u1_utils.h:424-460)."""
     xs, ys = np.meshgrid(np.arange(X), np.arange(Y), indexing="ij")

@@ -138,6 +138,31 @@ def test_stackable_synthetic_slabs_form_one_configuration():
     assert abs(latutil.average_plaquette(g, X, Yl * N) - np.exp(-0.5 / beta)) < 0.01
 
 
+def test_unit_built_fields_are_one_field_for_every_slab_count():
+    """bench.py builds its K-cycle fields from fixed units (latutil.synthetic_gauge_units): the same eight units cut 1, 2, 4
+    or 8 ways are the same global field (strong scaling compares like with like), and rank 0 of a weak-scaling run holds the
+    one-GPU field."""
+    import latutil
+    X, Y, unit = 16, 64, 8
+    whole = latutil.synthetic_gauge_units(X, Y, unit, 0, seed=7)
+    assert abs(latutil.average_plaquette(whole, X, Y) - np.exp(-0.5 / 6.0)) < 0.03
+    for n in (2, 4, 8):
+        Yl = Y // n
+        rebuilt = np.zeros_like(whole)
+        for r in range(n):
+            part = latutil.synthetic_gauge_units(X, Yl, unit, r * (Yl // unit), seed=7)
+            for mu in range(2):
+                # a slab's rows y0 .. y0 + Yl of both parity halves of the global eo array (quantum-mg_b200/shard.py)
+                for par in range(2):
+                    loc = part[mu * X * Yl + par * (X // 2) * Yl: mu * X * Yl + (par + 1) * (X // 2) * Yl]
+                    g0 = mu * X * Y + par * (X // 2) * Y + r * Yl * (X // 2)
+                    rebuilt[g0:g0 + Yl * (X // 2)] = loc
+        assert np.array_equal(rebuilt, whole), n
+    # weak scaling: rank 0's slab of a taller lattice is the one-rank field
+    assert np.array_equal(latutil.synthetic_gauge_units(X, Y, unit, 0, seed=7), whole)
+    assert not np.array_equal(latutil.synthetic_gauge_units(X, Y, unit, Y // unit, seed=7), whole)
+
+
 def test_global_index_rng_mapping_matches_slab_layout():
     """qmg_gaussian on a y-slab keys its counter by  p * (N half) + rank * half + i'  (csrc/qmg_blas.cu): that must be the
     position of local element i = p * half + i' in the global even-odd field, i.e. exactly what shard.Slab.take selects --
