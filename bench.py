@@ -157,11 +157,18 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
         # B200 extension: every coarse operator switches to its link-compressed apply (shared-memory tile kernel) the moment it
         # is built, so the BiCGstab-L null-vector solves of the level below already use it
         be.fn("kcycle_setup_link_compressed")(1)
+        # ... and the Wilson fine operator applies matrix-free (gauge links instead of stored blocks: 96 instead of 384 bytes per
+        # site, the same bits; Wilson2D::enable_matrix_free_apply checks the stored blocks first) from its first null-vector solve on
+        be.fn("kcycle_setup_matrix_free")(1)
     kc = KC(be, L, mass, gauge, n_refine=n_refine, seed=seed, inner_iters=100, coarsest_iters=400, Y=Yl)
     del gauge
+    mf_active = 0
     if backend == "gpu" and link_compressed:
         be.fn("kcycle_setup_link_compressed")(0)
+        be.fn("kcycle_setup_matrix_free")(0)
         kc.gamma5_hermitian(False)          # the first two solves are the stored-block reference point
+        mf_active = kc.matrix_free(True)
+        kc.matrix_free(False)
     out = kc.solve(tol=tol, restart=restart, max_iter=100)
     if backend == "gpu":
         # warm-up rule: the first solve also pays the cudaMalloc of every work vector (the block cache is empty); the
@@ -173,7 +180,9 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
             # B200 extension: every level whose stored blocks pass the gamma5-hermiticity check applies its
             # operator from clover / +x / +y blocks only (coarse levels: shared-memory tile kernel).  Same iteration counts.
             stored = out
-            n_sw = kc.gamma5_hermitian(True, tile_levels_only=True)      # the nc = 8 levels; the fine level keeps its stored blocks
+            n_sw = kc.gamma5_hermitian(True, tile_levels_only=True)      # the nc = 8 levels; the fine level keeps its stored blocks ...
+            if mf_active:
+                kc.matrix_free(True)                                      # ... or reads its gauge links
             out = kc.solve(tol=tol, restart=restart, max_iter=100)
             if os.environ.get("QMG_BENCH_PROFILE") == "1":
                 # one more solve with the per-entry-point profile on (every call bracketed by stream synchronisations: the
@@ -191,6 +200,7 @@ def kcycle_run(backend, L, seed=1337, n_refine=2, tol=1e-10, restart=32, gauge=N
                     sys.stderr.write("[bench] profiled solve: %.3f s, %d iterations (timed solve %.3f s)\n" % (prof["seconds"], prof["iter"], out["seconds"]))
             out["first_solve_seconds"], out["first_solve_iter"] = first["seconds"], first["iter"]
             out["link_compressed_levels"] = n_sw
+            out["matrix_free_fine_level"] = bool(mf_active)
             out["seconds_stored_blocks"], out["iter_stored_blocks"] = stored["seconds"], stored["iter"]
     out["mass"] = mass
     out["levels"] = n_refine + 1

@@ -39,6 +39,38 @@ public:
     generated = true;
   }
 
+  // B200 extension (not in the reference): the five stored 2 x 2 blocks of a site are functions of four U(1) links, so the
+  // whole-operator apply can read the links (96 instead of 384 bytes per site from HBM) and rebuild the block elements on the fly
+  // with the arithmetic of the fill -- the output has the same bits as the stored-block apply.  The operator takes its own copy
+  // of gauge_links (the caller keeps ownership of its array, as in the constructor) and CHECKS that the stored blocks equal the
+  // regenerated ones exactly first (false and nothing changes otherwise, e.g. after the n18 mutation of the clover).  Anything
+  // that edits the blocks afterwards (update_links, clear_stencils) drops it again; writing through the public pointers must be
+  // followed by disable_matrix_free_apply().  Pieces, dagger / rbjacobi / Schur variants keep reading the stored blocks.
+  bool enable_matrix_free_apply(complex<double>* gauge_links)
+  {
+    disable_matrix_free_apply();
+    if (lat->get_nc() != 2 || clover == 0 || hopping == 0 || swap_dagger || swap_rbjacobi || swap_rbj_dagger) return false;
+    const long V = lat->get_volume();
+    complex<double>* copy = allocate_vector<complex<double> >(2 * V);
+    copy_vector(copy, gauge_links, 2 * V);
+    complex<double>* halo = 0;
+    if (qmg_comm_active())
+    {
+      // on a y-slab row -1 of U_y lives on the lower rank: fetched once
+      const long row = lat->get_dim_mu(0);
+      halo = allocate_vector<complex<double> >(row);
+      complex<double>* unused = allocate_vector<complex<double> >(row);
+      QMG_CHK(qmg_halo_exchange(qmg_host::P(copy + V), lat->get_dim_mu(0), lat->get_dim_mu(1), 1, qmg_host::P(halo), qmg_host::P(unused)));
+      deallocate_vector(&unused);
+    }
+    mf_gauge = copy; mf_gauge_halo_ym = halo; mf_w = wilson_coeff;
+    qmg_stencil_desc d = describe();
+    double dev[2] = {1.0, 0.0};
+    QMG_CHK(qmg_wilson_mf_deviation(&d, dev));
+    if (dev[0] != 0.0) { disable_matrix_free_apply(); return false; }
+    return true;
+  }
+
   static int get_dof(int i = 0) { (void)i; return 2; }
   static chirality_state has_chirality() { return QMG_CHIRAL_YES; }
 

@@ -91,6 +91,12 @@ protected:
   // link-compressed apply (see enable_gamma5_hermitian_apply)
   bool gamma5_hermitian;
   complex<double>* herm_halo_ym;
+  // matrix-free apply (Wilson2D::enable_matrix_free_apply): the operator's own copy of the gauge links its stored blocks were
+  // filled from, row -1 of U_y on a y-slab, and the Wilson parameter; 0 = read the stored blocks
+  complex<double>* mf_gauge;
+  complex<double>* mf_gauge_halo_ym;
+  double mf_w;
+  bool mf_paused;
 
   complex<double>* scratch_extra() { if (extra_cvector == 0) extra_cvector = allocate_vector<complex<double> >(lat->get_size_cv()); return extra_cvector; }
   complex<double>* scratch_eo() { if (eo_cvector == 0) eo_cvector = allocate_vector<complex<double> >(lat->get_size_cv()); return eo_cvector; }
@@ -121,6 +127,11 @@ public:
     const bool original = !swap_dagger && !swap_rbjacobi && !swap_rbj_dagger && (cl == clover || cl == 0) && hp == hopping && hp != 0;
     d.gamma5_hermitian = (gamma5_hermitian && original) ? 1 : 0;
     d.hop_halo_ym = d.gamma5_hermitian ? qmg_host::P(herm_halo_ym) : 0;
+    // ... and so is the matrix-free one (it also needs the clover of the set: the kernel layer takes it for whole-operator applies only)
+    const bool mf = (mf_gauge != 0) && !mf_paused && original && cl == clover && cl != 0;
+    d.wilson_gauge = mf ? qmg_host::P(mf_gauge) : 0;
+    d.wilson_w = mf ? mf_w : 0.0;
+    d.wilson_gauge_halo_ym = mf ? qmg_host::P(mf_gauge_halo_ym) : 0;
     return d;
   }
   qmg_stencil_desc describe() const { return describe(clover, hopping, shift, eo_shift, dof_shift); }
@@ -167,6 +178,7 @@ public:
     shift_backup = shift; eo_shift_backup = eo_shift; dof_shift_backup = dof_shift;
     swap_dagger = swap_rbjacobi = swap_rbj_dagger = false;
     gamma5_hermitian = false; herm_halo_ym = 0;
+    mf_gauge = 0; mf_gauge_halo_ym = 0; mf_w = 0.0; mf_paused = false;
   }
 
   // B200 extension (not in the reference): for an operator with D^dag = gamma5 D gamma5 -- Wilson2D and the Galerkin
@@ -205,9 +217,20 @@ public:
   void disable_gamma5_hermitian_apply() { gamma5_hermitian = false; }
   bool uses_gamma5_hermitian_apply() const { return gamma5_hermitian; }
 
+  // drop the matrix-free apply (the stored blocks are read again)
+  void disable_matrix_free_apply()
+  {
+    if (mf_gauge != 0) deallocate_vector(&mf_gauge);
+    if (mf_gauge_halo_ym != 0) deallocate_vector(&mf_gauge_halo_ym);
+  }
+  bool uses_matrix_free_apply() const { return mf_gauge != 0 && !mf_paused; }
+  // read the stored blocks for a while without giving the gauge copy up (returns whether a matrix-free apply is set up at all)
+  bool pause_matrix_free_apply(bool pause) { mf_paused = pause; return mf_gauge != 0; }
+
   virtual ~Stencil2D()
   {
     if (herm_halo_ym != 0) deallocate_vector(&herm_halo_ym);
+    disable_matrix_free_apply();
     complex<double>** all[] = { &clover, &hopping, &twolink, &corner, &extra_cvector, &eo_cvector,
                                 &dagger_clover, &dagger_hopping, &dagger_twolink, &dagger_corner,
                                 &rbjacobi_clover, &rbjacobi_hopping, &rbjacobi_twolink, &rbjacobi_corner, &rbjacobi_cinv,
@@ -223,6 +246,7 @@ public:
     for (unsigned i = 0; i < sizeof(der) / sizeof(der[0]); i++) if (*der[i] != 0) deallocate_vector(der[i]);
     built_dagger = built_rbjacobi = false;
     gamma5_hermitian = false;      // the links changed: the relation has to be re-checked
+    disable_matrix_free_apply();   // ... and the gauge copy no longer describes the blocks
   }
 
   // stencil_2d.h:339-376 (including the reference's reset of built_rbjacobi where built_rbj_dagger is meant)
@@ -230,6 +254,7 @@ public:
   {
     const long cm = lat->get_size_cm(), hp = lat->get_size_hopping(), cr = lat->get_size_corner();
     gamma5_hermitian = false;
+    disable_matrix_free_apply();
     if (clover != 0) zero_vector(clover, cm);
     if (hopping != 0) zero_vector(hopping, hp);
     if (twolink != 0) zero_vector(twolink, hp);

@@ -115,6 +115,14 @@ typedef struct qmg_stencil_desc
    * qmg_stencil_gamma5_deviation reports they obey the relation, and clear it when blocks are edited.  nc must be even. */
   int gamma5_hermitian;
   const qmg_cplx* hop_halo_ym; /* gamma5_hermitian on a y-slab: row -1 of hopping_{+y} (X*nc*nc, layout (parity, x/2, nc*nc)) */
+  /* Opt-in matrix-free apply for Wilson2D (nc = 2): the stored blocks are the Wilson blocks of this U(1) gauge field
+   * (operators/wilson.h:153-209), so the WHOLE-operator apply (pieces = QMG_APPLY_ALL, all directions) reads the links -- 96
+   * instead of 384 bytes per site -- and rebuilds the block elements with the arithmetic of qmg_fill_wilson: same bits as the
+   * stored-block apply.  Set it only after qmg_wilson_mf_deviation returned 0, and clear it when blocks are edited.  Every other
+   * apply (pieces, variants, fused reductions) keeps reading the stored blocks.  NULL: off. */
+  const qmg_cplx* wilson_gauge;         /* 2 V complex: [mu V + site], mu = x, y (the nc = 1 lattice of Wilson2D's gauge_links) */
+  double wilson_w;                      /* Wilson parameter the blocks were filled with */
+  const qmg_cplx* wilson_gauge_halo_ym; /* y-slab: row -1 of U_y (X complex, layout (parity, x/2)), from qmg_halo_exchange */
 } qmg_stencil_desc;
 
 /* pieces bitmask (mirrors apply_M_clover/_eo/_oe/_shift, stencil_2d.h:694-909) */
@@ -158,6 +166,9 @@ int qmg_get_tile_kernel(void);
 /* result2 = { sum |hopping_{-mu}(x) - s s conj(hopping_{+mu}(x-mu))^T|^2 over sites and mu, sum |hopping|^2 }: how far the
  * stored backward blocks are from the gamma5-hermitian relation (see qmg_stencil_desc.gamma5_hermitian). */
 int qmg_stencil_gamma5_deviation(const qmg_stencil_desc* st, double* result2);
+/* { sum |stored - regenerated|^2, sum |stored|^2 } of an nc = 2 set against the Wilson blocks of st->wilson_gauge / wilson_w
+ * (operators/wilson.h:153-209): 0 exactly is the licence for the matrix-free apply (qmg_stencil_desc.wilson_gauge) */
+int qmg_wilson_mf_deviation(const qmg_stencil_desc* st, double* result2);
 
 /* Fused apply + reductions for the Krylov updates: out3 = { <lhs|rhs_dot>, |lhs|^2 } after lhs = A rhs.
  * (MR step: alpha = <Ar|r>/<Ar|Ar>, stateful_multigrid.h:860 via qlinalg minres.)

@@ -114,6 +114,49 @@ int qmg_fill_wilson(int X, int Y, double w, const qmg_cplx* gauge_, qmg_cplx* cl
   });
 }
 
+// How far the stored clover / hopping blocks of an nc = 2 set are from the Wilson blocks of the gauge field the descriptor
+// carries (wilson_gauge, wilson_w): result2 = { sum |stored - regenerated|^2, sum |stored|^2 } over all five blocks.  The
+// matrix-free apply (csrc/qmg_stencil.cu wilson_mf_kernel) may be switched on only when the first number is EXACTLY zero.
+int qmg_wilson_mf_deviation(const qmg_stencil_desc* st, double* result2)
+{
+  QMG_REQUIRE_INIT();
+  if (st == nullptr || st->clover == nullptr || st->hopping == nullptr || st->wilson_gauge == nullptr)
+    return fail_msg("qmg_wilson_mf_deviation: needs clover, hopping and wilson_gauge");
+  if (st->nc != 2) return fail_msg("qmg_wilson_mf_deviation: nc must be 2");
+  if (check_dims(st->X, st->Y, "qmg_wilson_mf_deviation: X and Y must be even and >= 2")) return 2;
+  const cd* gauge = CCD(st->wilson_gauge); const cd* clover = CCD(st->clover); const cd* hop = CCD(st->hopping);
+  const double w = st->wilson_w;
+  Geom g; g.xh = st->X / 2; g.Y = st->Y; g.half = (unsigned)(st->X / 2) * st->Y;
+  const long V = (long)st->X * st->Y;
+  HaloTemp halo; HaloRows hy;
+  { int hrc = gauge_halo(halo, gauge, st->X, st->Y, hy); if (hrc) return hrc; }
+  return launch_reduce<2>(V * 4 * 5, [=] __device__(long e, double (&acc)[2]) {
+    const long per = V * 4;
+    const int which = (int)(e / per);
+    const long r = e - (long)which * per;
+    const long site = r >> 2; const int c = (int)(r & 3);
+    const bool diagel = (c == 0 || c == 3);
+    cd want, have;
+    if (which == 0) { want = diagel ? cmake(2.0 * w, 0.0) : cmake(0.0, 0.0); have = clover[r]; }
+    else
+    {
+      const int mu = which - 1;
+      const cd u = link_for(g, gauge, hy, V, site, mu);
+      cd coef;
+      if (diagel) coef = cmake(-0.5 * w, 0.0);
+      else if (mu == 0) coef = cmake(0.5, 0.0);
+      else if (mu == 2) coef = cmake(-0.5, 0.0);
+      else if (mu == 1) coef = (c == 1) ? cmake(0.0, -0.5) : cmake(0.0, 0.5);
+      else coef = (c == 1) ? cmake(0.0, 0.5) : cmake(0.0, -0.5);
+      want = cmul(coef, u);
+      have = hop[(long)mu * per + r];
+    }
+    const double dx = have.x - want.x, dy = have.y - want.y;
+    acc[0] += dx * dx + dy * dy;
+    acc[1] += have.x * have.x + have.y * have.y;
+  }, result2);
+}
+
 // operators/staggered.h:50-72: +x -1/2 U, +y -1/2 eta U, -x +1/2 U*, -y +1/2 eta U*, eta = 1 - 2 (x mod 2)
 int qmg_fill_staggered(int X, int Y, const qmg_cplx* gauge_, qmg_cplx* hopping_)
 {

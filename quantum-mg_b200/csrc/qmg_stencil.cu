@@ -46,6 +46,10 @@ struct StencilKArgs
   const cd* hop_ym;     // herm + y-slab: row -1 of the +y hopping blocks (from the lower rank), layout (parity, x/2, nc nc)
   int y_off, y_stride, y_cnt;   // rows of this launch: y = y_off + i * y_stride, i < y_cnt (all rows: 0, 1, Y; the two
                                 // slab-boundary rows of a sharded apply: 0, Y-1, 2; its interior: 1, 1, Y-2)
+  // matrix-free Wilson apply (nc = 2, the whole operator): the stored blocks ARE the Wilson blocks of this gauge field
+  const cd* mf_gauge;           // [mu V + site], mu = x, y, on the nc = 1 lattice; nullptr: read the stored blocks
+  const cd* mf_gauge_ym;        // y-slab: row -1 of U_y (layout (parity, x/2)), from the lower rank
+  double mf_w;                  // Wilson parameter
 };
 
 // HERM: for an operator with D^dag = gamma5 D gamma5 (Wilson and its Galerkin coarsenings with chirality-preserving
@@ -1216,6 +1220,133 @@ static int build_args(const qmg_stencil_desc* st, int pieces, int dir_mask, qmg_
   if (single_site) { a.p_begin = 0; n_par = 1; }
   a.n_par = n_par;
   a.y_off = 0; a.y_stride = 1; a.y_cnt = a.g.Y;
+  // matrix-free flavour: only the whole operator (every piece, every direction) of an nc = 2 set that carries its gauge field
+  a.mf_gauge = nullptr; a.mf_gauge_ym = nullptr; a.mf_w = 0.0;
+  if (st->wilson_gauge != nullptr && st->nc == 2 && !single_site && (pieces & QMG_APPLY_ALL) == QMG_APPLY_ALL &&
+      !(pieces & QMG_APPLY_IDENTITY_CLOVER) && (dir_mask & 15) == 15 && st->clover != nullptr && st->hopping != nullptr &&
+      (!comm().active || st->wilson_gauge_halo_ym != nullptr))
+  {
+    a.mf_gauge = reinterpret_cast<const cd*>(st->wilson_gauge);
+    a.mf_gauge_ym = reinterpret_cast<const cd*>(st->wilson_gauge_halo_ym);
+    a.mf_w = st->wilson_w;
+  }
+  return 0;
+}
+
+// ---- matrix-free Wilson apply (nc = 2, opt-in) ---------------------------------------------------------------------------
+// The five stored 2 x 2 blocks of a Wilson site (320 of the apply's 384 bytes) are functions of four U(1) links: clover =
+// 2w on the diagonal, hopping_mu[a][b] = coef_mu[a][b] u_mu with coef from {-w/2, +-1/2, +-i/2} (operators/wilson.h:153-209,
+// csrc/qmg_setup.cu qmg_fill_wilson), u_{-mu}(x) = conj(u_mu(x - mu)).  When the caller vouches for that -- descriptor field
+// wilson_gauge, set by Wilson2D::enable_matrix_free_apply after qmg_wilson_mf_deviation found the stored blocks EQUAL to the
+// regenerated ones -- the whole-operator apply reads the links instead: 32 B of links + 32 B in + 32 B out = 96 B per site from
+// DRAM (the backward links and the neighbour spinors were fetched by a neighbouring thread and come out of L1 / L2).  One thread
+// per site forms the block elements with the fill kernel's cmul and runs the element kernel's chains -- per row c1 the partial
+// sums of columns c2 = 0, 1 over clover, shift, +x, +y, -x, -y, then their sum -- so the output has the SAME BITS as the
+// stored-block apply.  Pieces, variants (dagger, rbjacobi, Schur) and fused reductions keep reading the stored blocks.
+__device__ __forceinline__ void ld256_keep(const cd* p, cd& e0, cd& e1)
+{ asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e0.x), "=d"(e0.y), "=d"(e1.x), "=d"(e1.y) : "l"(p)); }
+__device__ __forceinline__ void ld256_stream(const cd* p, cd& e0, cd& e1)
+{ asm("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e0.x), "=d"(e0.y), "=d"(e1.x), "=d"(e1.y) : "l"(p)); }
+__device__ __forceinline__ void st256(cd* p, cd e0, cd e1)
+{ asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(e0.x), "d"(e0.y), "d"(e1.x), "d"(e1.y) : "memory"); }
+
+// element [c1][c2] of the hopping block in direction mu (+x, +y, -x, -y) for link value u: the arithmetic of qmg_fill_wilson
+__device__ __forceinline__ cd wilson_hop_element(int mu, int c1, int c2, cd u, double w)
+{
+  cd coef;
+  if (c1 == c2) coef = cmake(-0.5 * w, 0.0);
+  else if (mu == 0) coef = cmake(0.5, 0.0);
+  else if (mu == 2) coef = cmake(-0.5, 0.0);
+  else if (mu == 1) coef = (c1 == 0) ? cmake(0.0, -0.5) : cmake(0.0, 0.5);
+  else coef = (c1 == 0) ? cmake(0.0, 0.5) : cmake(0.0, -0.5);
+  return cmul(coef, u);
+}
+
+template <bool RESID>
+__global__ void __launch_bounds__(256) wilson_mf_kernel(const StencilKArgs a)
+{
+  constexpr int NC = 2;
+  const int bxi = (a.n_par == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int k = bxi * blockDim.x + threadIdx.x;
+  const int yi = blockIdx.y * blockDim.y + threadIdx.y;
+  const int y = a.y_off + yi * a.y_stride;
+  const int p = a.p_begin + ((a.n_par == 2) ? (blockIdx.x & 1) : 0);
+  if (!((k < a.g.xh) && (yi < a.y_cnt))) return;
+  const cd zero = cmake(0.0, 0.0);
+  const size_t V = 2 * (size_t)a.g.half;
+  const size_t site = (size_t)p * a.g.half + (size_t)y * a.g.xh + k;
+  const int q = 1 - p;
+  const int sft = (y + p) & 1;
+  int kxp = k + sft; kxp = (kxp == a.g.xh) ? 0 : kxp;
+  int kxm = k - 1 + sft; kxm = (kxm < 0) ? a.g.xh - 1 : kxm;
+  const int yp1 = (y + 1 == a.g.Y) ? 0 : y + 1;
+  const int ym1 = (y == 0) ? a.g.Y - 1 : y - 1;
+  const size_t qbase = (size_t)q * a.g.half;
+  const cd* in_q = a.in + qbase * NC;
+  const cd* s0 = in_q + ((size_t)y * a.g.xh + kxp) * NC;
+  const cd* s2 = in_q + ((size_t)y * a.g.xh + kxm) * NC;
+  const cd* s1 = (a.halo_yp != nullptr && y == a.g.Y - 1) ? a.halo_yp + ((size_t)q * a.g.xh + k) * NC : in_q + ((size_t)yp1 * a.g.xh + k) * NC;
+  const cd* s3 = (a.halo_ym != nullptr && y == 0) ? a.halo_ym + ((size_t)q * a.g.xh + k) * NC : in_q + ((size_t)ym1 * a.g.xh + k) * NC;
+  const cd* g2 = a.mf_gauge + qbase + (size_t)y * a.g.xh + kxm;
+  const cd* g3 = (a.mf_gauge_ym != nullptr && y == 0) ? a.mf_gauge_ym + ((size_t)q * a.g.xh + k) : a.mf_gauge + V + qbase + (size_t)ym1 * a.g.xh + k;
+
+  // every load ahead of the first product
+  cd u[4];
+  u[0] = ld_stream(a.mf_gauge + site);
+  u[1] = ld_stream(a.mf_gauge + V + site);
+  u[2] = ld_keep(g2);
+  u[3] = ld_keep(g3);
+  cd VC[2], VN[4][2];
+  ld256_keep(a.in + site * NC, VC[0], VC[1]);
+  ld256_keep(s0, VN[0][0], VN[0][1]);
+  ld256_keep(s1, VN[1][0], VN[1][1]);
+  ld256_keep(s2, VN[2][0], VN[2][1]);
+  ld256_keep(s3, VN[3][0], VN[3][1]);
+  cd OLD[2] = {zero, zero}, RB[2] = {zero, zero};
+  if (a.accumulate) { OLD[0] = a.out[site * NC]; OLD[1] = a.out[site * NC + 1]; }
+  if (RESID) ld256_stream(a.resid + site * NC, RB[0], RB[1]);
+  u[2] = cconj(u[2]);
+  u[3] = cconj(u[3]);
+
+  cd res[2];
+#pragma unroll
+  for (int c1 = 0; c1 < 2; c1++)
+  {
+    cd part[2];
+#pragma unroll
+    for (int c2 = 0; c2 < 2; c2++)
+    {
+      // the chain of the element kernel's lane (c1, c2): clover, diagonal shift, +x, +y, -x, -y
+      const cd CL = (c1 == c2) ? cmake(2.0 * a.mf_w, 0.0) : zero;
+      const cd DG = (a.use_diag && c1 == c2) ? a.diag[p][c2] : zero;
+      cd acc = zero;
+      cfma(acc, CL, VC[c2]);
+      cfma(acc, DG, VC[c2]);
+#pragma unroll
+      for (int mu = 0; mu < 4; mu++) cfma(acc, wilson_hop_element(mu, c1, c2, u[mu], a.mf_w), VN[mu][c2]);
+      part[c2] = acc;
+    }
+    cd r = cadd(part[0], part[1]);
+    r = cadd(r, OLD[c1]);
+    if (RESID) r = csub(RB[c1], r);
+    res[c1] = r;
+  }
+  st256(a.out + site * NC, res[0], res[1]);
+}
+
+static int launch_wilson_mf(const StencilKArgs& a, int n_par)
+{
+  const int row_threads = a.g.xh;
+  int bx = 256;
+  while (bx > 32 && bx / 2 >= row_threads) bx /= 2;
+  int by = 256 / bx;
+  if (by > a.y_cnt) by = a.y_cnt;
+  dim3 block(bx, by, 1);
+  dim3 grid(((row_threads + bx - 1) / bx) * n_par, (a.y_cnt + by - 1) / by, 1);
+  if (grid.y > 65535) return fail_msg("qmg_stencil_apply: Y too large for the launch grid");
+  if (a.resid != nullptr) wilson_mf_kernel<true><<<grid, block, 0, rt().stream>>>(a);
+  else wilson_mf_kernel<false><<<grid, block, 0, rt().stream>>>(a);
+  QMG_LAUNCH_CHECK();
   return 0;
 }
 
@@ -1252,6 +1383,7 @@ static int launch_stencil(const StencilKArgs& a, int n_par, bool reduce)
 
 static int dispatch_stencil(const StencilKArgs& a, int nc, int n_par, bool reduce)
 {
+  if (!reduce && a.mf_gauge != nullptr) return launch_wilson_mf(a, n_par);
   if (!reduce && a.herm && rt().tile_kernel)
   {
     // patch shapes: nc = 8: 8 x 4 sites (97 KB of shared memory, two CTAs per SM; 4x4, 8x2, 4x2 and 16x4 patches measured

@@ -244,6 +244,11 @@ class Stencil:
     def gamma5_hermitian(self, on=True):
         return int(self.be.fn("stencil_gamma5_hermitian")(self.h, 1 if on else 0))
 
+    def matrix_free(self, gauge=None, on=1):
+        """B200 extension (Wilson2D only): apply from the gauge links instead of the stored blocks, same bits.  on = 1 needs the gauge
+        array the operator was built from; 0 switches off, 2 / 3 pause / resume.  Returns 1 when active."""
+        return int(self.be.fn("stencil_matrix_free")(self.h, _c(carr(gauge)) if gauge is not None else None, int(on)))
+
     def eigs(self, type, nev, ncv=None, high=False, tol=1e-8, want_vectors=False):
         """B200 build only: nev extreme eigenpairs of the Hermitian operator `type` (arpack_dcn's Lanczos restatement)."""
         ncv = 3 * nev if ncv is None else ncv
@@ -457,6 +462,11 @@ class KCycle:
         """B200 extension: link-compressed applies on every level that passes the check (tile_levels_only: only on the levels
         with nc >= 4, where the shared-memory patch kernels make it faster); returns how many levels switched."""
         return int(self.be.fn("kcycle_gamma5_hermitian")(self.h, (2 if tile_levels_only else 1) if on else 0))
+
+    def matrix_free(self, on=True):
+        """B200 extension: pause / resume the matrix-free apply of the Wilson fine operator (set up at construction when
+        kcycle_setup_matrix_free(1) was in force); returns 1 when it is active afterwards."""
+        return int(self.be.fn("kcycle_matrix_free")(self.h, 1 if on else 0))
 
     def deflate_coarsest(self, num_low, num_high=0):
         """B200 build only: eigenpairs of the coarsest normal operator for the deflated coarsest solve; returns their eigenvalues."""

@@ -209,6 +209,26 @@ int CAPI(stencil_gamma5_hermitian)(void* h_, int on)
 #endif
 }
 
+// B200 extension: matrix-free apply of a Wilson2D operator from the gauge field `gauge` (host, 2 V links, the array the
+// operator was built from): on = 1 switch on (after the exact check of the stored blocks; returns 1 when active), 0 switch
+// off, 2 / 3 pause / resume without dropping the gauge copy.  Reference build and other operators: 0, nothing changes.
+int CAPI(stencil_matrix_free)(void* h_, const capi_cd* gauge, int on)
+{
+#ifdef QMG_B200_HOST
+  Stencil2D* s = ((capi::StencilH*)h_)->op;
+  Wilson2D* w = dynamic_cast<Wilson2D*>(s);
+  if (w == 0) return 0;
+  if (on == 0) { w->disable_matrix_free_apply(); return 0; }
+  if (on == 2) { w->pause_matrix_free_apply(true); return 0; }
+  if (on == 3) { w->pause_matrix_free_apply(false); return w->uses_matrix_free_apply() ? 1 : 0; }
+  if (gauge == 0) return 0;
+  capi::Stage g(gauge, 2L * s->lat->get_volume(), true, false);
+  return w->enable_matrix_free_apply((capi_cd*)g) ? 1 : 0;
+#else
+  (void)h_; (void)gauge; (void)on; return 0;
+#endif
+}
+
 // lhs = M_type rhs through the function-pointer wrappers apply_stencil_2D_* (stencil_2d.h:2571-2716)
 void CAPI(stencil_apply)(void* h_, int type, capi_cd* lhs, const capi_cd* rhs)
 {
@@ -710,6 +730,8 @@ struct KCycleH
 // B200 extension (see kcycle_setup_link_compressed below): switch every operator to its link-compressed apply as soon as it
 // exists, so that the null-vector solves of the set-up already run on clover / +x / +y blocks
 inline int& setup_link_compressed() { static int on = 0; return on; }
+// B200 extension (see kcycle_setup_matrix_free below): a Wilson fine operator applies matrix-free from the moment it is built
+inline int& setup_matrix_free() { static int on = 0; return on; }
 inline void maybe_link_compress(Stencil2D* s)
 {
 #ifdef QMG_B200_HOST
@@ -806,7 +828,14 @@ void* CAPI(kcycle_new)(int X, int Y, double mass, const capi_cd* gauge, const in
   {
     capi::Stage g(gauge, 2L * X * Y, true, false);
     if (staggered) h->op = new Staggered2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
-    else h->op = new Wilson2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
+    else
+    {
+      Wilson2D* w = new Wilson2D(h->lats[0], capi_cd(mass, 0.0), (capi_cd*)g);
+      h->op = w;
+#ifdef QMG_B200_HOST
+      if (capi::setup_matrix_free()) w->enable_matrix_free_apply((capi_cd*)g);
+#endif
+    }
   }
   h->coarsest = new StatefulMultigridMG::CoarsestSolveMG;
   h->coarsest->coarsest_stencil_app = (QMGStencilType)ip[13];
@@ -1070,6 +1099,28 @@ int CAPI(kcycle_setup_link_compressed)(int on)
   const int was = capi::setup_link_compressed();
   capi::setup_link_compressed() = on ? 1 : 0;
   return was;
+}
+// B200 extension: 1 = K-cycle objects built from now on apply their Wilson fine operator matrix-free (links instead of stored
+// blocks, same bits; Wilson2D::enable_matrix_free_apply) -- in the set-up's null-vector solves as well as in the solves.
+// Reference build: no-op.  Returns the previous setting.
+int CAPI(kcycle_setup_matrix_free)(int on)
+{
+  const int was = capi::setup_matrix_free();
+  capi::setup_matrix_free() = on ? 1 : 0;
+  return was;
+}
+// B200 extension: pause (on = 0) / resume (on = 1) the matrix-free apply of the fine operator of this K-cycle object; returns 1
+// when it is active afterwards.  Reference build: 0.
+int CAPI(kcycle_matrix_free)(void* h_, int on)
+{
+#ifdef QMG_B200_HOST
+  capi::KCycleH* h = (capi::KCycleH*)h_;
+  if (h->op == 0) return 0;
+  h->op->pause_matrix_free_apply(on == 0);
+  return h->op->uses_matrix_free_apply() ? 1 : 0;
+#else
+  (void)h_; (void)on; return 0;
+#endif
 }
 // B200 extension: link-compressed applies on every level of the hierarchy whose stored blocks obey the gamma5-hermitian
 // relation (checked per level); returns the number of levels switched.  Reference build: 0.

@@ -26,7 +26,8 @@ class StencilDesc(C.Structure):
                 ("clover", C.c_void_p), ("hopping", C.c_void_p),
                 ("shift", C.c_double * 2), ("eo_shift", C.c_double * 2), ("dof_shift", C.c_double * 2),
                 ("halo_ym", C.c_void_p), ("halo_yp", C.c_void_p),
-                ("gamma5_hermitian", C.c_int), ("hop_halo_ym", C.c_void_p)]
+                ("gamma5_hermitian", C.c_int), ("hop_halo_ym", C.c_void_p),
+                ("wilson_gauge", C.c_void_p), ("wilson_w", C.c_double), ("wilson_gauge_halo_ym", C.c_void_p)]
 
 
 class TransferDesc(C.Structure):
@@ -99,7 +100,7 @@ def to_device(a):
 
 
 def stencil_desc(X, Y, nc, clover=None, hopping=None, shift=0.0, eo_shift=0.0, dof_shift=0.0, halo_ym=None, halo_yp=None,
-                 gamma5_hermitian=False, hop_halo_ym=None):
+                 gamma5_hermitian=False, hop_halo_ym=None, wilson_gauge=None, wilson_w=1.0, wilson_gauge_halo_ym=None):
     d = StencilDesc()
     d.X, d.Y, d.nc = int(X), int(Y), int(nc)
     d.clover = clover.data_ptr() if clover is not None else None
@@ -112,8 +113,18 @@ def stencil_desc(X, Y, nc, clover=None, hopping=None, shift=0.0, eo_shift=0.0, d
     d.halo_yp = halo_yp.data_ptr() if halo_yp is not None else None
     d.gamma5_hermitian = 1 if gamma5_hermitian else 0
     d.hop_halo_ym = hop_halo_ym.data_ptr() if hop_halo_ym is not None else None
-    d._keep = (clover, hopping, halo_ym, halo_yp, hop_halo_ym)
+    d.wilson_gauge = wilson_gauge.data_ptr() if wilson_gauge is not None else None
+    d.wilson_w = float(wilson_w)
+    d.wilson_gauge_halo_ym = wilson_gauge_halo_ym.data_ptr() if wilson_gauge_halo_ym is not None else None
+    d._keep = (clover, hopping, halo_ym, halo_yp, hop_halo_ym, wilson_gauge, wilson_gauge_halo_ym)
     return d
+
+
+def wilson_mf_deviation(desc):
+    """sum |stored - regenerated|^2 of an nc = 2 set against the Wilson blocks of desc.wilson_gauge: 0.0 exactly licenses the matrix-free apply."""
+    out = (C.c_double * 2)()
+    check(lib().qmg_wilson_mf_deviation(C.byref(desc), out))
+    return out[0]
 
 
 def stencil_gamma5_deviation(desc):

@@ -452,6 +452,49 @@ def test_fused_kcycle_is_bit_identical(gpu, level_app, coarsest_app):
     kc.free()
 
 
+def test_wilson_matrix_free_operator_and_kcycle(ref, gpu):
+    """B200 extension on the host classes: Wilson2D::enable_matrix_free_apply checks the stored blocks, then every whole-operator
+    apply (apply_M, the residual epilogue of the K-cycle, the solvers' callbacks) reads the links -- same bits, so a K-cycle whose
+    fine operator applies matrix-free from the first null-vector solve on reproduces the stored-block hierarchy, iteration counts
+    and solution bit for bit (and the oracle's iteration count); an operator whose clover was edited (the n18 mutation) is refused."""
+    L = 64
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L * 2, 5)
+    lat = gpu.lattice(L, L, 2)
+    op = lat.wilson(-0.03, g)
+    want = [op.apply(b, t) for t in (0, 2)]
+    assert op.matrix_free(g) == 1
+    got = [op.apply(b, t) for t in (0, 2)]
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+    assert op.matrix_free(on=2) == 0 and op.matrix_free(on=3) == 1
+    op.add_to("clover", 1e-3 * latutil.gaussian_cv(4 * L * L, 2))
+    assert op.matrix_free(on=0) == 0 and op.matrix_free(g) == 0       # blocks no longer those of g: refused
+    op.free()
+
+    kr = capi.KCycle(ref, L, -0.03, g, n_refine=2, seed=5)
+    ir = kr.solve(b, tol=1e-10)
+    kr.free()
+    res = {}
+    for mf in (0, 1):
+        was = gpu.fn("kcycle_setup_matrix_free")(mf)
+        try:
+            kc = capi.KCycle(gpu, L, -0.03, g, n_refine=2, seed=5)
+        finally:
+            gpu.fn("kcycle_setup_matrix_free")(was)
+        assert kc.matrix_free(True) == mf
+        x, info = kc.solve(b, tol=1e-10, want_x=True)
+        res[mf] = (x, info, [kc.tracker(l) for l in range(3)])
+        if mf:
+            assert kc.matrix_free(False) == 0
+            x2, info2 = kc.solve(b, tol=1e-10, want_x=True)
+            assert np.array_equal(x2, x) and info2["iter"] == info["iter"]
+        kc.free()
+    (x0, i0, t0), (x1, i1, t1) = res[0], res[1]
+    assert i0["null_ops"] == i1["null_ops"] and i0["iter"] == i1["iter"] and t0 == t1
+    assert np.array_equal(x0, x1)
+    assert abs(i1["iter"] - ir["iter"]) <= 1
+
+
 def test_n19_schur_kcycle_parity(ref, gpu):
     """tests/n19_wilson_kcycle_precond: every level solved as the Schur system of the right-block-Jacobi operator,
     coarse stencils built from the rbjacobi fine stencil, outer tolerance 1e-8."""

@@ -336,6 +336,49 @@ def test_gamma5_hermitian_apply(ref, qmg_gpu):
     op.free()
 
 
+@pytest.mark.parametrize("X,Y", [(64, 64), (32, 96), (16, 8), (4, 2)])
+def test_wilson_matrix_free_apply_has_the_bits_of_the_stored_blocks(qmg_gpu, X, Y):
+    """B200 extension: the whole-operator Wilson apply from the gauge links (qmg_stencil_desc.wilson_gauge: 96 instead of 384
+    bytes per site) rebuilds the block elements with the fill's arithmetic and sums them in the element kernel's order -- plain,
+    accumulating, with shifts on parity and chirality, with the residual epilogue: np.array_equal with the stored-block apply.
+    Piece applies of the same descriptor keep reading the stored blocks; qmg_wilson_mf_deviation is 0 for untouched blocks and
+    positive as soon as one element is edited."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    w = 0.9
+    g = qmg.to_device(latutil.synthetic_gauge(X, Y, 6.0, 11))
+    cl, hp = qmg.fill_wilson(X, Y, g, w)
+    n = X * Y * 2
+    x, b = dev(qmg, latutil.gaussian_cv(n, 1)), dev(qmg, latutil.gaussian_cv(n, 2))
+    kw = dict(shift=-0.05 + 0.01j, eo_shift=0.02, dof_shift=0.003j)
+    stored = qmg.stencil_desc(X, Y, 2, cl, hp, **kw)
+    free = qmg.stencil_desc(X, Y, 2, cl, hp, wilson_gauge=g, wilson_w=w, **kw)
+    assert qmg.wilson_mf_deviation(free) == 0.0
+    launches = qmg.kernel_launches()
+    for pieces in (qmg.APPLY_ALL, qmg.APPLY_ALL | qmg.APPLY_ACCUMULATE, qmg.APPLY_ALL | qmg.APPLY_EVEN_ROWS_ONLY, qmg.APPLY_ALL | qmg.APPLY_ODD_ROWS_ONLY,
+                   qmg.APPLY_CLOVER | qmg.APPLY_SHIFT, qmg.APPLY_HOP_TO_EVEN | qmg.APPLY_HOP_TO_ODD):
+        want, got = dev(qmg, latutil.gaussian_cv(n, 3)), dev(qmg, latutil.gaussian_cv(n, 3))
+        qmg.stencil_apply(stored, want, x, pieces)
+        qmg.stencil_apply(free, got, x, pieces)
+        assert np.array_equal(host(got), host(want)), pieces
+    want, got = qmg.cvec(n), qmg.cvec(n)
+    qmg.check(lib.qmg_stencil_apply_residual(C.byref(stored), C.c_int(15), C.c_int(15), qmg.ptr(want), qmg.ptr(x), qmg.ptr(b)))
+    qmg.check(lib.qmg_stencil_apply_residual(C.byref(free), C.c_int(15), C.c_int(15), qmg.ptr(got), qmg.ptr(x), qmg.ptr(b)))
+    assert np.array_equal(host(got), host(want))
+    assert qmg.kernel_launches() > launches
+    # a single direction is a piece: stored blocks
+    want, got = qmg.cvec(n), qmg.cvec(n)
+    qmg.stencil_apply(stored, want, x, qmg.APPLY_ALL, 5)
+    qmg.stencil_apply(free, got, x, qmg.APPLY_ALL, 5)
+    assert np.array_equal(host(got), host(want))
+    # the licence is withdrawn by any edit of the blocks (tests/n18_rbjacobi_stencil_test mutates the clover), or by the wrong w
+    cl2 = cl.clone()
+    cl2[3] += 1e-13
+    assert qmg.wilson_mf_deviation(qmg.stencil_desc(X, Y, 2, cl2, hp, wilson_gauge=g, wilson_w=w)) > 0.0
+    assert qmg.wilson_mf_deviation(qmg.stencil_desc(X, Y, 2, cl, hp, wilson_gauge=g, wilson_w=1.0)) > 0.0
+
+
 def test_fused_krylov_step(qmg_gpu):
     """qmg_step_xr_norm (alpha formed on the device between two kernels, one host wait) == qmg_dot_norm + host alpha +
     qmg_update_xr_norm, bit for bit, including the MR aliasing p == r."""

@@ -127,6 +127,36 @@ def test_loopback_link_compressed_kcycle(qmg_gpu, loop):
     assert n0 == n1 == 3 and it0 == it1 and latutil.rel_l2(x1, x0) < 1e-9
 
 
+def test_loopback_matrix_free_wilson(qmg_gpu, loop):
+    """Matrix-free Wilson apply on a slab: row -1 of U_y comes from the lower rank (here: itself) -- the applies and a K-cycle
+    whose fine operator applies matrix-free have the bits of the periodic run."""
+    be = capi.Backend("gpu")
+    L = 64
+    g = latutil.load_gauge(L)
+    b = latutil.gaussian_cv(L * L * 2, 9)
+
+    def fn():
+        lat = be.lattice(L, L, 2)
+        op = lat.wilson(-0.03, g)
+        stored = op.apply(b, 0)
+        on = op.matrix_free(g)
+        free = op.apply(b, 0)
+        op.free()
+        was = be.fn("kcycle_setup_matrix_free")(1)
+        try:
+            kc = capi.KCycle(be, L, -0.03, g, n_refine=2, seed=5)
+        finally:
+            be.fn("kcycle_setup_matrix_free")(was)
+        active = kc.matrix_free(True)
+        x, info = kc.solve(b, tol=1e-10, want_x=True)
+        kc.free()
+        return on, active, stored, free, x, info["iter"]
+    (on0, ac0, s0, f0, x0, it0), (on1, ac1, s1, f1, x1, it1) = loop(fn)
+    assert on0 == on1 == 1 and ac0 == ac1 == 1
+    assert np.array_equal(f0, s0) and np.array_equal(f1, s1) and np.array_equal(f1, f0)
+    assert it0 == it1 and np.array_equal(x1, x0)
+
+
 def test_two_rank_kcycle():
     import torch
     if torch.cuda.device_count() < 2:
