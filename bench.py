@@ -332,7 +332,6 @@ def run_gpu(args):
     gauge = torch.polar(torch.ones_like(phases), phases)
     del phases
     clover, hopping = qmg.fill_wilson(X, Y, gauge)
-    del gauge
     rhs = qmg.cvec(n)
     qmg.check(lib.qmg_gaussian(qmg.ptr(rhs), C.c_long(n), C.c_uint64(7), C.c_uint64(rank), C.c_double(1.0)))
     lhs = qmg.cvec(n)
@@ -373,6 +372,35 @@ def run_gpu(args):
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = BYTES_PER_SITE * V * world / (ms_per_step * 1e-3) / 1e9
+
+    # beside the contract kernel: the opt-in matrix-free apply of the same operator (gauge links instead of stored blocks, 96 B per
+    # site, the same bits -- DESIGN.md K1); one GPU only (a slab needs row -1 of U_y from its neighbour, which the host classes fetch)
+    matrix_free = None
+    if world == 1:
+        try:
+            dmf = qmg.stencil_desc(X, Y, 2, clover, hopping, shift=-0.075, wilson_gauge=gauge, wilson_w=1.0)
+            if qmg.wilson_mf_deviation(dmf) == 0.0:
+                chk = qmg.cvec(n)
+                qmg.stencil_apply(dmf, chk, rhs)
+                same = bool(torch.equal(chk, lhs))
+                del chk
+                for _ in range(3):
+                    qmg.stencil_apply(dmf, lhs, rhs)
+                torch.cuda.synchronize()
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                m0.record()
+                for _ in range(args.steps):
+                    qmg.stencil_apply(dmf, lhs, rhs)
+                m1.record()
+                torch.cuda.synchronize()
+                mf_ms = m0.elapsed_time(m1) / args.steps
+                matrix_free = {"ms_per_apply": mf_ms, "bytes_per_site": 96.0, "GBps_on_its_bytes": 96.0 * V / (mf_ms * 1e-3) / 1e9,
+                               "speedup_vs_stored_blocks": ms_per_step / mf_ms, "output_bit_identical_to_stored_blocks": same,
+                               "kernel": "qmg::wilson_mf_tile_kernel<16, 8>", "opt_in": "Wilson2D::enable_matrix_free_apply / qmg_stencil_desc.wilson_gauge"}
+            del dmf
+        except Exception as exc:      # context only
+            matrix_free = {"error": repr(exc)[:200]}
+    del gauge
 
     # end to end: host rhs -> device, apply, device lhs -> host, through the C ABI
     e2e_steps = max(1, min(args.steps, 3))
@@ -531,6 +559,7 @@ def run_gpu(args):
                     "pcie_one_direction_at_a_time": pcie},
             "gpu_launches": launches,
             "clocks": clocks,
+            "wilson_matrix_free": matrix_free,
             "kcycle": kcycle,
             "kcycle_strong": kcycle_strong,
             "shard_parity": shard_parity,
