@@ -9,6 +9,7 @@
 #ifndef QMG_B200_TRANSFER
 #define QMG_B200_TRANSFER
 
+#include <cstdlib>
 #include <iostream>
 #include <complex>
 #include <vector>
@@ -36,6 +37,9 @@ private:
   QMGDoublingType doubling;
   bool is_init;
   qmg_transfer_desc desc;
+  // chirality-packed copy of the null vectors for prolong / restrict (see use_packed), built on first use
+  complex<double>* packed;
+  int packed_state;            // 0 not tried yet, 1 in use, -1 not applicable
 
 public:
   complex<double>** null_vectors;            // [coarse nc][fine size_cv], device
@@ -61,6 +65,26 @@ private:
   { QMG_CHK(qmg_prolong(&desc, reinterpret_cast<const qmg_cplx* const*>(vecs), nvec, qmg_host::P(coarse_cv), qmg_host::P(fine_cv))); }
   void restrict_f2c(complex<double>* fine_cv, complex<double>* coarse_cv, complex<double>** vecs, int nvec)
   { QMG_CHK(qmg_restrict(&desc, reinterpret_cast<const qmg_cplx* const*>(vecs), nvec, qmg_host::P(fine_cv), qmg_host::P(coarse_cv))); }
+
+  // B200 extension: with QMG_DOUBLE_PROJECTION null vector j carries the upper, j + nc/2 the lower chirality of one solve, so at
+  // every fine element half of the vectors are zero.  The first whole-set prolong / restrict packs the non-zero halves into one
+  // interleaved array (half the size of the set) after CHECKING that what it drops is exactly zero, and from then on the
+  // whole-set operations read that copy: 96 / 80 instead of 160 / 144 bytes per fine dof.  Writing through the public
+  // null_vectors pointers afterwards must be followed by drop_packed().  QMG_PACKED_TRANSFER=0 switches it off.
+  bool use_packed()
+  {
+    if (packed_state != 0) return packed_state > 0;
+    packed_state = -1;
+    const char* e = getenv("QMG_PACKED_TRANSFER");
+    if (e != 0 && e[0] == '0') return false;
+    if (!is_init || doubling != QMG_DOUBLE_PROJECTION || restrict_null_vectors != 0 || !qmg_transfer_packed_supported(&desc)) return false;
+    packed = allocate_vector<complex<double> >((long)fine_lat->get_size_cv() * (num_null_vec / 2));
+    double dropped = 1.0;
+    QMG_CHK(qmg_transfer_pack_chiral(&desc, reinterpret_cast<const qmg_cplx* const*>(null_vectors), num_null_vec, qmg_host::P(packed), &dropped));
+    if (dropped != 0.0) { deallocate_vector(&packed); return false; }
+    packed_state = 1;
+    return true;
+  }
 
   // one Gram-Schmidt pass over every aggregate (transfer.h:514-607); the factor is stored when block_cholesky != 0
   void block_orthonormalize()
@@ -133,7 +157,7 @@ public:
   TransferMG(Lattice2D* in_fine_lat, Lattice2D* in_coarse_lat, complex<double>** in_null_vectors, bool do_block_ortho = true,
              bool save_decomp = false, QMGDoublingType in_doubling = QMG_DOUBLE_NONE)
     : fine_lat(in_fine_lat), coarse_lat(in_coarse_lat), num_null_vec(in_coarse_lat->get_nc()), blocksizes(0), fine_sites_per_coarse(0),
-      doubling(in_doubling), is_init(false), null_vectors(0), restrict_null_vectors(0), block_cholesky(0), block_L(0), block_U(0)
+      doubling(in_doubling), is_init(false), packed(0), packed_state(0), null_vectors(0), restrict_null_vectors(0), block_cholesky(0), block_L(0), block_U(0)
   {
     if (!setup_geometry()) return;
     null_vectors = clone_vectors(in_null_vectors);
@@ -158,7 +182,7 @@ public:
   TransferMG(Lattice2D* in_fine_lat, Lattice2D* in_coarse_lat, complex<double>** in_prolong_null_vectors, complex<double>** in_restrict_null_vectors,
              bool do_block_bi_ortho = true, bool save_decomp = false, QMGDoublingType in_doubling = QMG_DOUBLE_NONE)
     : fine_lat(in_fine_lat), coarse_lat(in_coarse_lat), num_null_vec(in_coarse_lat->get_nc()), blocksizes(0), fine_sites_per_coarse(0),
-      doubling(in_doubling), is_init(false), null_vectors(0), restrict_null_vectors(0), block_cholesky(0), block_L(0), block_U(0)
+      doubling(in_doubling), is_init(false), packed(0), packed_state(0), null_vectors(0), restrict_null_vectors(0), block_cholesky(0), block_L(0), block_U(0)
   {
     if (!setup_geometry()) return;
     null_vectors = clone_vectors(in_prolong_null_vectors);
@@ -192,6 +216,7 @@ public:
       for (int i = 0; i < num_null_vec; i++) if (v[i] != 0) deallocate_vector(&v[i]);
       delete[] v;
     }
+    if (packed != 0) deallocate_vector(&packed);
     if (block_cholesky != 0) deallocate_vector(&block_cholesky);
     if (block_L != 0) deallocate_vector(&block_L);
     if (block_U != 0) deallocate_vector(&block_U);
@@ -199,14 +224,25 @@ public:
 
   bool is_initialized() { return is_init; }
   // fine += P coarse (accumulates, transfer.h:455)
-  void prolong_c2f(complex<double>* coarse_cv, complex<double>* fine_cv) { prolong_c2f(coarse_cv, fine_cv, null_vectors, num_null_vec); }
+  void prolong_c2f(complex<double>* coarse_cv, complex<double>* fine_cv)
+  {
+    if (use_packed()) QMG_CHK(qmg_prolong_packed(&desc, qmg_host::P(packed), qmg_host::P(coarse_cv), 0, qmg_host::P(fine_cv), 0));
+    else prolong_c2f(coarse_cv, fine_cv, null_vectors, num_null_vec);
+  }
   // coarse += R fine (accumulates, transfer.h:487)
   void restrict_f2c(complex<double>* fine_cv, complex<double>* coarse_cv)
-  { restrict_f2c(fine_cv, coarse_cv, restrict_null_vectors == 0 ? null_vectors : restrict_null_vectors, num_null_vec); }
+  {
+    if (use_packed()) QMG_CHK(qmg_restrict_packed(&desc, qmg_host::P(packed), qmg_host::P(fine_cv), qmg_host::P(coarse_cv), 0));
+    else restrict_f2c(fine_cv, coarse_cv, restrict_null_vectors == 0 ? null_vectors : restrict_null_vectors, num_null_vec);
+  }
+  // the packed copy is a snapshot of null_vectors: drop it after editing them through the public pointers
+  void drop_packed() { if (packed != 0) deallocate_vector(&packed); packed_state = 0; }
+  bool uses_packed_null_vectors() { return use_packed(); }
   // B200 extensions used by the K-cycle: the same sums in one pass each.
   // coarse = R fine, written outright (zero_vector + restrict_f2c)
   void restrict_f2c_overwrite(complex<double>* fine_cv, complex<double>* coarse_cv)
   {
+    if (use_packed()) { QMG_CHK(qmg_restrict_packed(&desc, qmg_host::P(packed), qmg_host::P(fine_cv), qmg_host::P(coarse_cv), 1)); return; }
     complex<double>** vecs = restrict_null_vectors == 0 ? null_vectors : restrict_null_vectors;
     QMG_CHK(qmg_restrict_overwrite(&desc, reinterpret_cast<const qmg_cplx* const*>(vecs), num_null_vec, qmg_host::P(fine_cv), qmg_host::P(coarse_cv)));
   }
@@ -214,6 +250,7 @@ public:
   bool can_fuse_prolong() const { return num_null_vec <= 8; }
   void prolong_c2f_add(complex<double>* coarse_cv, complex<double>* base_cv, complex<double>* fine_out)
   {
+    if (use_packed()) { QMG_CHK(qmg_prolong_packed(&desc, qmg_host::P(packed), qmg_host::P(coarse_cv), qmg_host::P(base_cv), qmg_host::P(fine_out), 1)); return; }
     QMG_CHK(qmg_prolong_add(&desc, reinterpret_cast<const qmg_cplx* const*>(null_vectors), num_null_vec, qmg_host::P(coarse_cv),
                             qmg_host::P(base_cv), qmg_host::P(fine_out)));
   }

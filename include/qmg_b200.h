@@ -335,6 +335,16 @@ int qmg_restrict_overwrite(const qmg_transfer_desc* t, const qmg_cplx* const* nu
  * one pass, the sum formed from zero first so the result is bit-identical; nvec <= 8; fine_out may alias base */
 int qmg_prolong_add(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec,
                     const qmg_cplx* coarse, const qmg_cplx* base, qmg_cplx* fine_out);
+/* Chirality-packed null vectors (B200 extension).  With QMG_DOUBLE_PROJECTION (every K-cycle of the reference) vector j holds the
+ * upper-chirality, vector j + ncc/2 the lower-chirality components of one solve: at a fine element of chirality h = (c >= ncf/2)
+ * only vectors [h ncc/2, (h+1) ncc/2) are non-zero.  pack_chiral writes packed[idx (ncc/2) + i] = nv[h ncc/2 + i][idx] (N_f ncc/2
+ * complex) and returns the sum of |nv|^2 over the entries it DROPS: the packed restrict / prolong (80 / 96 instead of 144 / 160 bytes
+ * per fine dof) may replace qmg_restrict / qmg_prolong(_add) only when that is exactly 0.  Same sums up to the order of the
+ * cross-lane additions of the restriction. */
+int qmg_transfer_packed_supported(const qmg_transfer_desc* t);
+int qmg_transfer_pack_chiral(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec, qmg_cplx* packed, double* dropped_norm2);
+int qmg_restrict_packed(const qmg_transfer_desc* t, const qmg_cplx* packed, const qmg_cplx* fine, qmg_cplx* coarse, int overwrite);
+int qmg_prolong_packed(const qmg_transfer_desc* t, const qmg_cplx* packed, const qmg_cplx* coarse, const qmg_cplx* base, qmg_cplx* fine_out, int use_base);
 /* one pass of per-aggregate Gram-Schmidt, in place (transfer.h:514-607);
  * cholesky: optional V_c*ncc*ncc output of the triangular factor (:555-594) or NULL */
 int qmg_block_orthonormalize(const qmg_transfer_desc* t, qmg_cplx* const* nullvecs_host, int nvec, qmg_cplx* cholesky);

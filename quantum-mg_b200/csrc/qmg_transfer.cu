@@ -187,6 +187,122 @@ __global__ void __launch_bounds__(256) prolong_kernel(const TGeom g, const VecPa
   fine[idx] = acc;
 }
 
+// ---- chirality-packed null vectors -----------------------------------------------------------------------------------------
+// With QMG_DOUBLE_PROJECTION (every K-cycle of the reference: tests/n13 :389, n16 :409, n19 :269, n22 :308) null vector j is the
+// upper-chirality projection and vector j + ncc/2 the lower one of the same solve: at a fine element of chirality h = (c >= ncf/2)
+// only the ncc/2 vectors [h ncc/2, (h + 1) ncc/2) can be non-zero, half of every prolong / restrict read is zeros.  The packed
+// copy keeps the non-zero half, interleaved -- packed[idx (ncc/2) + i] = nv[h ncc/2 + i][idx] -- so a fine element's coefficients
+// are ONE contiguous 16 (ncc/2)-byte run: prolong 160 -> 96, restrict 144 -> 80 bytes per fine dof.  qmg_transfer_pack_chiral
+// builds it and returns the sum of |nv|^2 over the entries it drops: the caller may use the packed kernels only if that is 0.
+template <int NVH>
+__global__ void __launch_bounds__(256) pack_chiral_kernel(long nf, int ncf, VecPack<2 * NVH> nv, cd* __restrict__ packed, double* partials, unsigned int* counter, double* result)
+{
+  __shared__ double smem[8];
+  double acc[1] = {0.0};
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < nf; idx += stride)
+  {
+    const int h = ((int)(idx % ncf) >= ncf / 2) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < NVH; i++)
+    {
+      const cd keep = h ? nv.p[NVH + i][idx] : nv.p[i][idx];
+      const cd drop = h ? nv.p[i][idx] : nv.p[NVH + i][idx];
+      packed[idx * NVH + i] = keep;
+      acc[0] += drop.x * drop.x + drop.y * drop.y;
+    }
+  }
+  grid_reduce_finish<1>(acc, smem, partials, counter, result);
+}
+
+// G = seg lanes per aggregate, lane j walking down the 2 by (row, parity) segments of its aggregate (element j of each): its
+// dof index c = j % ncf, hence its chirality, never changes, so it accumulates the NVH sums of ITS half; the lanes of one
+// chirality then add up over every lane bit but the chirality bit, and lanes 0 / (ncf/2) write the two halves of the coarse site.
+template <int NVH>
+__global__ void __launch_bounds__(256) restrict_packed_kernel(const TGeom g, const cd* __restrict__ packed, const cd* __restrict__ fine,
+                                                              cd* __restrict__ coarse, const int G, const int logG, const int overwrite)
+{
+  const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long agg = gt >> logG;
+  const int lane_in = (int)(gt & (G - 1));
+  const bool live = agg < g.Vc;
+  const int yc = live ? (int)(agg / g.Xc) : 0, xc = live ? (int)(agg - (long)yc * g.Xc) : 0;
+  cd acc[NVH];
+#pragma unroll
+  for (int i = 0; i < NVH; i++) acc[i] = cmake(0.0, 0.0);
+  if (live)
+  {
+    int e = lane_in;
+    for (; e + G < g.fspc; e += 2 * G)
+    {
+      const long i0 = agg_elem_index(g, xc, yc, e), i1 = agg_elem_index(g, xc, yc, e + G);
+      const cd f0 = __ldg(fine + i0), f1 = __ldg(fine + i1);
+      cd n0[NVH], n1[NVH];
+#pragma unroll
+      for (int i = 0; i < NVH; i++) { n0[i] = ld_stream(packed + i0 * NVH + i); n1[i] = ld_stream(packed + i1 * NVH + i); }
+#pragma unroll
+      for (int i = 0; i < NVH; i++) { cfma_conj(acc[i], n0[i], f0); cfma_conj(acc[i], n1[i], f1); }
+    }
+    for (; e < g.fspc; e += G)
+    {
+      const long idx = agg_elem_index(g, xc, yc, e);
+      const cd f = __ldg(fine + idx);
+#pragma unroll
+      for (int i = 0; i < NVH; i++) cfma_conj(acc[i], ld_stream(packed + idx * NVH + i), f);
+    }
+  }
+  const int cb = g.ncf / 2;       // the lane bit that tells the chirality
+  for (int off = G >> 1; off >= 1; off >>= 1)
+  {
+    if (off == cb) continue;
+#pragma unroll
+    for (int i = 0; i < NVH; i++) acc[i] = cadd(acc[i], shfl_xor_c(acc[i], off));
+  }
+  if (live && (lane_in & ~cb) == 0)
+  {
+    const int h = (lane_in & cb) ? 1 : 0;
+    cd* dst = coarse + coarse_index(g, xc, yc) * g.ncc + h * NVH;
+#pragma unroll
+    for (int i = 0; i < NVH; i++) dst[i] = overwrite ? acc[i] : cadd(dst[i], acc[i]);
+  }
+}
+
+// fine element per thread: fine_out = (use_base ? base (or 0) : fine) + sum_i packed[idx][i] coarse[aggregate][h NVH + i]
+template <int NVH>
+__global__ void __launch_bounds__(256) prolong_packed_kernel(const TGeom g, const cd* __restrict__ packed, const cd* __restrict__ coarse,
+                                                             cd* __restrict__ fine, const cd* __restrict__ base, const int use_base)
+{
+  const int rowlen = g.xhf * g.ncf;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= rowlen) return;
+  const int y = blockIdx.y, p = blockIdx.z;
+  const int k = col / g.ncf, c = col - k * g.ncf;
+  const int x = 2 * k + ((y + p) & 1);
+  const long ci = coarse_index(g, x / g.bx, y / g.by);
+  const long idx = ((long)(y + p * g.Yf) * g.xhf) * g.ncf + col;
+  const int h = (c >= g.ncf / 2) ? 1 : 0;
+  cd acc = use_base ? cmake(0.0, 0.0) : fine[idx];
+  const cd* cv = coarse + ci * g.ncc + h * NVH;
+  cd n[NVH];
+#pragma unroll
+  for (int i = 0; i < NVH; i++) n[i] = ld_stream(packed + idx * NVH + i);
+#pragma unroll
+  for (int i = 0; i < NVH; i++) cfma(acc, n[i], __ldg(cv + i));
+  if (use_base && base != nullptr) acc = cadd(base[idx], acc);
+  fine[idx] = acc;
+}
+
+// shapes the packed kernels cover: symmetric chirality split (ncf, ncc even), NVH = ncc / 2 in {1, 2, 4, 8}, even blocks whose
+// (row, parity) segments are a power of two <= 32 lanes and a multiple of ncf
+static bool packed_shape_ok(const TGeom& g)
+{
+  const int nvh = g.ncc / 2;
+  if ((g.ncf & 1) || (g.ncc & 1) || !(nvh == 1 || nvh == 2 || nvh == 4 || nvh == 8)) return false;
+  if (!g.even_bx || g.seg > 32 || (g.seg & (g.seg - 1)) != 0 || g.seg % g.ncf != 0) return false;
+  if ((g.ncf & (g.ncf - 1)) != 0) return false;
+  return true;
+}
+
 template <int NV>
 static int launch_restrict(const TGeom& g, const qmg_cplx* const* vecs, int count, int v0, const qmg_cplx* fine, qmg_cplx* coarse, int overwrite = 0)
 {
@@ -472,6 +588,67 @@ int qmg_prolong_add(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_
   if (nvec > 2) return launch_prolong<4>(g, nullvecs_host, nvec, 0, coarse, fine_out, base, 1);
   if (nvec == 2) return launch_prolong<2>(g, nullvecs_host, nvec, 0, coarse, fine_out, base, 1);
   return launch_prolong<1>(g, nullvecs_host, nvec, 0, coarse, fine_out, base, 1);
+}
+
+// 1 when qmg_transfer_pack_chiral / qmg_restrict_packed / qmg_prolong_packed cover this transfer's shape
+int qmg_transfer_packed_supported(const qmg_transfer_desc* t)
+{
+  TGeom g;
+  if (make_geom(t, g, "qmg_transfer_packed_supported")) return 0;
+  return packed_shape_ok(g) ? 1 : 0;
+}
+
+int qmg_transfer_pack_chiral(const qmg_transfer_desc* t, const qmg_cplx* const* nullvecs_host, int nvec, qmg_cplx* packed, double* dropped_norm2)
+{
+  QMG_REQUIRE_INIT();
+  TGeom g; int rc = make_geom(t, g, "qmg_transfer_pack_chiral"); if (rc) return rc;
+  if (nvec != g.ncc || !packed_shape_ok(g)) return fail_msg("qmg_transfer_pack_chiral: shape not covered (see qmg_transfer_packed_supported)");
+  const long nf = (long)g.Xf * g.Yf * g.ncf;
+  Runtime& r = rt();
+  long want = (nf + 255) / 256, cap = (long)r.sm_count * 8;
+  const int grid = (int)(want < cap ? want : cap);
+#define QMG_PACK(H) case H: { VecPack<2 * H> pk; for (int v = 0; v < 2 * H; v++) pk.p[v] = reinterpret_cast<const cd*>(nullvecs_host[v]); \
+      pack_chiral_kernel<H><<<grid, 256, 0, r.stream>>>(nf, g.ncf, pk, reinterpret_cast<cd*>(packed), r.d_partials, r.d_counter, r.d_result); break; }
+  switch (g.ncc / 2) { QMG_PACK(1) QMG_PACK(2) QMG_PACK(4) QMG_PACK(8) default: break; }
+#undef QMG_PACK
+  QMG_LAUNCH_CHECK();
+  return fetch_result(dropped_norm2, 1);
+}
+
+// coarse (+)= P^dag fine from the packed copy; overwrite != 0: coarse = P^dag fine
+int qmg_restrict_packed(const qmg_transfer_desc* t, const qmg_cplx* packed, const qmg_cplx* fine, qmg_cplx* coarse, int overwrite)
+{
+  QMG_REQUIRE_INIT();
+  TGeom g; int rc = make_geom(t, g, "qmg_restrict_packed"); if (rc) return rc;
+  if (!packed_shape_ok(g)) return fail_msg("qmg_restrict_packed: shape not covered (see qmg_transfer_packed_supported)");
+  int G = 1, logG = 0;
+  while (G < g.seg) { G <<= 1; logG++; }
+  const long threads = g.Vc * G;
+  const long blocks = (threads + 255) / 256;
+  if (blocks > 0x7fffffffL) return fail_msg("restrict: lattice too large for the launch grid");
+#define QMG_RP(H) case H: restrict_packed_kernel<H><<<(unsigned)blocks, 256, 0, rt().stream>>>(g, reinterpret_cast<const cd*>(packed), \
+      reinterpret_cast<const cd*>(fine), reinterpret_cast<cd*>(coarse), G, logG, overwrite); break;
+  switch (g.ncc / 2) { QMG_RP(1) QMG_RP(2) QMG_RP(4) QMG_RP(8) default: break; }
+#undef QMG_RP
+  QMG_LAUNCH_CHECK();
+  return 0;
+}
+
+// use_base == 0: fine_out += P coarse;  else fine_out = base + P coarse (base NULL: P coarse), the sum formed from zero first
+int qmg_prolong_packed(const qmg_transfer_desc* t, const qmg_cplx* packed, const qmg_cplx* coarse, const qmg_cplx* base, qmg_cplx* fine_out, int use_base)
+{
+  QMG_REQUIRE_INIT();
+  TGeom g; int rc = make_geom(t, g, "qmg_prolong_packed"); if (rc) return rc;
+  if (!packed_shape_ok(g)) return fail_msg("qmg_prolong_packed: shape not covered (see qmg_transfer_packed_supported)");
+  const int rowlen = g.xhf * g.ncf;
+  dim3 grid((rowlen + 255) / 256, g.Yf, 2);
+  if (g.Yf > 65535) return fail_msg("prolong: Y too large for the launch grid");
+#define QMG_PP(H) case H: prolong_packed_kernel<H><<<grid, 256, 0, rt().stream>>>(g, reinterpret_cast<const cd*>(packed), reinterpret_cast<const cd*>(coarse), \
+      reinterpret_cast<cd*>(fine_out), reinterpret_cast<const cd*>(base), use_base); break;
+  switch (g.ncc / 2) { QMG_PP(1) QMG_PP(2) QMG_PP(4) QMG_PP(8) default: break; }
+#undef QMG_PP
+  QMG_LAUNCH_CHECK();
+  return 0;
 }
 
 int qmg_block_orthonormalize(const qmg_transfer_desc* t, qmg_cplx* const* nullvecs_host, int nvec, qmg_cplx* cholesky)

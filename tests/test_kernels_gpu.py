@@ -379,6 +379,66 @@ def test_wilson_matrix_free_apply_has_the_bits_of_the_stored_blocks(qmg_gpu, X, 
     assert qmg.wilson_mf_deviation(qmg.stencil_desc(X, Y, 2, cl, hp, wilson_gauge=g, wilson_w=1.0)) > 0.0
 
 
+@pytest.mark.parametrize("case", [(16, 16, 2, 4, 4, 8), (16, 16, 8, 4, 4, 8), (8, 8, 4, 2, 2, 4), (32, 16, 2, 8, 4, 2), (16, 32, 2, 8, 8, 8)])
+def test_chirality_packed_transfer(qmg_gpu, case):
+    """B200 extension: with chirality-doubled null vectors (vector j upper, j + ncc/2 lower components) the packed copy keeps the
+    non-zero half of every fine element; restrict / prolong from it against the unpacked kernels (the restriction adds its lanes
+    up in another order: 1e-14; the prolongation drops exact zeros only), the accumulate / overwrite / base flavours, and the
+    refusal: vectors that are not chirally split report what packing would drop."""
+    import ctypes as C
+    qmg = qmg_gpu
+    lib = qmg.lib()
+    Xf, Yf, ncf, Xc, Yc, ncc = case
+    nf, ncv, nvh = Xf * Yf * ncf, Xc * Yc * ncc, ncc // 2
+    t = qmg.TransferDesc(Xf, Yf, ncf, Xc, Yc, ncc)
+    assert lib.qmg_transfer_packed_supported(C.byref(t)) == 1
+    comp = np.arange(nf) % ncf
+    vecs = []
+    for v in range(ncc):
+        a = latutil.gaussian_cv(nf, 300 + v)
+        a[(comp >= ncf // 2) != (v >= nvh)] = 0.0       # vector v lives on the chirality half v // nvh
+        vecs.append(dev(qmg, a))
+    PP = C.c_void_p * ncc
+    ptrs = PP(*[qmg.ptr(v) for v in vecs])
+    packed = qmg.cvec(nf * nvh)
+    dropped = C.c_double(-1.0)
+    qmg.check(lib.qmg_transfer_pack_chiral(C.byref(t), ptrs, C.c_int(ncc), qmg.ptr(packed), C.byref(dropped)))
+    assert dropped.value == 0.0
+    fine, coarse, base = dev(qmg, latutil.gaussian_cv(nf, 1)), dev(qmg, latutil.gaussian_cv(ncv, 2)), dev(qmg, latutil.gaussian_cv(nf, 3))
+    # restrict: overwrite and accumulate
+    want, got = qmg.cvec(ncv), dev(qmg, latutil.gaussian_cv(ncv, 9))
+    qmg.check(lib.qmg_restrict_overwrite(C.byref(t), ptrs, C.c_int(ncc), qmg.ptr(fine), qmg.ptr(want)))
+    qmg.check(lib.qmg_restrict_packed(C.byref(t), qmg.ptr(packed), qmg.ptr(fine), qmg.ptr(got), C.c_int(1)))
+    assert latutil.rel_l2(host(got), host(want)) < 1e-14
+    want, got = dev(qmg, latutil.gaussian_cv(ncv, 9)), dev(qmg, latutil.gaussian_cv(ncv, 9))
+    qmg.check(lib.qmg_restrict(C.byref(t), ptrs, C.c_int(ncc), qmg.ptr(fine), qmg.ptr(want)))
+    qmg.check(lib.qmg_restrict_packed(C.byref(t), qmg.ptr(packed), qmg.ptr(fine), qmg.ptr(got), C.c_int(0)))
+    assert latutil.rel_l2(host(got), host(want)) < 1e-14
+    # zero + accumulate == overwrite, bit for bit (the fused K-cycle relies on it)
+    z = qmg.cvec(ncv)
+    qmg.check(lib.qmg_restrict_packed(C.byref(t), qmg.ptr(packed), qmg.ptr(fine), qmg.ptr(z), C.c_int(0)))
+    o = dev(qmg, latutil.gaussian_cv(ncv, 9))
+    qmg.check(lib.qmg_restrict_packed(C.byref(t), qmg.ptr(packed), qmg.ptr(fine), qmg.ptr(o), C.c_int(1)))
+    assert np.array_equal(host(z), host(o))
+    # prolong: accumulate, base, no base
+    want, got = dev(qmg, latutil.gaussian_cv(nf, 4)), dev(qmg, latutil.gaussian_cv(nf, 4))
+    qmg.check(lib.qmg_prolong(C.byref(t), ptrs, C.c_int(ncc), qmg.ptr(coarse), qmg.ptr(want)))
+    qmg.check(lib.qmg_prolong_packed(C.byref(t), qmg.ptr(packed), qmg.ptr(coarse), None, qmg.ptr(got), C.c_int(0)))
+    assert latutil.rel_l2(host(got), host(want)) < 1e-15
+    for b in (base, None):
+        want, got = qmg.cvec(nf), qmg.cvec(nf)
+        qmg.check(lib.qmg_prolong_add(C.byref(t), ptrs, C.c_int(ncc), qmg.ptr(coarse), qmg.ptr(b) if b is not None else None, qmg.ptr(want)))
+        qmg.check(lib.qmg_prolong_packed(C.byref(t), qmg.ptr(packed), qmg.ptr(coarse), qmg.ptr(b) if b is not None else None, qmg.ptr(got), C.c_int(1)))
+        assert latutil.rel_l2(host(got), host(want)) < 1e-15
+    # not chirally split: packing says how much it would drop
+    vecs[0][1 if ncf == 2 else ncf // 2] = 1e-9
+    qmg.check(lib.qmg_transfer_pack_chiral(C.byref(t), ptrs, C.c_int(ncc), qmg.ptr(packed), C.byref(dropped)))
+    assert dropped.value > 0.0
+    # odd blocks are not covered
+    t_odd = qmg.TransferDesc(12, 12, 2, 4, 4, 8)
+    assert lib.qmg_transfer_packed_supported(C.byref(t_odd)) == 0
+
+
 def test_fused_krylov_step(qmg_gpu):
     """qmg_step_xr_norm (alpha formed on the device between two kernels, one host wait) == qmg_dot_norm + host alpha +
     qmg_update_xr_norm, bit for bit, including the MR aliasing p == r."""
