@@ -60,6 +60,43 @@ inline inversion_info minres_core(complex<double>* phi, complex<double>* phi0, i
   bool converged = false;
   bool acc_done = false;
   complex<double>* acc = (hints != 0) ? hints->accumulate_into : 0;
+
+  // MR(2) from a zero start in two passes (see qmg_mr2_gram): q1 = A r0, p2 = A q1, one pass of dot products, one update.
+  // Taken only where the two-step loop below would run both steps anyway (a tolerance the first step cannot meet).
+  if (zero_start && max_iter == 2 && (flags & SOLVE_TWO_STEP_MR) && (flags & SOLVE_LAST_X_ONLY) && (flags & SOLVE_NO_FINAL_RESIDUAL))
+  {
+    typedef complex<double> cplx;
+    complex<double>* q1 = p;
+    complex<double>* p2 = allocate_vector<complex<double> >(size);
+    matrix_vector(q1, const_cast<complex<double>*>(phi0), extra_info);
+    matrix_vector(p2, q1, extra_info);
+    double g[9];
+    QMG_CHK(qmg_mr2_gram(P(phi0), P(q1), P(p2), size, g));
+    const cplx a(g[0], g[1]), c(g[3], g[4]), d(g[5], g[6]);
+    const double b = g[2], e = g[7], f = g[8];
+    const cplx a1 = omega * a / b;
+    const double r1sq = f - 2.0 * std::real(std::conj(a1) * a) + std::norm(a1) * b;
+    const cplx q2r1 = a - a1 * b - std::conj(a1) * c + std::norm(a1) * d;
+    const double q2q2 = b - 2.0 * std::real(std::conj(a1) * d) + std::norm(a1) * e;
+    const bool usable = (b > 0.0) && (q2q2 > 0.0) && !(r1sq < eps * eps * f);
+    if (usable)
+    {
+      const cplx a2 = omega * q2r1 / q2q2;
+      const cplx cx0 = a1 + a2, cx1 = -a1 * a2, cr1 = -(a1 + a2), cr2 = a1 * a2;
+      const double vx0[2] = { cx0.real(), cx0.imag() }, vx1[2] = { cx1.real(), cx1.imag() }, vr1[2] = { cr1.real(), cr1.imag() }, vr2[2] = { cr2.real(), cr2.imag() };
+      QMG_CHK(qmg_mr2_update(vx0, vx1, vr1, vr2, P(phi0), P(q1), P(p2), acc != 0 ? P(acc) : 0, P(acc != 0 ? acc : phi), rout != 0 ? P(rout) : 0, size));
+      deallocate_vector(&p2);
+      invif.ops_count += 3;        // what the reference counts: two iterations and the final residual (A.0 was counted above)
+      invif.iter = 2; invif.success = false; invif.resSq = r1sq;
+      say(verb, VERB_SUMMARY, "MR", "", true, invif.success, invif.iter, invif.ops_count, sqrt(invif.resSq / f));
+      hints->executed += 2;
+      if (rout != 0) hints->residual_valid = true; else deallocate_vector(&r);
+      deallocate_vector(&p);
+      return invif;
+    }
+    deallocate_vector(&p2);      // (a breakdown, or a first step that already meets the tolerance: the step-by-step loop decides)
+  }
+
   if (!zero_start && (max_iter <= 0 || sqrt(rsq) < eps * bsqrt)) converged = (sqrt(rsq) < eps * bsqrt);
   else for (k = 1; k <= max_iter; k++)
   {

@@ -27,6 +27,8 @@ enum
   SOLVE_ZERO_START = 1,          // x is zero by contract and its content is NOT read: r0 = b without applying A to zero
   SOLVE_NO_FINAL_RESIDUAL = 2,   // do not recompute |b - A x| at exit (resSq then holds the recursive value)
   SOLVE_LAST_X_ONLY = 4,         // smoother: the last permitted iteration updates x only (its residual is never read)
+  SOLVE_TWO_STEP_MR = 8,         // MR with exactly two iterations from a zero start may run in its two-pass form (A applied to A r0
+                                 // instead of to r1, both step lengths from one pass of dot products): same iterates up to rounding
 };
 // (SolveHints::residual_out, MR only: the solver's own residual vector at exit -- b - A x by the recurrence r -= alpha A r --
 //  is left there for the caller, who then does not have to apply A to x to get it.  With SOLVE_LAST_X_ONLY the last step

@@ -98,6 +98,7 @@ protected:
   complex<double>** coarsest_evecs;
   bool fused_cycle;
   bool residual_handover;
+  bool two_step_mr;          // QMG_MR2=0: MR(2) smoothers step by step even when residual_handover allows the two-pass form
 
   static void check_level_solve(LevelSolveMG* s, const char* where)
   {
@@ -121,6 +122,8 @@ public:
     fused_cycle = !(e != 0 && e[0] == '0');
     const char* e2 = getenv("QMG_RESIDUAL_HANDOVER");
     residual_handover = !(e2 != 0 && e2[0] == '0');
+    const char* e3 = getenv("QMG_MR2");
+    two_step_mr = !(e3 != 0 && e3[0] == '0');
     qmg_host::overwriting_precond() = mg_preconditioner;    // writes every element of its output: the solvers need not zero it
   }
   ~StatefulMultigridMG()
@@ -281,7 +284,9 @@ public:
   // (7 -> 6 at the BASELINE settings).  The two residuals are the same vector up to rounding (two MR steps from a zero start),
   // so this is the one shortcut that is NOT bit-identical: 0 keeps the explicit residual and with it the bits of the unfused cycle.
   // The same switch lets the post-smoother answer a flexible solver's request for A lhs (A lhs = rhs - r2', r2' its recurrence
-  // residual; inverters/generic_gcr.h PrecondAzRequest): the Krylov apply after each K-cycle application goes too (6 -> 5).
+  // residual; inverters/generic_gcr.h PrecondAzRequest): the Krylov apply after each K-cycle application goes too (6 -> 5), and
+  // lets MR(2) smoothers run in their two-pass form (SOLVE_TWO_STEP_MR, inverters/generic_minres.h): 20 instead of 30 vector
+  // passes of BLAS-1 per K-cycle application and one host wait per smoother instead of two.
   void set_residual_handover(bool on) { residual_handover = on; }
   bool get_residual_handover() { return residual_handover; }
   void shift_all_to_nullvec(int i) { if (tracker_ok(i, "shift to null vectors")) dslash_tracker_list[i]->shift_all_to_nullvec(); }
@@ -403,7 +408,7 @@ public:
     matrix_op_cplx coarse_op = Stencil2D::get_apply_function(ctype);
     const int nc_solve = (int)(ctype == QMG_MATVEC_RIGHT_SCHUR ? nc / 2 : nc);
     // the smoother shortcuts: zero start, no unread residual; its last step may skip r only when the tolerance cannot stop it earlier anyway
-    const int smooth_flags = SOLVE_ZERO_START | SOLVE_NO_FINAL_RESIDUAL | SOLVE_LAST_X_ONLY;
+    const int smooth_flags = SOLVE_ZERO_START | SOLVE_NO_FINAL_RESIDUAL | SOLVE_LAST_X_ONLY | ((mg->residual_handover && mg->two_step_mr) ? qmg_host::SOLVE_TWO_STEP_MR : 0);
 
     // 1. pre-smooth: z1 ~ A^-1 rhs, r1 = rhs - A z1
     complex<double>* z1 = fpool->check_out();

@@ -275,6 +275,13 @@ int qmg_gcr_orthogonalize(const qmg_cplx* const* Ap_host, const qmg_cplx* const*
 int qmg_multi_axpy(const double* a_host, const qmg_cplx* const* xs_host, int k, qmg_cplx* y, long n);
 /* y = x0 + sum_j a_j xs[j]   (GCR: p_k = r + sum beta_i p_i without a separate copy); x0 == y allowed */
 int qmg_multi_axpyz(const double* a_host, const qmg_cplx* const* xs_host, int k, const qmg_cplx* x0, qmg_cplx* y, long n);
+/* Two MR steps from a zero start (the K-cycle's smoother, /root/reference/multigrid/stateful_multigrid.h:860,1046) in two vector
+ * passes: with q1 = A r0 and p2 = A q1 (instead of A r1 = q1 - a1 p2) both step lengths follow from one pass of dot products,
+ * out9 = { <q1|r0> (re, im), <q1|q1>, <p2|r0> (re, im), <p2|q1> (re, im), <p2|p2>, <r0|r0> }, and x, r2 from one update:
+ * x_out = (acc ? acc : 0) + cx0 r0 + cx1 q1 ; r_out = r0 + cr1 q1 + cr2 p2 (r_out NULL: not formed; may alias r0). */
+int qmg_mr2_gram(const qmg_cplx* r0, const qmg_cplx* q1, const qmg_cplx* p2, long n, double* out9);
+int qmg_mr2_update(const double* cx0, const double* cx1, const double* cr1, const double* cr2, const qmg_cplx* r0, const qmg_cplx* q1, const qmg_cplx* p2,
+                   const qmg_cplx* acc, qmg_cplx* x_out, qmg_cplx* r_out, long n);
 /* BiCGstab(L) sweeps (quantum-linalg minv_vector_bicgstab_l as the K-cycle set-up calls it,
  * /root/reference/tests/n13_wilson_kcycle/wilson_kcycle.cpp:359) with the BLAS-1 traffic of a sweep cut from 280 to 148 vector
  * passes; every element sees the floating-point operations of the call-by-call sequence in the same order.  L <= qmg_bicgstab_max_l().

@@ -675,6 +675,59 @@ int qmg_krylov_step(double omega, const qmg_cplx* p_, const qmg_cplx* q_, const 
 
 } // extern "C"
 
+// ------------------------------------------------------- two MR steps from a zero start in two passes --
+// The K-cycle's smoother is MR(2) from a zero start: r1 = r0 - a1 A r0, x = a1 r0 + a2 r1, r2 = r1 - a2 A r1.  Applying A to
+// q1 = A r0 instead of to r1 (A r1 = q1 - a1 A q1: the same number of applies) leaves nothing between the two applies, and both
+// step lengths follow from ONE pass of dot products over r0, q1 = A r0, p2 = A q1:
+//   a1 = w <q1|r0> / <q1|q1> ;  <q2|r1> = <q1|r0> - a1 <q1|q1> - conj(a1) <p2|r0> + |a1|^2 <p2|q1> ;
+//   <q2|q2> = <q1|q1> - 2 Re(conj(a1) <p2|q1>) + |a1|^2 <p2|p2> ;  a2 = w <q2|r1> / <q2|q2>
+//   x = (a1 + a2) r0 - a1 a2 q1 ;  r2 = r0 - (a1 + a2) q1 + a1 a2 p2
+// -- 3 + 5 vector passes and one host wait instead of 13 passes and two.  The iterates are those of MR(2) up to rounding.
+extern "C" {
+
+// out9 = { Re<q1|r0>, Im<q1|r0>, <q1|q1>, Re<p2|r0>, Im<p2|r0>, Re<p2|q1>, Im<p2|q1>, <p2|p2>, <r0|r0> }   (<x|y> = sum conj(x) y)
+int qmg_mr2_gram(const qmg_cplx* r0_, const qmg_cplx* q1_, const qmg_cplx* p2_, long n, double* out9)
+{
+  QMG_REQUIRE_INIT();
+  if (n <= 0) return fail_msg("qmg_mr2_gram: empty vector");
+  const cd* r0 = CCD(r0_); const cd* q1 = CCD(q1_); const cd* p2 = CCD(p2_);
+  return launch_reduce<9>(n, [=] __device__(long i, double (&acc)[9]) {
+    const cd r = r0[i], q = q1[i], p = p2[i];
+    acc[0] += q.x * r.x + q.y * r.y; acc[1] += q.x * r.y - q.y * r.x;
+    acc[2] += q.x * q.x + q.y * q.y;
+    acc[3] += p.x * r.x + p.y * r.y; acc[4] += p.x * r.y - p.y * r.x;
+    acc[5] += p.x * q.x + p.y * q.y; acc[6] += p.x * q.y - p.y * q.x;
+    acc[7] += p.x * p.x + p.y * p.y;
+    acc[8] += r.x * r.x + r.y * r.y;
+  }, out9);
+}
+
+// x_out = (acc ? acc : 0) + cx0 r0 + cx1 q1 ;  r_out = r0 + cr1 q1 + cr2 p2 (if r_out != NULL; may alias r0).  Coefficients: 2 doubles each.
+int qmg_mr2_update(const double* cx0, const double* cx1, const double* cr1, const double* cr2, const qmg_cplx* r0_, const qmg_cplx* q1_, const qmg_cplx* p2_,
+                   const qmg_cplx* acc_, qmg_cplx* x_out_, qmg_cplx* r_out_, long n)
+{
+  QMG_REQUIRE_INIT();
+  if (n <= 0) return fail_msg("qmg_mr2_update: empty vector");
+  const cd* r0 = CCD(r0_); const cd* q1 = CCD(q1_); const cd* p2 = CCD(p2_); const cd* accv = CCD(acc_); cd* x = CD(x_out_); cd* rr = CD(r_out_);
+  const cd a0 = cmake(cx0[0], cx0[1]), a1 = cmake(cx1[0], cx1[1]), b1 = cmake(cr1[0], cr1[1]), b2 = cmake(cr2[0], cr2[1]);
+  return launch_ew(n, [=] __device__(long i) {
+    const cd r = r0[i], q = q1[i];
+    cd xi = cmul(a0, r);
+    cfma(xi, a1, q);
+    if (accv != nullptr) xi = cadd(accv[i], xi);
+    x[i] = xi;
+    if (rr != nullptr)
+    {
+      cd t = r;
+      cfma(t, b1, q);
+      cfma(t, b2, p2[i]);
+      rr[i] = t;
+    }
+  });
+}
+
+} // extern "C"
+
 // ------------------------------------------------------- BiCGstab(L) sweeps with their vector traffic cut in half --
 // One sweep of BiCGstab(L) as the reference's set-up runs it (tests/n13_wilson_kcycle/wilson_kcycle.cpp:359, L = 6) is 2 L
 // operator applies and, written call by call, 280 vector reads / writes of BLAS-1 -- twice the bytes of the applies on the
