@@ -492,6 +492,10 @@ def run_gpu(args):
             kcycle["seconds"], kcycle["setup_seconds"], kcycle["precond_apply_s"] = (float(v) for v in t.tolist())
             kcycle["comm"] = qmg.comm_counters()
         if world == 1 and args.cpu_kcycle_L > 0 and not args.no_cpu:
+            # hand the big leg's 150 GB of parked blocks back first: the small leg's set-up would otherwise time the driver's frees
+            lib.qmg_trim()
+            torch.cuda.empty_cache()
+            torch.cuda.synchronize()
             kcycle_same = kcycle_run("gpu", args.cpu_kcycle_L)
     # strong scaling of the solve: the SAME kcycle_L x kcycle_L lattice (a stack of N independently drawn slabs) on N GPUs;
     # its N = 1 point is the `kcycle` leg above

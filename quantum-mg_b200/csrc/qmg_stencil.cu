@@ -1345,7 +1345,10 @@ template <int TK, int TY, bool RESID>
 __global__ void __launch_bounds__(TK * TY * 2, 4) wilson_mf_tile_kernel(const StencilKArgs a)
 {
   constexpr int NC = 2, VK = TK + 2, UK = TK + 1, NT = TK * TY * 2;
-  __shared__ __align__(32) cd sV[(TY + 2) * 2 * VK * NC];      // [ry = row + 1][parity][kk = k - k0 + 1][c]
+  // the two spinor components sit in planes of their own: consecutive threads then touch consecutive 16-byte words (as [..][c]
+  // pairs every access was a two-way bank conflict: 94 M conflicts in 227 M wavefronts, L1 at 87 %, profiles/r06l_ncu_...)
+  constexpr int PLANE = (TY + 2) * 2 * VK;
+  __shared__ __align__(16) cd sV[2 * PLANE];                    // [c][ry = row + 1][parity][kk = k - k0 + 1]
   __shared__ __align__(16) cd sUx[TY * 2 * UK];                // [row][parity][kk = k - k0 + 1]  (kk = 0: the column to the left)
   __shared__ __align__(16) cd sUy[(TY + 1) * 2 * TK];          // [ry = row + 1][parity][k - k0]  (ry = 0: the row below)
   const int tid = threadIdx.x;
@@ -1380,7 +1383,7 @@ __global__ void __launch_bounds__(TK * TY * 2, 4) wilson_mf_tile_kernel(const St
     {
       const int side = j & 1, pp = (j >> 1) & 1, r = j >> 2;
       ld256_keep(a.in + ((size_t)pp * half + (size_t)(y0 + r) * xh + (side ? kr : kl)) * NC, h0, h1);
-      hdst = sV + (((r + 1) * 2 + pp) * VK + (side ? TK + 1 : 0)) * NC; hpair = true;
+      hdst = sV + ((r + 1) * 2 + pp) * VK + (side ? TK + 1 : 0); hpair = true;
     }
     else if ((j -= N_VCOL) < N_VROW)
     {
@@ -1389,7 +1392,7 @@ __global__ void __launch_bounds__(TK * TY * 2, 4) wilson_mf_tile_kernel(const St
       if (top) src = halo_t ? a.halo_yp + ((size_t)pp * xh + k0 + kk) * NC : a.in + ((size_t)pp * half + (size_t)yt * xh + k0 + kk) * NC;
       else src = halo_b ? a.halo_ym + ((size_t)pp * xh + k0 + kk) * NC : a.in + ((size_t)pp * half + (size_t)yb * xh + k0 + kk) * NC;
       ld256_keep(src, h0, h1);
-      hdst = sV + (((top ? TY + 1 : 0) * 2 + pp) * VK + kk + 1) * NC; hpair = true;
+      hdst = sV + ((top ? TY + 1 : 0) * 2 + pp) * VK + kk + 1; hpair = true;
     }
     else if ((j -= N_VROW) < N_UX)
     {
@@ -1405,11 +1408,11 @@ __global__ void __launch_bounds__(TK * TY * 2, 4) wilson_mf_tile_kernel(const St
     }
   }
   {
-    cd* d = sV + (((ty + 1) * 2 + p) * VK + tk + 1) * NC;
-    d[0] = v0; d[1] = v1;
+    cd* d = sV + ((ty + 1) * 2 + p) * VK + tk + 1;
+    d[0] = v0; d[PLANE] = v1;
     sUx[(ty * 2 + p) * UK + tk + 1] = ux;
     sUy[((ty + 1) * 2 + p) * TK + tk] = uy;
-    if (hdst != nullptr) { hdst[0] = h0; if (hpair) hdst[1] = h1; }
+    if (hdst != nullptr) { hdst[0] = h0; if (hpair) hdst[PLANE] = h1; }
   }
   __syncthreads();
 
@@ -1431,17 +1434,17 @@ __global__ void __launch_bounds__(TK * TY * 2, 4) wilson_mf_tile_kernel(const St
       cfma(t, DG, vc);
       acc[c1][c2] = t;
     }
-  const cd* rowq = sV + ((ty + 1) * 2 + q) * VK * NC;
+  const cd* rowq = sV + ((ty + 1) * 2 + q) * VK;
 #pragma unroll
   for (int mu = 0; mu < 4; mu++)
   {
     cd um;
     const cd* vn;
-    if (mu == 0) { um = ux; vn = rowq + (tk + 1 + sft) * NC; }                                                        // (q, y, k + sft)
-    else if (mu == 1) { um = uy; vn = sV + (((ty + 2) * 2 + q) * VK + tk + 1) * NC; }                                  // (q, y + 1, k)
-    else if (mu == 2) { um = cconj(sUx[(ty * 2 + q) * UK + tk + sft]); vn = rowq + (tk + sft) * NC; }                  // (q, y, k - 1 + sft) and its U_x
-    else { um = cconj(sUy[(ty * 2 + q) * TK + tk]); vn = sV + ((ty * 2 + q) * VK + tk + 1) * NC; }                     // (q, y - 1, k) and its U_y
-    const cd n0 = vn[0], n1 = vn[1];
+    if (mu == 0) { um = ux; vn = rowq + (tk + 1 + sft); }                                                        // (q, y, k + sft)
+    else if (mu == 1) { um = uy; vn = sV + ((ty + 2) * 2 + q) * VK + tk + 1; }                                  // (q, y + 1, k)
+    else if (mu == 2) { um = cconj(sUx[(ty * 2 + q) * UK + tk + sft]); vn = rowq + (tk + sft); }                  // (q, y, k - 1 + sft) and its U_x
+    else { um = cconj(sUy[(ty * 2 + q) * TK + tk]); vn = sV + (ty * 2 + q) * VK + tk + 1; }                     // (q, y - 1, k) and its U_y
+    const cd n0 = vn[0], n1 = vn[PLANE];
 #pragma unroll
     for (int c1 = 0; c1 < 2; c1++)
     {
