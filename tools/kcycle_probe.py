@@ -27,6 +27,7 @@ ap.add_argument("--restart", type=int, default=32)
 ap.add_argument("--seed", type=int, default=1337)
 ap.add_argument("--hermitian", action="store_true", help="link-compressed (gamma5-hermitian) applies on every level that qualifies")
 ap.add_argument("--hermitian-setup", action="store_true", dest="hermitian_setup", help="link-compressed applies already during the set-up (null-vector solves)")
+ap.add_argument("--matrix-free", action="store_true", dest="matrix_free", help="Wilson fine operator applies matrix-free (gauge links instead of stored blocks)")
 ap.add_argument("--unfused", action="store_true", help="the reference's sweep-for-sweep K-cycle (round-1 behaviour) instead of the fused one")
 args = ap.parse_args()
 if args.backend == "gpu":
@@ -35,6 +36,8 @@ if args.backend == "gpu":
 be = capi.Backend(args.backend)
 if args.backend == "gpu" and args.hermitian_setup:
     be.fn("kcycle_setup_link_compressed")(1)
+if args.backend == "gpu" and args.matrix_free:
+    be.fn("kcycle_setup_matrix_free")(1)
 for L in args.sizes:
     t0 = time.perf_counter()
     g = latutil.synthetic_gauge(L, L, 6.0, args.seed, slab=True)
