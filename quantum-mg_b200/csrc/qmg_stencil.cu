@@ -1468,7 +1468,7 @@ static int wilson_mf_tile_mode() { static int v = -1; if (v < 0) { const char* e
 
 static int launch_wilson_mf(const StencilKArgs& a, int n_par)
 {
-  constexpr int MTK = 16, MTY = 8;
+  constexpr int MTK = 16, MTY = 8;      // (apply_sharded cuts a slab into bands of this height)
   if (wilson_mf_tile_mode() && n_par == 2 && a.y_stride == 1 && a.g.xh % MTK == 0 && a.y_cnt % MTY == 0 && a.y_cnt / MTY <= 65535)
   {
     dim3 grid(a.g.xh / MTK, a.y_cnt / MTY, 1);
@@ -1597,6 +1597,20 @@ static int apply_sharded(StencilKArgs& a, int nc, int n_par)
     a.y_off = 0; a.y_stride = 1; a.y_cnt = TY8;
     rc = dispatch_stencil(a, nc, n_par, false); if (rc) return rc;
     a.y_off = a.g.Y - TY8;
+    return dispatch_stencil(a, nc, n_par, false);
+  }
+  // matrix-free Wilson set: whole patches of the patch kernel inside, one patch-high band at either end once the rows have arrived
+  constexpr int MFY = 8, MFK = 16;
+  if (a.mf_gauge != nullptr && n_par == 2 && a.g.xh % MFK == 0 && a.g.Y % MFY == 0 && a.g.Y >= 3 * MFY)
+  {
+    StencilKArgs in = a;
+    in.y_off = MFY; in.y_stride = 1; in.y_cnt = a.g.Y - 2 * MFY;
+    rc = dispatch_stencil(in, nc, n_par, false); if (rc) return rc;
+    rc = halo_exchange_end(); if (rc) return rc;
+    a.halo_ym = rows.ym; a.halo_yp = rows.yp;
+    a.y_off = 0; a.y_stride = 1; a.y_cnt = MFY;
+    rc = dispatch_stencil(a, nc, n_par, false); if (rc) return rc;
+    a.y_off = a.g.Y - MFY;
     return dispatch_stencil(a, nc, n_par, false);
   }
   if (a.g.Y > 2)
