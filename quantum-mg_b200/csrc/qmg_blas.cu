@@ -848,11 +848,11 @@ int qmg_bicgstab_mgs(int L, qmg_cplx* const* r_host, long n, double* sums_host)
   QMG_REQUIRE_INIT();
   if (L < 1 || L > kBicgMaxL) return fail_msg("qmg_bicgstab_mgs: 1 <= L <= 7");
   if (n <= 0) return fail_msg("qmg_bicgstab_mgs: empty vector");
-  static double* table[64] = { nullptr };
-  const int dev = rt().device & 63;
-  if (table[dev] == nullptr) QMG_CUDA(cudaMalloc(&table[dev], sizeof(double) * kBicgMaxL * kMgsStride));
-  double* tab = table[dev];
-  int rc = 0;
+  // the table of the passes' sums: a block of the caching allocator (returned below; the stream orders its next use after this one)
+  void* tab_v = nullptr;
+  int rc = qmg_malloc(&tab_v, sizeof(double) * kBicgMaxL * kMgsStride);
+  if (rc) return rc;
+  double* tab = static_cast<double*>(tab_v);
   for (int i = 0; i < L && rc == 0; i++)
   {
     // pass i: r_i (i >= 1) is subtracted from r_{i+1} .. r_L, then the sums of r_{i+1}
@@ -864,9 +864,11 @@ int qmg_bicgstab_mgs(int L, qmg_cplx* const* r_host, long n, double* sums_host)
     switch (M) { QMG_MGS(1) QMG_MGS(2) QMG_MGS(3) QMG_MGS(4) QMG_MGS(5) QMG_MGS(6) QMG_MGS(7) default: break; }
 #undef QMG_MGS
   }
-  if (rc) return rc;
-  QMG_CUDA(cudaMemcpyAsync(sums_host, tab, sizeof(double) * L * kMgsStride, cudaMemcpyDeviceToHost, rt().stream));
-  QMG_CUDA(cudaStreamSynchronize(rt().stream));
+  if (rc) { qmg_free(tab_v); return rc; }
+  cudaError_t ce = cudaMemcpyAsync(sums_host, tab, sizeof(double) * L * kMgsStride, cudaMemcpyDeviceToHost, rt().stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(rt().stream);
+  qmg_free(tab_v);
+  if (ce != cudaSuccess) return fail_msg(cudaGetErrorString(ce));
   return 0;
 }
 
